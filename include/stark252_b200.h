@@ -1,0 +1,181 @@
+/*
+ * stark252_b200.h -- C ABI of the B200-native LDE + commitment path of the lambdaworks Cairo prover.
+ *
+ * The reference (lambdaclass/lambdaworks_cairo_prover) has no FFI on this path: the seam is a set of
+ * Rust generic functions.  Every entry point below names the reference
+ * function it replaces (paths relative to the reference root); INTEGRATION.md shows the Rust
+ * `extern "C"` block and the call-site changes a maintainer would make.
+ *
+ * Conventions
+ *   - Field elements cross the boundary in the reference's in-memory format ("LW"): 4 x u64,
+ *     limbs[0] MOST significant, Montgomery form (R = 2^256), fully reduced -- i.e. a Rust
+ *     `&[FieldElement<Stark252PrimeField>]` can be passed as is (zero-copy on the host side).
+ *   - Commitments / Merkle nodes are 32-byte Keccak-256 digests.
+ *   - `mem` says where caller buffers live: S252_HOST (pageable or pinned host memory; copies are
+ *     issued by the library) or S252_DEVICE (already resident in this GPU's HBM).
+ *   - Every function returns S252_OK or a negative error code and never throws/panics across the
+ *     boundary; s252_last_error() returns a message for the last failure on that context.
+ *     The reference returns Result<_, FFTError> / Option and unwraps at the call sites
+ *     (prover.rs:184,260,267; trace.rs:109; fri_commitment.rs:37; prover.rs:383-384).
+ *   - Products of a commit stay resident on the GPU (the reference keeps Round1/Round2 alive until
+ *     the proof is assembled, prover.rs:45-69) behind opaque handles freed by *_destroy.
+ *   - A context owns one CUDA stream; calls on one context are serialised by the caller (the
+ *     prover thread).  Use one context per thread for concurrent fine-grained calls (the
+ *     reference calls evaluate_offset_fft from rayon workers, prover.rs:169-183).
+ *   - There is no CPU fallback: without a CUDA device s252_ctx_create fails with S252_ERR_CUDA.
+ */
+#ifndef STARK252_B200_H
+#define STARK252_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define S252_OK 0
+#define S252_ERR_INVALID -1      /* bad argument (the reference's FFTError::InputError / debug_assert) */
+#define S252_ERR_CUDA -2         /* CUDA runtime failure, or no device */
+#define S252_ERR_NOT_FOUND -3    /* grinding: no nonce in range (reference: None -> expect panic) */
+#define S252_ERR_RANGE -4        /* position out of range (reference: get_proof_by_pos -> None) */
+
+#define S252_HOST 0
+#define S252_DEVICE 1
+
+typedef struct s252_ctx s252_ctx;
+typedef struct s252_commit s252_commit;          /* coefficients + LDE columns + batched Merkle tree */
+typedef struct s252_fri s252_fri;                /* all FRI layers: evaluations + Merkle trees */
+typedef struct s252_transcript s252_transcript;  /* DefaultTranscript (host) */
+
+/* LW element: FieldElement<Stark252PrimeField> as laid out by lambdaworks-math */
+typedef struct { uint64_t limbs[4]; } s252_fe;
+
+/* ---- context ---------------------------------------------------------------------------- */
+int s252_ctx_create(int device, s252_ctx **out);
+void s252_ctx_destroy(s252_ctx *ctx);
+const char *s252_last_error(const s252_ctx *ctx);
+/* Block until everything issued on the context's stream has finished. */
+int s252_ctx_synchronize(s252_ctx *ctx);
+/* The context's CUDA stream as a cudaStream_t (for event timing by the caller). */
+void *s252_ctx_stream(s252_ctx *ctx);
+/* Number of kernels this library has launched on the context since creation. */
+uint64_t s252_ctx_launch_count(const s252_ctx *ctx);
+/* Device allocation helpers for callers that want S252_DEVICE buffers without another runtime. */
+int s252_device_alloc(s252_ctx *ctx, size_t bytes, void **out);
+int s252_device_free(s252_ctx *ctx, void *ptr);
+int s252_copy_to_device(s252_ctx *ctx, void *dst, const void *src, size_t bytes);
+int s252_copy_to_host(s252_ctx *ctx, void *dst, const void *src, size_t bytes);
+
+/* ---- FFTPoly: fine-grained entry points ------------------------------------------------ */
+/* Polynomial::interpolate_fft(evals)                       -- call site src/starks/trace.rs:107
+ * n must be a power of two; writes n coefficients (trailing zeros are NOT trimmed). */
+int s252_interpolate_fft(s252_ctx *ctx, const s252_fe *evals, size_t n, s252_fe *coeffs, int mem);
+/* Polynomial::interpolate_offset_fft(evals, offset)        -- src/starks/constraints/evaluation_table.rs:32 */
+int s252_interpolate_offset_fft(s252_ctx *ctx, const s252_fe *evals, size_t n, const s252_fe *offset,
+                                s252_fe *coeffs, int mem);
+/* Length evaluate_offset_fft will produce: max(coeff_len, domain_size).next_power_of_two() * blowup,
+ * with coeff_len = n_coeffs (pass the trimmed length, as Polynomial::new trims). domain_size 0 = None. */
+size_t s252_evaluate_offset_fft_len(size_t n_coeffs, size_t blowup, size_t domain_size);
+/* p.evaluate_offset_fft(blowup, domain_size, offset)       -- src/starks/prover.rs:117,
+ * src/starks/fri/fri_commitment.rs:36.  out[i] = p(offset * w_len^i), natural order. */
+int s252_evaluate_offset_fft(s252_ctx *ctx, const s252_fe *coeffs, size_t n_coeffs, size_t blowup,
+                             size_t domain_size, const s252_fe *offset, s252_fe *out, size_t out_capacity, int mem);
+/* evaluate_polynomial_on_lde_domain(p, blowup, domain_size, offset) -- src/starks/prover.rs:106-123
+ * (incl. the step rule); writes domain_size*blowup elements. */
+int s252_evaluate_polynomial_on_lde_domain(s252_ctx *ctx, const s252_fe *coeffs, size_t n_coeffs, size_t blowup,
+                                           size_t domain_size, const s252_fe *offset, s252_fe *out, int mem);
+
+/* ---- round 1 / round 2 commits ------------------------------------------------------------ */
+/* interpolate_and_commit(trace, domain, transcript)         -- src/starks/prover.rs:126-159
+ * trace: row-major n_rows x n_cols (TraceTable.table, src/starks/trace.rs:9-13).
+ * Does compute_trace_polys (trace.rs:104), compute_lde_trace_evaluations (prover.rs:161-185) and
+ * batch_commit (prover.rs:96-104); the caller appends `root` to its transcript (prover.rs:151). */
+int s252_interpolate_and_commit(s252_ctx *ctx, const s252_fe *trace, size_t n_rows, size_t n_cols, size_t blowup,
+                                uint64_t coset_offset, int mem, s252_commit **out, uint8_t root[32]);
+/* Round 2 (src/starks/prover.rs:254-276): evaluate_polynomial_on_lde_domain for each of n_polys
+ * polynomials (polys: n_polys x n_coeffs, polynomial-major; n_coeffs <= domain_size) and
+ * batch_commit over the zipped rows. */
+int s252_lde_and_commit(s252_ctx *ctx, const s252_fe *polys, size_t n_coeffs, size_t n_polys, size_t domain_size,
+                        size_t blowup, uint64_t coset_offset, int mem, s252_commit **out, uint8_t root[32]);
+/* BatchedMerkleTree::build(rows) / FriMerkleTree::build(evals) -- src/starks/prover.rs:101,
+ * src/starks/fri/fri_commitment.rs:39.  rows: row-major n_rows x n_cols; n_rows a power of two. */
+int s252_merkle_build(s252_ctx *ctx, const s252_fe *rows, size_t n_rows, size_t n_cols, int mem, s252_commit **out,
+                      uint8_t root[32]);
+void s252_commit_destroy(s252_commit *c);
+size_t s252_commit_n_cols(const s252_commit *c);
+size_t s252_commit_n_rows(const s252_commit *c);       /* rows of the committed (LDE) table */
+size_t s252_commit_n_coeffs(const s252_commit *c);     /* coefficients kept per column (0 if none) */
+/* tree.root */
+int s252_commit_root(const s252_commit *c, uint8_t root[32]);
+/* Copy out LDE column `col`, rows [first, first+count)       -- reads of lde_trace, prover.rs:243 */
+int s252_commit_read_lde(s252_commit *c, size_t col, size_t first, size_t count, s252_fe *out);
+/* Copy out the coefficients of column `col`                 -- reads of trace_polys, prover.rs:314,360 */
+int s252_commit_read_coeffs(s252_commit *c, size_t col, s252_fe *out);
+/* Copy out Merkle nodes [first, first+count) of the heap array (root = node 0, leaf i = n-1+i). */
+int s252_commit_read_nodes(s252_commit *c, size_t first, size_t count, uint8_t *out);
+/* open_deep_composition_poly's reads (src/starks/prover.rs:484-529): for each of n_idx row indices,
+ * rows_out[q*n_cols + j] = LDE value and paths_out[(q*depth + k)*32..] = tree.get_proof_by_pos(idx)
+ * merkle_path entry k (leaf -> root), depth = log2(n_rows).  Either output may be NULL. */
+int s252_commit_open(s252_commit *c, const uint64_t *indices, size_t n_idx, s252_fe *rows_out, uint8_t *paths_out);
+/* Raw device pointers (column-major, library-internal element format) for fusing
+ * later prover stages on the GPU. */
+const void *s252_commit_device_lde(const s252_commit *c);
+const void *s252_commit_device_coeffs(const s252_commit *c);
+const void *s252_commit_device_nodes(const s252_commit *c);
+
+/* ---- FRI ------------------------------------------------------------------------------------- */
+/* fri_commit_phase(number_layers, p_0, transcript, coset_offset, domain_size)
+ *                                                           -- src/starks/fri/mod.rs:20-72
+ * p0: n_coeffs coefficients (n_coeffs <= domain_size).  Appends every layer root, samples every
+ * zeta and appends the last value through `transcript`, exactly in the reference's order.
+ * roots_out: number_layers x 32 bytes (may be NULL). */
+int s252_fri_commit_phase(s252_ctx *ctx, size_t number_layers, const s252_fe *p0, size_t n_coeffs,
+                          s252_transcript *transcript, const s252_fe *coset_offset, size_t domain_size, int mem,
+                          s252_fri **out, s252_fe *last_value, uint8_t *roots_out);
+void s252_fri_destroy(s252_fri *f);
+size_t s252_fri_n_layers(const s252_fri *f);
+/* FriLayer.evaluation[first..first+count) of layer k */
+int s252_fri_read_layer(s252_fri *f, size_t layer, size_t first, size_t count, s252_fe *out);
+int s252_fri_read_nodes(s252_fri *f, size_t layer, size_t first, size_t count, uint8_t *out);
+/* fri_query_phase's reads (src/starks/fri/mod.rs:74-127) for the given iotas: per query q and layer k
+ * (size_k = domain_size >> k): evals[q*L+k] = evaluation[iota % size_k],
+ * evals_sym[q*L+k] = evaluation[(iota + size_k/2) % size_k] and their auth paths, each padded to
+ * `path_stride` digests (use log2(domain_size)); path k has log2(size_k) entries. */
+int s252_fri_query(s252_fri *f, const uint64_t *iotas, size_t n_queries, s252_fe *evals, s252_fe *evals_sym,
+                   uint8_t *paths, uint8_t *paths_sym, size_t path_stride);
+
+/* ---- grinding --------------------------------------------------------------------------------- */
+/* generate_nonce_with_grinding(challenge, grinding_factor)  -- src/starks/grinding.rs:40-48
+ * Returns the SMALLEST nonce; S252_ERR_NOT_FOUND if none below `limit` (0 = 2^64-1). */
+int s252_generate_nonce_with_grinding(s252_ctx *ctx, const uint8_t challenge[32], uint8_t grinding_factor,
+                                      uint64_t limit, uint64_t *nonce);
+
+/* ---- transcript (host) -------------------------------------------------------------------------- */
+/* DefaultTranscript (lambdaworks-crypto) and the helpers of src/starks/transcript.rs:13-51 */
+s252_transcript *s252_transcript_new(void);
+void s252_transcript_free(s252_transcript *t);
+void s252_transcript_append(s252_transcript *t, const uint8_t *data, size_t len);
+void s252_transcript_challenge(s252_transcript *t, uint8_t out[32]);
+void s252_transcript_to_field(s252_transcript *t, s252_fe *out);
+uint64_t s252_transcript_to_usize(s252_transcript *t);
+
+/* ---- diagnostics ----------------------------------------------------------------------------- */
+/* Integer-pipe peak micro-benchmarks on this device (the roofline denominators that are not in
+ * MEASURED_PEAKS.json): results in Gops/s of 32-bit lane-operations.
+ * out[0] = IMAD.WIDE.U32 (independent mad.wide chains), out[1] = LOP3, out[2] = SHF (funnel shift),
+ * out[3] = IADD3 with carry, out[4] = IMAD.WIDE and LOP3 interleaved 1:1 (sum of both). */
+int s252_microbench_int_pipes(s252_ctx *ctx, double out[5]);
+/* Montgomery multiplications per second (Gmul/s) of fe_mul in a register-resident loop. */
+int s252_microbench_fe_mul(s252_ctx *ctx, double *gmuls);
+/* Keccak-f[1600] permutations per second (Gperm/s), register-resident. */
+int s252_microbench_keccak(s252_ctx *ctx, double *gperms);
+/* Element-wise field ops on device buffers of LW elements, for parity tests:
+ * op 0: a*b, 1: a+b, 2: a-b, 3: a^-1 (b ignored). */
+int s252_fe_binop(s252_ctx *ctx, int op, const s252_fe *a, const s252_fe *b, s252_fe *out, size_t n, int mem);
+/* Keccak256 of n messages of msg_len bytes each (host buffers), through the device Keccak. */
+int s252_keccak256_batch(s252_ctx *ctx, const uint8_t *msgs, size_t msg_len, size_t n, uint8_t *digests);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,78 @@
+// keccak.cuh -- Keccak-f[1600] / Keccak-256 (0x01 padding, rate 136) on the integer pipes.
+// The reference hashes with the sha3 crate's Keccak256 (Cargo.toml:17): Merkle leaves and nodes
+// (src/starks/config.rs:10-20), the Fiat-Shamir transcript and grinding (src/starks/grinding.rs).
+// One thread per hash; the 25 lanes stay in registers (50 x u32), rotations are funnel shifts,
+// chi is one LOP3 per 32-bit half.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace s252 {
+
+__constant__ uint64_t KECCAK_RC[24] = {
+    0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL,
+    0x000000000000808bULL, 0x0000000080000001ULL, 0x8000000080008081ULL, 0x8000000000008009ULL,
+    0x000000000000008aULL, 0x0000000000000088ULL, 0x0000000080008009ULL, 0x000000008000000aULL,
+    0x000000008000808bULL, 0x800000000000008bULL, 0x8000000000008089ULL, 0x8000000000008003ULL,
+    0x8000000000008002ULL, 0x8000000000000080ULL, 0x000000000000800aULL, 0x800000008000000aULL,
+    0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
+
+__device__ __forceinline__ uint64_t rol64(uint64_t x, int n) {
+    // n is a compile-time constant at every call site
+    uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+    if (n == 0) return x;
+    if (n == 32) return ((uint64_t)lo << 32) | hi;
+    uint32_t rlo, rhi;
+    if (n < 32) {
+        rlo = __funnelshift_l(hi, lo, n);
+        rhi = __funnelshift_l(lo, hi, n);
+    } else {
+        rlo = __funnelshift_l(lo, hi, n - 32);
+        rhi = __funnelshift_l(hi, lo, n - 32);
+    }
+    return ((uint64_t)rhi << 32) | rlo;
+}
+__device__ __forceinline__ uint64_t xor5(uint64_t a, uint64_t b, uint64_t c, uint64_t d, uint64_t e) {
+    return a ^ b ^ c ^ d ^ e;
+}
+__device__ __forceinline__ uint64_t chi(uint64_t a, uint64_t b, uint64_t c) { return a ^ (~b & c); }
+
+__device__ __forceinline__ void keccak_f1600(uint64_t s[25]) {
+#pragma unroll 1
+    for (int r = 0; r < 24; ++r) {
+        uint64_t C0 = xor5(s[0], s[5], s[10], s[15], s[20]);
+        uint64_t C1 = xor5(s[1], s[6], s[11], s[16], s[21]);
+        uint64_t C2 = xor5(s[2], s[7], s[12], s[17], s[22]);
+        uint64_t C3 = xor5(s[3], s[8], s[13], s[18], s[23]);
+        uint64_t C4 = xor5(s[4], s[9], s[14], s[19], s[24]);
+        uint64_t D0 = C4 ^ rol64(C1, 1), D1 = C0 ^ rol64(C2, 1), D2 = C1 ^ rol64(C3, 1), D3 = C2 ^ rol64(C4, 1),
+                 D4 = C3 ^ rol64(C0, 1);
+        // theta + rho + pi: B[y][(2x+3y)%5] = rol(s[x][y] ^ D[x], r[x][y])
+        uint64_t B00 = s[0] ^ D0;
+        uint64_t B10 = rol64(s[1] ^ D1, 1), B20 = rol64(s[2] ^ D2, 62), B05 = rol64(s[3] ^ D3, 28), B15 = rol64(s[4] ^ D4, 27);
+        uint64_t B16 = rol64(s[5] ^ D0, 36), B01 = rol64(s[6] ^ D1, 44), B11 = rol64(s[7] ^ D2, 6), B21 = rol64(s[8] ^ D3, 55),
+                 B06 = rol64(s[9] ^ D4, 20);
+        uint64_t B07 = rol64(s[10] ^ D0, 3), B17 = rol64(s[11] ^ D1, 10), B02 = rol64(s[12] ^ D2, 43), B12 = rol64(s[13] ^ D3, 25),
+                 B22 = rol64(s[14] ^ D4, 39);
+        uint64_t B23 = rol64(s[15] ^ D0, 41), B08 = rol64(s[16] ^ D1, 45), B18 = rol64(s[17] ^ D2, 15), B03 = rol64(s[18] ^ D3, 21),
+                 B13 = rol64(s[19] ^ D4, 8);
+        uint64_t B14 = rol64(s[20] ^ D0, 18), B24 = rol64(s[21] ^ D1, 2), B09 = rol64(s[22] ^ D2, 61), B19 = rol64(s[23] ^ D3, 56),
+                 B04 = rol64(s[24] ^ D4, 14);
+        // names above are B<index> with index = x' + 5*y' already; rows of five:
+        // row 0: B00 B01 B02 B03 B04 ; row 1: B05 B06 B07 B08 B09 ; row 2: B10..B14 ; row 3: B15..B19 ; row 4: B20..B24
+        s[0] = chi(B00, B01, B02) ^ KECCAK_RC[r];
+        s[1] = chi(B01, B02, B03); s[2] = chi(B02, B03, B04); s[3] = chi(B03, B04, B00); s[4] = chi(B04, B00, B01);
+        s[5] = chi(B05, B06, B07); s[6] = chi(B06, B07, B08); s[7] = chi(B07, B08, B09); s[8] = chi(B08, B09, B05);
+        s[9] = chi(B09, B05, B06);
+        s[10] = chi(B10, B11, B12); s[11] = chi(B11, B12, B13); s[12] = chi(B12, B13, B14); s[13] = chi(B13, B14, B10);
+        s[14] = chi(B14, B10, B11);
+        s[15] = chi(B15, B16, B17); s[16] = chi(B16, B17, B18); s[17] = chi(B17, B18, B19); s[18] = chi(B18, B19, B15);
+        s[19] = chi(B19, B15, B16);
+        s[20] = chi(B20, B21, B22); s[21] = chi(B21, B22, B23); s[22] = chi(B22, B23, B24); s[23] = chi(B23, B24, B20);
+        s[24] = chi(B24, B20, B21);
+    }
+}
+
+__device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
+
+}  // namespace s252

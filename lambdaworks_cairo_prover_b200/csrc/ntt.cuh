@@ -1,0 +1,212 @@
+// ntt.cuh -- shared-memory-staged NTT passes over Stark252 (natural order in, natural order out).
+//
+// A size-N transform (N = 2^n) is run as one, two or three passes ("four-step" decomposition):
+//
+//   strided pass  (kind A)  view the column as [outer][L][inner]; for every (o, i) run a size-L DIT
+//                           NTT along the middle axis, multiply output k by the inter-pass twiddle
+//                           ptw[k*inner + i] = s^i * w_(L*inner)^(k*i) [* 1/N] and store in place
+//                           of the input position.  A block owns a tile of T consecutive i, so
+//                           every global access is a run of T*32 bytes.
+//   final pass    (kind B)  rows of L contiguous elements; a block owns T rows whose outputs are
+//                           adjacent (consecutive k1), runs a size-L NTT on each and scatters
+//                           output k of row (k1,k2) to  (k1 + N1*k2 + N1*N2*k)*ostride + coset.
+//
+// Coset evaluation (evaluate_offset_fft: out[i] = p(h*w_M^i), M = b*N) is b independent size-N
+// coset transforms (coset r has shift s_r = h*w_M^r and lands on outputs b*k + r).  A coset
+// transform costs nothing extra: the shift only changes the level twiddles of the FIRST pass
+// (level of size n uses s^(L/n... ) * w_n^j) and its inter-pass table.
+//
+// Inside a block the tile lives in shared memory as [pos][T]; every level is one radix-2 DIT
+// butterfly per work item (a, b) -> (a + w*b, a - w*b + 2p) with lazy reduction: values grow by 2p
+// per level (< 24p after 11 levels, 32p is the limit), and are brought back to [0,p) once, at the
+// store.  The butterfly is ~175 integer instructions, so the 8 shared-memory accesses per level
+// are noise; HBM traffic per pass is one read and one write of the data.
+#pragma once
+#include "fe.cuh"
+
+namespace s252 {
+
+constexpr int NTT_THREADS = 256;
+constexpr int NTT_TILE_LOG = 11;                       // 2048 elements = 64 KB of shared memory
+constexpr int NTT_TILE = 1 << NTT_TILE_LOG;
+constexpr int NTT_MAX_LOGL = NTT_TILE_LOG;
+
+struct NttPass {
+    const fe* in;
+    fe* out;
+    const fe* lvl;        // level twiddles: [ncosets][L]; level of half-size h uses lvl[h + j], j < h
+    const fe* ptw;        // kind A: [ncosets][L*inner] inter-pass twiddles
+    const fe* oscale;     // kind B, optional: [N1*N2*L] multiplier per natural output index
+    unsigned long long in_col_stride, out_col_stride;   // elements between columns
+    unsigned long long in_coset_stride, out_coset_stride;   // elements between cosets (0 = shared)
+    unsigned logL, logT;
+    unsigned logInner;    // kind A
+    unsigned logOuter;    // kind A
+    unsigned logN1, logN2;   // kind B: digits that precede this one (rows = N1*N2 per column)
+    unsigned ncosets;     // b (1 for plain transforms)
+    unsigned ostride;     // kind B: output index multiplier (b for coset evaluation, else 1)
+    unsigned ncols;
+    unsigned lvl_per_coset;   // 1 if the level twiddles differ per coset
+    unsigned ptw_per_coset;   // kind A: 1 if the inter-pass twiddles differ per coset
+    unsigned rows_are_cols;   // kind B single-pass: the T rows of a tile are T different columns
+    unsigned in_lw;           // kind B single-pass: input is in the reference's LW element format
+    unsigned out_lw;          // kind B: store outputs in LW format
+};
+
+__device__ __forceinline__ unsigned bitrev32(unsigned x, unsigned bits) { return bits ? __brev(x) >> (32 - bits) : 0u; }
+
+// All levels of a size-L DIT transform on every one of the T sequences held in sm[pos*T + t]
+// (input already in bit-reversed position order).
+__device__ __forceinline__ void block_dit(fe* sm, const fe* __restrict__ lvl, unsigned logL, unsigned logT) {
+    const unsigned T = 1u << logT;
+    const unsigned items = (1u << (logL - 1)) << logT;
+    for (unsigned lev = 0; lev < logL; ++lev) {
+        const unsigned half = 1u << lev;
+        for (unsigned w = threadIdx.x; w < items; w += NTT_THREADS) {
+            const unsigned t = w & (T - 1);
+            const unsigned j = w >> logT;
+            const unsigned jj = j & (half - 1);
+            const unsigned i0 = ((j >> lev) << (lev + 1)) + jj;
+            fe* pa = sm + ((i0 << logT) + t);
+            fe* pb = sm + (((i0 + half) << logT) + t);
+            const fe a = ld_fe(pa);
+            const fe b = ld_fe(pb);
+            const fe tw = ldg_fe(lvl + half + jj);
+            const fe v = fe_mul(b, tw);
+            st_fe(pa, fe_add_lazy(a, v));
+            st_fe(pb, fe_sub_lazy<2>(a, v));
+        }
+        __syncthreads();
+    }
+}
+
+// ---- kind A: strided pass -------------------------------------------------------------------
+__global__ void __launch_bounds__(NTT_THREADS) ntt_pass_strided(NttPass P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    fe* sm = reinterpret_cast<fe*>(smem_raw);
+    const unsigned L = 1u << P.logL, T = 1u << P.logT;
+    const unsigned coset = blockIdx.x % P.ncosets;
+    const unsigned tile = blockIdx.x / P.ncosets;
+    const unsigned col = blockIdx.y;
+    const unsigned tiles_per_outer = 1u << (P.logInner - P.logT);
+    const unsigned long long o = tile / tiles_per_outer;
+    const unsigned long long i0 = (unsigned long long)(tile % tiles_per_outer) << P.logT;
+    const fe* in = P.in + col * P.in_col_stride + coset * P.in_coset_stride + ((o << P.logL) << P.logInner) + i0;
+    fe* out = P.out + col * P.out_col_stride + coset * P.out_coset_stride + ((o << P.logL) << P.logInner) + i0;
+    const unsigned n = L << P.logT;
+    for (unsigned e = threadIdx.x; e < n; e += NTT_THREADS) {
+        const unsigned t = e & (T - 1), pos = e >> P.logT;
+        const fe v = ld_fe(in + ((unsigned long long)pos << P.logInner) + t);
+        st_fe(sm + ((bitrev32(pos, P.logL) << P.logT) + t), v);
+    }
+    __syncthreads();
+    block_dit(sm, P.lvl + (P.lvl_per_coset ? (size_t)coset << P.logL : 0), P.logL, P.logT);
+    const fe* ptw = P.ptw + (P.ptw_per_coset ? (size_t)coset << (P.logL + P.logInner) : 0) + i0;
+    for (unsigned e = threadIdx.x; e < n; e += NTT_THREADS) {
+        const unsigned t = e & (T - 1), k = e >> P.logT;
+        fe v = ld_fe(sm + e);
+        const fe w = ldg_fe(ptw + ((unsigned long long)k << P.logInner) + t);
+        v = fe_reduce(fe_mul(v, w));
+        st_fe(out + ((unsigned long long)k << P.logInner) + t, v);
+    }
+}
+
+// ---- kind B: final pass ----------------------------------------------------------------------
+__global__ void __launch_bounds__(NTT_THREADS) ntt_pass_final(NttPass P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    fe* sm = reinterpret_cast<fe*>(smem_raw);
+    const unsigned L = 1u << P.logL, T = 1u << P.logT;
+    const unsigned coset = blockIdx.x % P.ncosets;
+    const unsigned tile = blockIdx.x / P.ncosets;
+    const unsigned n = L << P.logT;
+    unsigned long long out_base;     // natural output index of (row t = 0, k = 0)
+    const fe* in;
+    fe* out;
+    unsigned col0 = blockIdx.y, live = T;     // live: rows of the tile that exist
+    if (P.rows_are_cols) {
+        col0 = tile << P.logT;
+        live = min(T, P.ncols - col0);
+        in = P.in + col0 * P.in_col_stride + coset * P.in_coset_stride;
+        out = P.out + col0 * P.out_col_stride;
+        out_base = 0;
+    } else {
+        // tile -> (k2, group of T consecutive k1)
+        const unsigned groups = 1u << (P.logN1 - P.logT);
+        const unsigned k2 = tile / groups;
+        const unsigned k1 = (tile % groups) << P.logT;
+        in = P.in + col0 * P.in_col_stride + coset * P.in_coset_stride +
+             ((((unsigned long long)k1 << P.logN2) + k2) << P.logL);
+        out = P.out + col0 * P.out_col_stride;
+        out_base = k1 + ((unsigned long long)k2 << P.logN1);
+    }
+    // row t of the tile starts at in + t*row_stride
+    const unsigned long long row_stride = P.rows_are_cols ? P.in_col_stride : (1ull << (P.logN2 + P.logL));
+    for (unsigned e = threadIdx.x; e < n; e += NTT_THREADS) {
+        const unsigned pos = e & (L - 1), t = e >> P.logL;
+        fe v = fe_zero();
+        if (t < live) {
+            const fe* src = in + t * row_stride + pos;
+            v = P.in_lw ? ld_lw(src) : ld_fe(src);
+        }
+        st_fe(sm + ((bitrev32(pos, P.logL) << P.logT) + t), v);
+    }
+    __syncthreads();
+    block_dit(sm, P.lvl + (P.lvl_per_coset ? (size_t)coset << P.logL : 0), P.logL, P.logT);
+    const unsigned logRows = P.logN1 + P.logN2;
+    for (unsigned e = threadIdx.x; e < n; e += NTT_THREADS) {
+        const unsigned t = e & (T - 1), k = e >> P.logT;
+        if (t >= live) continue;
+        fe v = ld_fe(sm + e);
+        unsigned long long oi;     // natural output index within the column
+        fe* dst;
+        if (P.rows_are_cols) {
+            oi = k;
+            dst = out + t * P.out_col_stride + (unsigned long long)k * P.ostride + coset;
+        } else {
+            oi = out_base + t + ((unsigned long long)k << logRows);
+            dst = out + oi * P.ostride + coset;
+        }
+        if (P.oscale) v = fe_mul(v, ldg_fe(P.oscale + oi));
+        v = fe_reduce(v);
+        if (P.out_lw) st_lw(dst, v); else st_fe(dst, v);
+    }
+}
+
+// ---- table generation ---------------------------------------------------------------------
+// lvl[c][h + j] = shift_c^(L/(2h)) * w_(2h)^j  for h = 1, 2, .., L/2, j < h   (lvl[c][0] unused)
+// where shift_c = base_shift * coset_step^c  and  w_(2h) = wL^(L/(2h)).
+__global__ void gen_level_twiddles(fe* lvl, unsigned logL, unsigned ncosets, fe wL, fe base_shift, fe coset_step) {
+    const unsigned L = 1u << logL;
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= L * ncosets) return;
+    const unsigned c = idx >> logL, x = idx & (L - 1);
+    if (x == 0) { st_fe(lvl + idx, fe_one()); return; }
+    const unsigned lev = 31 - __clz(x);            // h = 2^lev
+    const unsigned j = x - (1u << lev);
+    const unsigned e = L >> (lev + 1);             // L/(2h)
+    const fe shift = fe_mul_full(base_shift, fe_pow(coset_step, c));
+    const fe a = fe_pow(shift, e);
+    const fe b = fe_pow(wL, (uint64_t)e * j);
+    st_fe(lvl + idx, fe_mul_full(a, b));
+}
+// ptw[c][k*inner + i] = scale * (shift_c * wS^k)^i,  S = L*inner, k < L, i < inner
+__global__ void gen_pass_twiddles(fe* ptw, unsigned logL, unsigned logInner, unsigned ncosets, fe wS, fe base_shift,
+                                  fe coset_step, fe scale) {
+    const unsigned long long S = 1ull << (logL + logInner);
+    const unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= S * ncosets) return;
+    const unsigned c = (unsigned)(idx >> (logL + logInner));
+    const unsigned long long x = idx & (S - 1);
+    const unsigned long long k = x >> logInner, i = x & ((1ull << logInner) - 1);
+    const fe shift = fe_mul_full(base_shift, fe_pow(coset_step, c));
+    const fe g = fe_mul_full(shift, fe_pow(wS, k));
+    st_fe(ptw + idx, fe_mul_full(scale, fe_pow(g, i)));
+}
+// out[k] = scale * base^k
+__global__ void gen_powers(fe* out, unsigned long long n, fe base, fe scale) {
+    const unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    st_fe(out + idx, fe_mul_full(scale, fe_pow(base, idx)));
+}
+
+}  // namespace s252

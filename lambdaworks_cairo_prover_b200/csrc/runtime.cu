@@ -1,0 +1,1005 @@
+// runtime.cu -- host runtime + C ABI (include/stark252_b200.h) over the sm_100a kernels.
+//
+// One context = one device + one stream + a cache of twiddle tables.  Device memory comes from
+// the stream-ordered pool (cudaMallocAsync) with the release threshold raised, so the multi-GB
+// LDE / scratch buffers of consecutive commits are recycled without going back to the driver.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/stark252_b200.h"
+#include "commit.cuh"
+#include "fe.cuh"
+#include "host_field.hpp"
+#include "keccak.cuh"
+#include "microbench.cuh"
+#include "ntt.cuh"
+
+using s252::fe;
+namespace H = s252::host;
+
+// --------------------------------------------------------------------------------------------
+struct s252_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    std::map<std::string, fe*> tables;   // cached twiddle tables (device)
+    size_t table_bytes = 0;
+    unsigned max_logl = s252::NTT_MAX_LOGL;
+};
+
+struct s252_commit {
+    s252_ctx* ctx = nullptr;
+    size_t n_cols = 0, n_rows = 0, n_coeffs = 0;
+    fe* coeffs = nullptr;       // [n_cols][n_coeffs]
+    fe* lde = nullptr;          // [n_cols][n_rows]
+    uint64_t* nodes = nullptr;  // [(2*n_rows-1)][4]
+};
+
+struct FriLayerDev {
+    size_t size = 0;
+    fe* evals = nullptr;
+    uint64_t* nodes = nullptr;
+};
+struct s252_fri {
+    s252_ctx* ctx = nullptr;
+    size_t domain_size = 0;
+    std::vector<FriLayerDev> layers;
+};
+
+#define FAIL(ctx, code, ...)                                     \
+    do {                                                         \
+        char _b[512];                                            \
+        std::snprintf(_b, sizeof _b, __VA_ARGS__);               \
+        (ctx)->err = _b;                                         \
+        return (code);                                           \
+    } while (0)
+#define CU(ctx, call)                                                                                  \
+    do {                                                                                               \
+        cudaError_t _e = (call);                                                                       \
+        if (_e != cudaSuccess) FAIL(ctx, S252_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(_e), \
+                                    __FILE__, __LINE__);                                               \
+    } while (0)
+#define TRY(expr)                  \
+    do {                           \
+        int _rc = (expr);          \
+        if (_rc != S252_OK) return _rc; \
+    } while (0)
+#define LAUNCH_CHECK(ctx)           \
+    do {                            \
+        (ctx)->launches++;          \
+        CU(ctx, cudaGetLastError()); \
+    } while (0)
+
+static inline bool is_pow2(size_t n) { return n && !(n & (n - 1)); }
+static inline unsigned ilog2(size_t n) { unsigned k = 0; while (((size_t)1 << k) < n) ++k; return k; }
+static inline size_t next_pow2(size_t n) { size_t r = 1; while (r < n) r <<= 1; return r; }
+
+template <typename T>
+static int dalloc(s252_ctx* ctx, T** p, size_t count) {
+    *p = nullptr;
+    if (count == 0) count = 1;
+    CU(ctx, cudaMallocAsync((void**)p, count * sizeof(T), ctx->stream));
+    return S252_OK;
+}
+template <typename T>
+static void dfree(s252_ctx* ctx, T* p) {
+    if (p) cudaFreeAsync((void*)p, ctx->stream);
+}
+// RAII for temporaries
+template <typename T>
+struct Tmp {
+    s252_ctx* ctx;
+    T* p = nullptr;
+    explicit Tmp(s252_ctx* c) : ctx(c) {}
+    ~Tmp() { dfree(ctx, p); }
+    Tmp(const Tmp&) = delete;
+    Tmp& operator=(const Tmp&) = delete;
+};
+
+// --------------------------------------------------------------------------------------------
+// context
+extern "C" int s252_ctx_create(int device, s252_ctx** out) {
+    if (!out) return S252_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0 || device < 0 || device >= count) return S252_ERR_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return S252_ERR_CUDA;
+    s252_ctx* ctx = new s252_ctx();
+    ctx->device = device;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return S252_ERR_CUDA; }
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    cudaFuncSetAttribute(s252::ntt_pass_strided, cudaFuncAttributeMaxDynamicSharedMemorySize, s252::NTT_TILE * 32);
+    cudaFuncSetAttribute(s252::ntt_pass_final, cudaFuncAttributeMaxDynamicSharedMemorySize, s252::NTT_TILE * 32);
+    if (const char* e = std::getenv("S252_MAX_LOGL")) {
+        int v = std::atoi(e);
+        if (v >= 4 && v <= s252::NTT_MAX_LOGL) ctx->max_logl = (unsigned)v;
+    }
+    *out = ctx;
+    return S252_OK;
+}
+extern "C" void s252_ctx_destroy(s252_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& kv : ctx->tables) cudaFree(kv.second);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+extern "C" const char* s252_last_error(const s252_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+extern "C" int s252_ctx_synchronize(s252_ctx* ctx) {
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return S252_OK;
+}
+extern "C" void* s252_ctx_stream(s252_ctx* ctx) { return (void*)ctx->stream; }
+extern "C" uint64_t s252_ctx_launch_count(const s252_ctx* ctx) { return ctx->launches; }
+extern "C" int s252_device_alloc(s252_ctx* ctx, size_t bytes, void** out) {
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMalloc(out, bytes ? bytes : 1));
+    return S252_OK;
+}
+extern "C" int s252_device_free(s252_ctx* ctx, void* ptr) {
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, cudaFree(ptr));
+    return S252_OK;
+}
+extern "C" int s252_copy_to_device(s252_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    CU(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return S252_OK;
+}
+extern "C" int s252_copy_to_host(s252_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    CU(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return S252_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// twiddle tables
+static std::string fe_key(const fe& a) {
+    char b[80];
+    std::snprintf(b, sizeof b, "%08x%08x%08x%08x%08x%08x%08x%08x", a.l[7], a.l[6], a.l[5], a.l[4], a.l[3], a.l[2], a.l[1], a.l[0]);
+    return b;
+}
+static int table_alloc(s252_ctx* ctx, const std::string& key, size_t count, fe** out, bool* fresh) {
+    auto it = ctx->tables.find(key);
+    if (it != ctx->tables.end()) { *out = it->second; *fresh = false; return S252_OK; }
+    fe* p = nullptr;
+    CU(ctx, cudaMalloc((void**)&p, count * sizeof(fe)));
+    ctx->tables[key] = p;
+    ctx->table_bytes += count * sizeof(fe);
+    *out = p;
+    *fresh = true;
+    return S252_OK;
+}
+static int get_level_table(s252_ctx* ctx, unsigned logL, unsigned ncosets, const fe& wL, const fe& shift,
+                           const fe& step, const fe** out) {
+    std::string key = "lvl:" + std::to_string(logL) + ":" + std::to_string(ncosets) + ":" + fe_key(wL) + ":" +
+                      fe_key(shift) + ":" + fe_key(step);
+    fe* t; bool fresh;
+    const size_t count = ((size_t)1 << logL) * ncosets;
+    TRY(table_alloc(ctx, key, count, &t, &fresh));
+    if (fresh) {
+        s252::gen_level_twiddles<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(t, logL, ncosets, wL, shift, step);
+        LAUNCH_CHECK(ctx);
+    }
+    *out = t;
+    return S252_OK;
+}
+static int get_pass_table(s252_ctx* ctx, unsigned logL, unsigned logInner, unsigned ncosets, const fe& wS,
+                          const fe& shift, const fe& step, const fe& scale, const fe** out) {
+    std::string key = "ptw:" + std::to_string(logL) + ":" + std::to_string(logInner) + ":" + std::to_string(ncosets) +
+                      ":" + fe_key(wS) + ":" + fe_key(shift) + ":" + fe_key(step) + ":" + fe_key(scale);
+    fe* t; bool fresh;
+    const size_t count = ((size_t)1 << (logL + logInner)) * ncosets;
+    TRY(table_alloc(ctx, key, count, &t, &fresh));
+    if (fresh) {
+        s252::gen_pass_twiddles<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(t, logL, logInner, ncosets, wS, shift, step, scale);
+        LAUNCH_CHECK(ctx);
+    }
+    *out = t;
+    return S252_OK;
+}
+static int get_power_table(s252_ctx* ctx, size_t n, const fe& base, const fe& scale, const fe** out) {
+    std::string key = "pow:" + std::to_string(n) + ":" + fe_key(base) + ":" + fe_key(scale);
+    fe* t; bool fresh;
+    TRY(table_alloc(ctx, key, n, &t, &fresh));
+    if (fresh) {
+        s252::gen_powers<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(t, n, base, scale);
+        LAUNCH_CHECK(ctx);
+    }
+    *out = t;
+    return S252_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// One batched transform over `ncols` columns of N = 2^logn elements (internal format unless in_lw).
+//   forward:  out[(k*ncosets + c)] = sum_n in[n] * (shift*step^c)^n * w_N^(n k)      (natural order)
+//   inverse:  out[k] = oscale[k] * (1/N) * sum_n in[n] * w_N^(-n k)
+struct Xform {
+    unsigned logn = 0;
+    bool inverse = false;
+    unsigned ncosets = 1;
+    fe shift = s252::fe_one();       // coset shift of coset 0 (forward only)
+    fe step = s252::fe_one();        // ratio between consecutive coset shifts (forward only)
+    bool has_offset_scale = false;   // inverse only: multiply output k by oscale_base^k
+    fe oscale_base = s252::fe_one();
+};
+
+static int run_ntt(s252_ctx* ctx, const Xform& X, const fe* in, size_t in_col_stride, bool in_lw, fe* out,
+                   size_t out_col_stride, bool out_lw, unsigned ncols) {
+    const unsigned logn = X.logn;
+    const size_t N = (size_t)1 << logn;
+    const unsigned maxl = ctx->max_logl;
+    if (ncols == 0) return S252_OK;
+    if (X.ncosets == 0 || !is_pow2(X.ncosets)) FAIL(ctx, S252_ERR_INVALID, "coset count must be a power of two");
+    fe wN;
+    if (!H::primitive_root(logn, &wN)) FAIL(ctx, S252_ERR_INVALID, "no root of unity of order 2^%u", logn);
+    auto root = [&](unsigned lg) { fe w; H::primitive_root(lg, &w); return X.inverse ? H::inv(w) : w; };
+    const fe n_inv = X.inverse ? H::inv(H::from_u64((uint64_t)N)) : H::one();
+
+    s252::NttPass P{};
+    P.ncosets = X.ncosets;
+    P.ncols = ncols;
+    P.ostride = X.ncosets;
+    const unsigned smem = s252::NTT_TILE * 32;
+
+    // digits
+    unsigned npass = logn <= maxl ? 1 : (logn <= 2 * maxl ? 2 : 3);
+    if (logn > 3 * maxl) FAIL(ctx, S252_ERR_INVALID, "transform of size 2^%u is not supported", logn);
+
+    const fe* oscale = nullptr;
+    if (X.inverse && (X.has_offset_scale || npass == 1)) {
+        TRY(get_power_table(ctx, N, X.has_offset_scale ? X.oscale_base : H::one(), npass == 1 ? n_inv : H::one(), &oscale));
+    }
+
+    if (npass == 1) {
+        const fe* lvl;
+        TRY(get_level_table(ctx, logn, X.ncosets, root(logn), X.shift, X.step, &lvl));
+        unsigned logT = s252::NTT_TILE_LOG - logn;
+        if (logT > 5) logT = 5;
+        while (logT > 0 && (1u << logT) > ncols) --logT;
+        P.in = in; P.out = out; P.lvl = lvl; P.ptw = nullptr; P.oscale = oscale;
+        P.in_col_stride = in_col_stride; P.out_col_stride = out_col_stride;
+        P.in_coset_stride = 0; P.out_coset_stride = 0;
+        P.logL = logn; P.logT = logT; P.logN1 = 0; P.logN2 = 0;
+        P.lvl_per_coset = X.ncosets > 1; P.rows_are_cols = 1; P.in_lw = in_lw; P.out_lw = out_lw;
+        const unsigned tiles = (ncols + (1u << logT) - 1) >> logT;
+        s252::ntt_pass_final<<<dim3(tiles * X.ncosets, 1), s252::NTT_THREADS, smem, ctx->stream>>>(P);
+        LAUNCH_CHECK(ctx);
+        return S252_OK;
+    }
+    if (in_lw) FAIL(ctx, S252_ERR_INVALID, "internal: LW input only on the single-pass path");
+
+    unsigned l1, l2 = 0, l3;
+    if (npass == 2) {
+        l3 = (logn + 1) / 2;
+        l1 = logn - l3;
+    } else {
+        l3 = (logn + 2) / 3;
+        l2 = (logn - l3 + 1) / 2;
+        l1 = logn - l3 - l2;
+    }
+    // scratch: [col][coset][N]
+    Tmp<fe> Z(ctx);
+    TRY(dalloc(ctx, &Z.p, (size_t)ncols * X.ncosets * N));
+
+    // pass A1: L = 2^l1 over stride 2^(logn-l1)
+    {
+        const unsigned logInner = logn - l1;
+        const fe shiftL = H::pow_u64(X.shift, (uint64_t)1 << logInner);
+        const fe stepL = H::pow_u64(X.step, (uint64_t)1 << logInner);
+        const fe *lvl, *ptw;
+        TRY(get_level_table(ctx, l1, X.ncosets, root(l1), shiftL, stepL, &lvl));
+        TRY(get_pass_table(ctx, l1, logInner, X.ncosets, root(logn), X.shift, X.step, n_inv, &ptw));
+        unsigned logT = std::min(s252::NTT_TILE_LOG - l1, logInner);
+        if (logT > 5) logT = 5;
+        P.in = in; P.out = Z.p; P.lvl = lvl; P.ptw = ptw; P.oscale = nullptr;
+        P.in_col_stride = in_col_stride; P.out_col_stride = (size_t)X.ncosets * N;
+        P.in_coset_stride = 0; P.out_coset_stride = N;
+        P.logL = l1; P.logT = logT; P.logInner = logInner; P.logOuter = 0;
+        P.lvl_per_coset = X.ncosets > 1; P.ptw_per_coset = X.ncosets > 1; P.rows_are_cols = 0; P.in_lw = 0; P.out_lw = 0;
+        const size_t tiles = (size_t)1 << (logInner - logT);
+        s252::ntt_pass_strided<<<dim3((unsigned)(tiles * X.ncosets), ncols), s252::NTT_THREADS, smem, ctx->stream>>>(P);
+        LAUNCH_CHECK(ctx);
+    }
+    if (npass == 3) {
+        // pass A2: in place on Z, view [2^l1][2^l2][2^l3]
+        const fe *lvl, *ptw;
+        TRY(get_level_table(ctx, l2, 1, root(l2), H::one(), H::one(), &lvl));
+        TRY(get_pass_table(ctx, l2, l3, 1, root(l2 + l3), H::one(), H::one(), H::one(), &ptw));
+        unsigned logT = std::min(s252::NTT_TILE_LOG - l2, l3);
+        if (logT > 5) logT = 5;
+        P.in = Z.p; P.out = Z.p; P.lvl = lvl; P.ptw = ptw; P.oscale = nullptr;
+        P.in_col_stride = (size_t)X.ncosets * N; P.out_col_stride = (size_t)X.ncosets * N;
+        P.in_coset_stride = N; P.out_coset_stride = N;
+        P.logL = l2; P.logT = logT; P.logInner = l3; P.logOuter = l1;
+        P.lvl_per_coset = 0; P.ptw_per_coset = 0;
+        const size_t tiles = (size_t)1 << (l1 + l3 - logT);
+        s252::ntt_pass_strided<<<dim3((unsigned)(tiles * X.ncosets), ncols), s252::NTT_THREADS, smem, ctx->stream>>>(P);
+        LAUNCH_CHECK(ctx);
+    }
+    {
+        // final pass: rows of 2^l3
+        const fe* lvl;
+        TRY(get_level_table(ctx, l3, 1, root(l3), H::one(), H::one(), &lvl));
+        unsigned logT = std::min(s252::NTT_TILE_LOG - l3, l1);
+        if (logT > 5) logT = 5;
+        P.in = Z.p; P.out = out; P.lvl = lvl; P.ptw = nullptr; P.oscale = oscale;
+        P.in_col_stride = (size_t)X.ncosets * N; P.out_col_stride = out_col_stride;
+        P.in_coset_stride = N; P.out_coset_stride = 0;
+        P.logL = l3; P.logT = logT; P.logN1 = l1; P.logN2 = l2;
+        P.lvl_per_coset = 0; P.ptw_per_coset = 0; P.rows_are_cols = 0; P.in_lw = 0; P.out_lw = out_lw;
+        const size_t tiles = (size_t)1 << (l1 + l2 - logT);
+        s252::ntt_pass_final<<<dim3((unsigned)(tiles * X.ncosets), ncols), s252::NTT_THREADS, smem, ctx->stream>>>(P);
+        LAUNCH_CHECK(ctx);
+    }
+    return S252_OK;
+}
+
+// Batched Merkle tree over `n_rows` rows of column-major `cols`.
+static int build_tree(s252_ctx* ctx, const fe* cols, size_t col_stride, unsigned ncols, size_t n_rows, uint64_t* nodes) {
+    if (!is_pow2(n_rows)) FAIL(ctx, S252_ERR_INVALID, "merkle tree needs a power-of-two number of leaves (got %zu)", n_rows);
+    const unsigned depth = ilog2(n_rows);
+    s252::merkle_leaves<<<(unsigned)((n_rows + 127) / 128), 128, 0, ctx->stream>>>(cols, col_stride, ncols, n_rows,
+                                                                                nodes + 4 * (n_rows - 1));
+    LAUNCH_CHECK(ctx);
+    unsigned level = depth;
+    while (level > 0) {
+        const unsigned levels = std::min<unsigned>(s252::MERKLE_FUSED_LEVELS, level);
+        const size_t nchildren = (size_t)1 << level;
+        const unsigned blocks = (unsigned)std::max<size_t>(1, nchildren / (2 * s252::MERKLE_BLOCK));
+        s252::merkle_nodes<<<blocks, s252::MERKLE_BLOCK, 0, ctx->stream>>>(nodes, level, levels);
+        LAUNCH_CHECK(ctx);
+        level -= levels;
+    }
+    return S252_OK;
+}
+// only the node levels (leaves already hashed)
+static int build_tree_nodes(s252_ctx* ctx, size_t n_rows, uint64_t* nodes) {
+    unsigned level = ilog2(n_rows);
+    while (level > 0) {
+        const unsigned levels = std::min<unsigned>(s252::MERKLE_FUSED_LEVELS, level);
+        const size_t nchildren = (size_t)1 << level;
+        const unsigned blocks = (unsigned)std::max<size_t>(1, nchildren / (2 * s252::MERKLE_BLOCK));
+        s252::merkle_nodes<<<blocks, s252::MERKLE_BLOCK, 0, ctx->stream>>>(nodes, level, levels);
+        LAUNCH_CHECK(ctx);
+        level -= levels;
+    }
+    return S252_OK;
+}
+
+// Bring a caller buffer of `count` LW elements onto the device (no format change).
+static int stage_in(s252_ctx* ctx, const s252_fe* src, size_t count, int mem, Tmp<fe>& staged, const fe** dev) {
+    if (mem == S252_DEVICE) { *dev = reinterpret_cast<const fe*>(src); return S252_OK; }
+    TRY(dalloc(ctx, &staged.p, count));
+    CU(ctx, cudaMemcpyAsync(staged.p, src, count * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
+    *dev = staged.p;
+    return S252_OK;
+}
+static int stage_out(s252_ctx* ctx, const fe* dev_lw, s252_fe* dst, size_t count, int mem) {
+    if (mem == S252_DEVICE) return S252_OK;   // written in place
+    CU(ctx, cudaMemcpyAsync(dst, dev_lw, count * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return S252_OK;
+}
+static int convert_lw_to_internal(s252_ctx* ctx, const fe* in, fe* out, size_t n) {
+    s252::lw_to_internal<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(in, out, n);
+    LAUNCH_CHECK(ctx);
+    return S252_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// FFTPoly entry points
+static int interpolate_common(s252_ctx* ctx, const s252_fe* evals, size_t n, const s252_fe* offset, s252_fe* coeffs, int mem) {
+    if (!ctx || !evals || !coeffs) return S252_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (!is_pow2(n)) FAIL(ctx, S252_ERR_INVALID, "FFTError: input length %zu is not a power of two", n);
+    Tmp<fe> staged(ctx), conv(ctx), outbuf(ctx);
+    const fe* din;
+    TRY(stage_in(ctx, evals, n, mem, staged, &din));
+    Xform X;
+    X.logn = ilog2(n);
+    X.inverse = true;
+    if (offset) {
+        const fe off = H::from_lw(offset->limbs);
+        if (H::is_zero(off)) FAIL(ctx, S252_ERR_INVALID, "coset offset must be non-zero");
+        X.has_offset_scale = true;
+        X.oscale_base = H::inv(off);
+    }
+    fe* dout = reinterpret_cast<fe*>(coeffs);
+    if (mem == S252_HOST) { TRY(dalloc(ctx, &outbuf.p, n)); dout = outbuf.p; }
+    bool in_lw = true;
+    if (X.logn > ctx->max_logl) {
+        TRY(dalloc(ctx, &conv.p, n));
+        TRY(convert_lw_to_internal(ctx, din, conv.p, n));
+        din = conv.p;
+        in_lw = false;
+    }
+    TRY(run_ntt(ctx, X, din, n, in_lw, dout, n, true, 1));
+    TRY(stage_out(ctx, dout, coeffs, n, mem));
+    return S252_OK;
+}
+extern "C" int s252_interpolate_fft(s252_ctx* ctx, const s252_fe* evals, size_t n, s252_fe* coeffs, int mem) {
+    return interpolate_common(ctx, evals, n, nullptr, coeffs, mem);
+}
+extern "C" int s252_interpolate_offset_fft(s252_ctx* ctx, const s252_fe* evals, size_t n, const s252_fe* offset,
+                                           s252_fe* coeffs, int mem) {
+    if (!offset) return S252_ERR_INVALID;
+    return interpolate_common(ctx, evals, n, offset, coeffs, mem);
+}
+extern "C" size_t s252_evaluate_offset_fft_len(size_t n_coeffs, size_t blowup, size_t domain_size) {
+    return next_pow2(std::max(n_coeffs, domain_size)) * blowup;
+}
+
+// Evaluate `ncols` polynomials (internal format, [ncols][n_pad] with n_pad = 2^k coefficients,
+// zero padded) on the coset  offset * w_len^i, len = n_pad * ncosets.  out: [ncols][len].
+static const unsigned MAX_COSETS = 64;
+static int evaluate_cosets(s252_ctx* ctx, const fe* coeffs, size_t coeff_stride, bool in_lw, unsigned logn_pad,
+                           unsigned ncosets, const fe& offset, fe* out, size_t out_stride, bool out_lw, unsigned ncols) {
+    const size_t len = ((size_t)1 << logn_pad) * ncosets;
+    fe wlen;
+    if (!H::primitive_root(ilog2(len), &wlen)) FAIL(ctx, S252_ERR_INVALID, "domain of size %zu has no root of unity", len);
+    Xform X;
+    X.logn = logn_pad;
+    X.ncosets = ncosets;
+    X.shift = offset;
+    X.step = wlen;
+    return run_ntt(ctx, X, coeffs, coeff_stride, in_lw, out, out_stride, out_lw, ncols);
+}
+
+// Shared by evaluate_offset_fft / evaluate_polynomial_on_lde_domain / FRI layer 0: coefficients in
+// LW format on the device -> evaluations on a domain of `len` points (len >= n_coeffs, power of two).
+// Pads the coefficient vector so that at most MAX_COSETS cosets are needed.
+static int evaluate_from_lw(s252_ctx* ctx, const fe* dcoeffs_lw, size_t n_coeffs, size_t len, const fe& offset, fe* out,
+                            bool out_lw) {
+    size_t n_pad = next_pow2(std::max<size_t>(n_coeffs, 1));
+    if (n_pad > len) FAIL(ctx, S252_ERR_INVALID, "polynomial with %zu coefficients does not fit a domain of %zu", n_coeffs, len);
+    while (len / n_pad > MAX_COSETS) n_pad <<= 1;
+    Tmp<fe> pad(ctx);
+    TRY(dalloc(ctx, &pad.p, n_pad));
+    if (n_pad > n_coeffs) CU(ctx, cudaMemsetAsync(pad.p + n_coeffs, 0, (n_pad - n_coeffs) * sizeof(fe), ctx->stream));
+    if (n_coeffs) TRY(convert_lw_to_internal(ctx, dcoeffs_lw, pad.p, n_coeffs));
+    return evaluate_cosets(ctx, pad.p, n_pad, false, ilog2(n_pad), (unsigned)(len / n_pad), offset, out, len, out_lw, 1);
+}
+
+extern "C" int s252_evaluate_offset_fft(s252_ctx* ctx, const s252_fe* coeffs, size_t n_coeffs, size_t blowup,
+                                        size_t domain_size, const s252_fe* offset, s252_fe* out, size_t out_capacity, int mem) {
+    if (!ctx || !offset || !out || (!coeffs && n_coeffs)) return S252_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (!is_pow2(blowup)) FAIL(ctx, S252_ERR_INVALID, "blowup factor %zu is not a power of two", blowup);
+    const size_t len = s252_evaluate_offset_fft_len(n_coeffs, blowup, domain_size);
+    if (out_capacity < len) FAIL(ctx, S252_ERR_INVALID, "output buffer holds %zu elements, %zu needed", out_capacity, len);
+    Tmp<fe> staged(ctx), outbuf(ctx);
+    const fe* din = nullptr;
+    if (n_coeffs) TRY(stage_in(ctx, coeffs, n_coeffs, mem, staged, &din));
+    fe* dout = reinterpret_cast<fe*>(out);
+    if (mem == S252_HOST) { TRY(dalloc(ctx, &outbuf.p, len)); dout = outbuf.p; }
+    TRY(evaluate_from_lw(ctx, din, n_coeffs, len, H::from_lw(offset->limbs), dout, true));
+    TRY(stage_out(ctx, dout, out, len, mem));
+    return S252_OK;
+}
+extern "C" int s252_evaluate_polynomial_on_lde_domain(s252_ctx* ctx, const s252_fe* coeffs, size_t n_coeffs, size_t blowup,
+                                                      size_t domain_size, const s252_fe* offset, s252_fe* out, int mem) {
+    if (!ctx || !offset || !out || (!coeffs && n_coeffs)) return S252_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (!is_pow2(blowup) || !is_pow2(domain_size)) FAIL(ctx, S252_ERR_INVALID, "blowup and domain size must be powers of two");
+    const size_t len = s252_evaluate_offset_fft_len(n_coeffs, blowup, domain_size);
+    const size_t want = domain_size * blowup;
+    const size_t step = len / want;
+    Tmp<fe> staged(ctx), full(ctx), outbuf(ctx);
+    const fe* din = nullptr;
+    if (n_coeffs) TRY(stage_in(ctx, coeffs, n_coeffs, mem, staged, &din));
+    fe* dout = reinterpret_cast<fe*>(out);
+    if (mem == S252_HOST) { TRY(dalloc(ctx, &outbuf.p, want)); dout = outbuf.p; }
+    if (step == 1) {
+        TRY(evaluate_from_lw(ctx, din, n_coeffs, len, H::from_lw(offset->limbs), dout, true));
+    } else {
+        // prover.rs:118-122: evaluate on the larger domain and keep every step-th point
+        TRY(dalloc(ctx, &full.p, len));
+        TRY(evaluate_from_lw(ctx, din, n_coeffs, len, H::from_lw(offset->limbs), full.p, true));
+        s252::subsample<<<(unsigned)((want + 255) / 256), 256, 0, ctx->stream>>>(full.p, dout, want, step);
+        LAUNCH_CHECK(ctx);
+    }
+    TRY(stage_out(ctx, dout, out, want, mem));
+    return S252_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// commits
+static void commit_free(s252_commit* c) {
+    if (!c) return;
+    dfree(c->ctx, c->coeffs);
+    dfree(c->ctx, c->lde);
+    dfree(c->ctx, c->nodes);
+    delete c;
+}
+static int fetch_root(s252_ctx* ctx, const uint64_t* nodes, uint8_t root[32]) {
+    CU(ctx, cudaMemcpyAsync(root, nodes, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return S252_OK;
+}
+
+extern "C" int s252_interpolate_and_commit(s252_ctx* ctx, const s252_fe* trace, size_t n_rows, size_t n_cols, size_t blowup,
+                                           uint64_t coset_offset, int mem, s252_commit** out, uint8_t root[32]) {
+    if (!ctx || !trace || !out || !root) return S252_ERR_INVALID;
+    *out = nullptr;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (!is_pow2(n_rows) || n_cols == 0) FAIL(ctx, S252_ERR_INVALID, "FFTError: trace length %zu is not a power of two", n_rows);
+    if (!is_pow2(blowup) || blowup > MAX_COSETS) FAIL(ctx, S252_ERR_INVALID, "blowup factor %zu must be a power of two <= %u", blowup, MAX_COSETS);
+    if (coset_offset == 0) FAIL(ctx, S252_ERR_INVALID, "coset offset must be non-zero");
+    const size_t N = n_rows, M = n_rows * blowup;
+    const unsigned c = (unsigned)n_cols;
+    s252_commit* cm = new s252_commit();
+    cm->ctx = ctx; cm->n_cols = n_cols; cm->n_rows = M; cm->n_coeffs = N;
+    int rc = [&]() -> int {
+        Tmp<fe> staged(ctx), cols(ctx);
+        const fe* dtrace;
+        TRY(stage_in(ctx, trace, N * c, mem, staged, &dtrace));
+        // TraceTable::cols(): row-major LW -> column-major internal
+        TRY(dalloc(ctx, &cols.p, N * c));
+        s252::rows_lw_to_cols<<<dim3((unsigned)((N + 31) / 32), (c + 31) / 32), 256, 0, ctx->stream>>>(dtrace, N, c, cols.p, N);
+        LAUNCH_CHECK(ctx);
+        // compute_trace_polys: interpolate_fft per column
+        TRY(dalloc(ctx, &cm->coeffs, N * c));
+        Xform I;
+        I.logn = ilog2(N);
+        I.inverse = true;
+        TRY(run_ntt(ctx, I, cols.p, N, false, cm->coeffs, N, false, c));
+        // compute_lde_trace_evaluations: evaluate_offset_fft(blowup, Some(N), h) per column
+        TRY(dalloc(ctx, &cm->lde, M * c));
+        TRY(evaluate_cosets(ctx, cm->coeffs, N, false, ilog2(N), (unsigned)blowup, H::from_u64(coset_offset), cm->lde, M, false, c));
+        // batch_commit over the rows of the LDE table
+        TRY(dalloc(ctx, &cm->nodes, 4 * (2 * M - 1)));
+        TRY(build_tree(ctx, cm->lde, M, c, M, cm->nodes));
+        TRY(fetch_root(ctx, cm->nodes, root));
+        return S252_OK;
+    }();
+    if (rc != S252_OK) { commit_free(cm); return rc; }
+    *out = cm;
+    return S252_OK;
+}
+
+extern "C" int s252_lde_and_commit(s252_ctx* ctx, const s252_fe* polys, size_t n_coeffs, size_t n_polys, size_t domain_size,
+                                   size_t blowup, uint64_t coset_offset, int mem, s252_commit** out, uint8_t root[32]) {
+    if (!ctx || !polys || !out || !root) return S252_ERR_INVALID;
+    *out = nullptr;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (!is_pow2(domain_size) || !is_pow2(blowup) || blowup > MAX_COSETS || n_polys == 0)
+        FAIL(ctx, S252_ERR_INVALID, "domain size and blowup must be powers of two");
+    if (n_coeffs > domain_size)
+        FAIL(ctx, S252_ERR_INVALID, "polynomials with %zu coefficients exceed the trace domain %zu; use "
+                                    "s252_evaluate_polynomial_on_lde_domain + s252_merkle_build", n_coeffs, domain_size);
+    if (coset_offset == 0) FAIL(ctx, S252_ERR_INVALID, "coset offset must be non-zero");
+    const size_t N = domain_size, M = domain_size * blowup;
+    const unsigned c = (unsigned)n_polys;
+    s252_commit* cm = new s252_commit();
+    cm->ctx = ctx; cm->n_cols = n_polys; cm->n_rows = M; cm->n_coeffs = N;
+    int rc = [&]() -> int {
+        Tmp<fe> staged(ctx);
+        const fe* dpolys;
+        TRY(stage_in(ctx, polys, n_coeffs * c, mem, staged, &dpolys));
+        TRY(dalloc(ctx, &cm->coeffs, N * c));
+        CU(ctx, cudaMemsetAsync(cm->coeffs, 0, N * c * sizeof(fe), ctx->stream));
+        for (unsigned j = 0; j < c; ++j)
+            if (n_coeffs) TRY(convert_lw_to_internal(ctx, dpolys + j * n_coeffs, cm->coeffs + j * N, n_coeffs));
+        TRY(dalloc(ctx, &cm->lde, M * c));
+        TRY(evaluate_cosets(ctx, cm->coeffs, N, false, ilog2(N), (unsigned)blowup, H::from_u64(coset_offset), cm->lde, M, false, c));
+        TRY(dalloc(ctx, &cm->nodes, 4 * (2 * M - 1)));
+        TRY(build_tree(ctx, cm->lde, M, c, M, cm->nodes));
+        TRY(fetch_root(ctx, cm->nodes, root));
+        return S252_OK;
+    }();
+    if (rc != S252_OK) { commit_free(cm); return rc; }
+    *out = cm;
+    return S252_OK;
+}
+
+extern "C" int s252_merkle_build(s252_ctx* ctx, const s252_fe* rows, size_t n_rows, size_t n_cols, int mem, s252_commit** out,
+                                 uint8_t root[32]) {
+    if (!ctx || !rows || !out || !root) return S252_ERR_INVALID;
+    *out = nullptr;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (!is_pow2(n_rows) || n_cols == 0) FAIL(ctx, S252_ERR_INVALID, "merkle tree needs a power-of-two number of leaves (got %zu)", n_rows);
+    const unsigned c = (unsigned)n_cols;
+    s252_commit* cm = new s252_commit();
+    cm->ctx = ctx; cm->n_cols = n_cols; cm->n_rows = n_rows; cm->n_coeffs = 0;
+    int rc = [&]() -> int {
+        Tmp<fe> staged(ctx);
+        const fe* drows;
+        TRY(stage_in(ctx, rows, n_rows * c, mem, staged, &drows));
+        TRY(dalloc(ctx, &cm->lde, n_rows * c));
+        s252::rows_lw_to_cols<<<dim3((unsigned)((n_rows + 31) / 32), (c + 31) / 32), 256, 0, ctx->stream>>>(drows, n_rows, c, cm->lde, n_rows);
+        LAUNCH_CHECK(ctx);
+        TRY(dalloc(ctx, &cm->nodes, 4 * (2 * n_rows - 1)));
+        TRY(build_tree(ctx, cm->lde, n_rows, c, n_rows, cm->nodes));
+        TRY(fetch_root(ctx, cm->nodes, root));
+        return S252_OK;
+    }();
+    if (rc != S252_OK) { commit_free(cm); return rc; }
+    *out = cm;
+    return S252_OK;
+}
+extern "C" void s252_commit_destroy(s252_commit* c) {
+    if (!c) return;
+    cudaSetDevice(c->ctx->device);
+    commit_free(c);
+}
+extern "C" size_t s252_commit_n_cols(const s252_commit* c) { return c->n_cols; }
+extern "C" size_t s252_commit_n_rows(const s252_commit* c) { return c->n_rows; }
+extern "C" size_t s252_commit_n_coeffs(const s252_commit* c) { return c->n_coeffs; }
+extern "C" int s252_commit_root(const s252_commit* c, uint8_t root[32]) {
+    s252_ctx* ctx = c->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    return fetch_root(ctx, c->nodes, root);
+}
+static int read_internal_as_lw(s252_ctx* ctx, const fe* src, size_t count, s252_fe* out) {
+    Tmp<fe> tmp(ctx);
+    TRY(dalloc(ctx, &tmp.p, count));
+    s252::internal_to_lw<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(src, tmp.p, count);
+    LAUNCH_CHECK(ctx);
+    CU(ctx, cudaMemcpyAsync(out, tmp.p, count * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return S252_OK;
+}
+extern "C" int s252_commit_read_lde(s252_commit* c, size_t col, size_t first, size_t count, s252_fe* out) {
+    s252_ctx* ctx = c->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (col >= c->n_cols || first + count > c->n_rows) FAIL(ctx, S252_ERR_RANGE, "LDE read out of range");
+    if (count == 0) return S252_OK;
+    return read_internal_as_lw(ctx, c->lde + col * c->n_rows + first, count, out);
+}
+extern "C" int s252_commit_read_coeffs(s252_commit* c, size_t col, s252_fe* out) {
+    s252_ctx* ctx = c->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (!c->coeffs || col >= c->n_cols) FAIL(ctx, S252_ERR_RANGE, "coefficient read out of range");
+    return read_internal_as_lw(ctx, c->coeffs + col * c->n_coeffs, c->n_coeffs, out);
+}
+extern "C" int s252_commit_read_nodes(s252_commit* c, size_t first, size_t count, uint8_t* out) {
+    s252_ctx* ctx = c->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (first + count > 2 * c->n_rows - 1) FAIL(ctx, S252_ERR_RANGE, "node read out of range");
+    CU(ctx, cudaMemcpyAsync(out, c->nodes + 4 * first, count * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return S252_OK;
+}
+static int open_common(s252_ctx* ctx, const fe* cols, size_t col_stride, unsigned ncols, const uint64_t* nodes, size_t n_rows,
+                       const uint64_t* indices, size_t n_idx, s252_fe* rows_out, uint8_t* paths_out) {
+    if (n_idx == 0) return S252_OK;
+    for (size_t q = 0; q < n_idx; ++q)
+        if (indices[q] >= n_rows) FAIL(ctx, S252_ERR_RANGE, "position %llu is outside the tree (%zu leaves)", (unsigned long long)indices[q], n_rows);
+    const unsigned depth = ilog2(n_rows);
+    Tmp<unsigned long long> didx(ctx);
+    Tmp<fe> drows(ctx);
+    Tmp<uint64_t> dpaths(ctx);
+    TRY(dalloc(ctx, &didx.p, n_idx));
+    CU(ctx, cudaMemcpyAsync(didx.p, indices, n_idx * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (rows_out) {
+        TRY(dalloc(ctx, &drows.p, n_idx * ncols));
+        s252::gather_rows<<<(unsigned)((n_idx * ncols + 127) / 128), 128, 0, ctx->stream>>>(cols, col_stride, ncols, didx.p, (unsigned)n_idx, drows.p);
+        LAUNCH_CHECK(ctx);
+        CU(ctx, cudaMemcpyAsync(rows_out, drows.p, n_idx * ncols * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (paths_out && depth) {
+        TRY(dalloc(ctx, &dpaths.p, n_idx * depth * 4));
+        s252::gather_paths<<<(unsigned)((n_idx * depth + 127) / 128), 128, 0, ctx->stream>>>(nodes, depth, didx.p, (unsigned)n_idx, dpaths.p);
+        LAUNCH_CHECK(ctx);
+        CU(ctx, cudaMemcpyAsync(paths_out, dpaths.p, n_idx * depth * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return S252_OK;
+}
+extern "C" int s252_commit_open(s252_commit* c, const uint64_t* indices, size_t n_idx, s252_fe* rows_out, uint8_t* paths_out) {
+    s252_ctx* ctx = c->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (!indices && n_idx) return S252_ERR_INVALID;
+    return open_common(ctx, c->lde, c->n_rows, (unsigned)c->n_cols, c->nodes, c->n_rows, indices, n_idx, rows_out, paths_out);
+}
+extern "C" const void* s252_commit_device_lde(const s252_commit* c) { return c->lde; }
+extern "C" const void* s252_commit_device_coeffs(const s252_commit* c) { return c->coeffs; }
+extern "C" const void* s252_commit_device_nodes(const s252_commit* c) { return c->nodes; }
+
+// --------------------------------------------------------------------------------------------
+// FRI
+static void fri_free(s252_fri* f) {
+    if (!f) return;
+    for (auto& l : f->layers) { dfree(f->ctx, l.evals); dfree(f->ctx, l.nodes); }
+    delete f;
+}
+extern "C" int s252_fri_commit_phase(s252_ctx* ctx, size_t number_layers, const s252_fe* p0, size_t n_coeffs,
+                                     s252_transcript* transcript, const s252_fe* coset_offset, size_t domain_size, int mem,
+                                     s252_fri** out, s252_fe* last_value, uint8_t* roots_out) {
+    if (!ctx || !transcript || !coset_offset || !out || !last_value || (!p0 && n_coeffs)) return S252_ERR_INVALID;
+    *out = nullptr;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (!is_pow2(domain_size)) FAIL(ctx, S252_ERR_INVALID, "FRI domain size %zu is not a power of two", domain_size);
+    if (n_coeffs > domain_size) FAIL(ctx, S252_ERR_INVALID, "p0 has %zu coefficients, more than the domain size %zu", n_coeffs, domain_size);
+    const unsigned logM = ilog2(domain_size);
+    if (number_layers > logM) FAIL(ctx, S252_ERR_INVALID, "%zu FRI layers do not fit a domain of size %zu", number_layers, domain_size);
+    fe h = H::from_lw(coset_offset->limbs);
+    if (H::is_zero(h)) FAIL(ctx, S252_ERR_INVALID, "coset offset must be non-zero");
+    s252_fri* f = new s252_fri();
+    f->ctx = ctx; f->domain_size = domain_size;
+    int rc = [&]() -> int {
+        Tmp<fe> staged(ctx);
+        const fe* dp0 = nullptr;
+        if (n_coeffs) TRY(stage_in(ctx, p0, n_coeffs, mem, staged, &dp0));
+        // layer 0: FriLayer::new(p0, h, domain_size)
+        FriLayerDev cur;
+        cur.size = domain_size;
+        TRY(dalloc(ctx, &cur.evals, domain_size));
+        f->layers.push_back(cur);   // owned by f from here on
+        TRY(evaluate_from_lw(ctx, dp0, n_coeffs, domain_size, h, f->layers[0].evals, false));
+        fe wM, w_inv;
+        H::primitive_root(logM, &wM);
+        w_inv = H::inv(wM);
+        const fe* inv_tw = nullptr;
+        if (domain_size >= 2) TRY(get_power_table(ctx, domain_size / 2, w_inv, H::one(), &inv_tw));
+        const fe inv2 = H::inv(H::from_u64(2));
+        uint8_t root[32];
+        if (number_layers > 0) {
+            TRY(dalloc(ctx, &f->layers[0].nodes, 4 * (2 * domain_size - 1)));
+            TRY(build_tree(ctx, f->layers[0].evals, domain_size, 1, domain_size, f->layers[0].nodes));
+            TRY(fetch_root(ctx, f->layers[0].nodes, root));
+            transcript->append(root, 32);                       // fri/mod.rs:37
+            if (roots_out) std::memcpy(roots_out, root, 32);
+        }
+        size_t size = domain_size;
+        for (size_t k = 1; k <= number_layers; ++k) {
+            // fri/mod.rs:43-54 (k < number_layers) and :58-60 (the last fold)
+            const fe zeta = transcript->to_field();
+            const fe cfac = H::mul(zeta, H::mul(inv2, H::inv(h)));   // zeta / (2 h_k)
+            const size_t half = size / 2;
+            if (half == 0) FAIL(ctx, S252_ERR_INVALID, "FRI layer of size %zu cannot be folded", size);
+            const bool commit = k < number_layers;
+            FriLayerDev nxt;
+            nxt.size = half;
+            TRY(dalloc(ctx, &nxt.evals, half));
+            f->layers.push_back(nxt);
+            FriLayerDev& L = f->layers.back();
+            if (commit) TRY(dalloc(ctx, &L.nodes, 4 * (2 * half - 1)));
+            s252::fri_fold_commit<<<(unsigned)((half + 127) / 128), 128, 0, ctx->stream>>>(
+                f->layers[k - 1].evals, half, inv_tw, (unsigned long long)(domain_size / size), cfac, inv2, L.evals,
+                commit ? L.nodes + 4 * (half - 1) : nullptr);
+            LAUNCH_CHECK(ctx);
+            h = H::sqr(h);
+            size = half;
+            if (commit) {
+                TRY(build_tree_nodes(ctx, half, L.nodes));
+                TRY(fetch_root(ctx, L.nodes, root));
+                transcript->append(root, 32);                   // fri/mod.rs:54
+                if (roots_out) std::memcpy(roots_out + 32 * k, root, 32);
+            }
+        }
+        if (number_layers == 0) {
+            // degenerate: no committed layer, a single fold (fri/mod.rs:58-60)
+            const fe zeta = transcript->to_field();
+            const fe cfac = H::mul(zeta, H::mul(inv2, H::inv(h)));
+            const size_t half = size / 2;
+            if (half == 0) FAIL(ctx, S252_ERR_INVALID, "FRI domain of size %zu cannot be folded", size);
+            FriLayerDev nxt;
+            nxt.size = half;
+            TRY(dalloc(ctx, &nxt.evals, half));
+            f->layers.push_back(nxt);
+            s252::fri_fold_commit<<<(unsigned)((half + 127) / 128), 128, 0, ctx->stream>>>(
+                f->layers[0].evals, half, inv_tw, 1ull, cfac, inv2, f->layers.back().evals, nullptr);
+            LAUNCH_CHECK(ctx);
+            size = half;
+        }
+        // last_value = coefficient 0 of the fully folded polynomial = mean of its evaluations on the
+        // remaining coset (it has at most `size` coefficients because n_coeffs <= domain_size).
+        std::vector<fe> tail(size);
+        CU(ctx, cudaMemcpyAsync(tail.data(), f->layers.back().evals, size * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        fe acc = H::zero();
+        for (size_t i = 0; i < size; ++i) acc = H::add(acc, tail[i]);
+        const fe lv = H::mul(acc, H::inv(H::from_u64((uint64_t)size)));
+        H::to_lw(lv, last_value->limbs);
+        uint8_t be[32];
+        H::to_bytes_be(lv, be);
+        transcript->append(be, 32);                             // fri/mod.rs:69
+        // the folded tail is not a FriLayer of the reference: drop it
+        dfree(ctx, f->layers.back().evals);
+        f->layers.pop_back();
+        if (number_layers == 0) { dfree(ctx, f->layers.back().evals); f->layers.pop_back(); }
+        return S252_OK;
+    }();
+    if (rc != S252_OK) { fri_free(f); return rc; }
+    *out = f;
+    return S252_OK;
+}
+extern "C" void s252_fri_destroy(s252_fri* f) {
+    if (!f) return;
+    cudaSetDevice(f->ctx->device);
+    fri_free(f);
+}
+extern "C" size_t s252_fri_n_layers(const s252_fri* f) { return f->layers.size(); }
+extern "C" int s252_fri_read_layer(s252_fri* f, size_t layer, size_t first, size_t count, s252_fe* out) {
+    s252_ctx* ctx = f->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (layer >= f->layers.size() || first + count > f->layers[layer].size) FAIL(ctx, S252_ERR_RANGE, "FRI layer read out of range");
+    if (count == 0) return S252_OK;
+    return read_internal_as_lw(ctx, f->layers[layer].evals + first, count, out);
+}
+extern "C" int s252_fri_read_nodes(s252_fri* f, size_t layer, size_t first, size_t count, uint8_t* out) {
+    s252_ctx* ctx = f->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (layer >= f->layers.size() || first + count > 2 * f->layers[layer].size - 1) FAIL(ctx, S252_ERR_RANGE, "FRI node read out of range");
+    CU(ctx, cudaMemcpyAsync(out, f->layers[layer].nodes + 4 * first, count * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return S252_OK;
+}
+extern "C" int s252_fri_query(s252_fri* f, const uint64_t* iotas, size_t n_queries, s252_fe* evals, s252_fe* evals_sym,
+                              uint8_t* paths, uint8_t* paths_sym, size_t path_stride) {
+    s252_ctx* ctx = f->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (!iotas && n_queries) return S252_ERR_INVALID;
+    const size_t L = f->layers.size();
+    std::vector<uint64_t> idx(n_queries), idx_sym(n_queries);
+    std::vector<s252_fe> col(n_queries);
+    std::vector<uint8_t> pth;
+    for (size_t k = 0; k < L; ++k) {
+        const FriLayerDev& lay = f->layers[k];
+        const unsigned depth = ilog2(lay.size);
+        if (paths && path_stride < depth) FAIL(ctx, S252_ERR_INVALID, "path_stride %zu is smaller than the tree depth %u", path_stride, depth);
+        for (size_t q = 0; q < n_queries; ++q) {
+            idx[q] = iotas[q] % lay.size;                              // fri/mod.rs:101
+            idx_sym[q] = (iotas[q] + lay.size / 2) % lay.size;         // fri/mod.rs:102
+        }
+        pth.resize(n_queries * depth * 32);
+        for (int sym = 0; sym < 2; ++sym) {
+            s252_fe* ev = sym ? evals_sym : evals;
+            uint8_t* pp = sym ? paths_sym : paths;
+            TRY(open_common(ctx, lay.evals, lay.size, 1, lay.nodes, lay.size, sym ? idx_sym.data() : idx.data(), n_queries,
+                            ev ? col.data() : nullptr, pp ? pth.data() : nullptr));
+            for (size_t q = 0; q < n_queries; ++q) {
+                if (ev) ev[q * L + k] = col[q];
+                if (pp) std::memcpy(pp + (q * L + k) * path_stride * 32, pth.data() + q * depth * 32, depth * 32);
+            }
+        }
+    }
+    return S252_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// grinding
+extern "C" int s252_generate_nonce_with_grinding(s252_ctx* ctx, const uint8_t challenge[32], uint8_t grinding_factor,
+                                                 uint64_t limit, uint64_t* nonce) {
+    if (!ctx || !challenge || !nonce) return S252_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (grinding_factor > 64) FAIL(ctx, S252_ERR_NOT_FOUND, "a 64-bit head cannot have %u trailing zeros", grinding_factor);
+    if (limit == 0) limit = ~0ull;   // the reference searches 0..u64::MAX
+    uint64_t lanes[4];
+    std::memcpy(lanes, challenge, 32);   // little-endian host
+    Tmp<unsigned long long> best(ctx);
+    TRY(dalloc(ctx, &best.p, 1));
+    // windows grow from 2^16 to 2^26 candidates: small factors finish in one tiny launch
+    uint64_t base = 0;
+    unsigned long long window = 1ull << 16;
+    while (base < limit) {
+        const unsigned long long count = std::min<unsigned long long>(window, limit - base);
+        CU(ctx, cudaMemsetAsync(best.p, 0xff, 8, ctx->stream));
+        s252::grind_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(lanes[0], lanes[1], lanes[2], lanes[3], base, count,
+                                                                                   grinding_factor, best.p);
+        LAUNCH_CHECK(ctx);
+        unsigned long long found;
+        CU(ctx, cudaMemcpyAsync(&found, best.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        if (found != ~0ull) { *nonce = found; return S252_OK; }
+        base += count;
+        if (window < (1ull << 26)) window <<= 2;
+    }
+    FAIL(ctx, S252_ERR_NOT_FOUND, "nonce not found below %llu", (unsigned long long)limit);
+}
+
+// --------------------------------------------------------------------------------------------
+// transcript
+extern "C" s252_transcript* s252_transcript_new(void) { return new s252_transcript(); }
+extern "C" void s252_transcript_free(s252_transcript* t) { delete t; }
+extern "C" void s252_transcript_append(s252_transcript* t, const uint8_t* data, size_t len) { t->append(data, len); }
+extern "C" void s252_transcript_challenge(s252_transcript* t, uint8_t out[32]) { t->challenge(out); }
+extern "C" void s252_transcript_to_field(s252_transcript* t, s252_fe* out) { H::to_lw(t->to_field(), out->limbs); }
+extern "C" uint64_t s252_transcript_to_usize(s252_transcript* t) { return t->to_usize(); }
+
+// --------------------------------------------------------------------------------------------
+// diagnostics
+extern "C" int s252_fe_binop(s252_ctx* ctx, int op, const s252_fe* a, const s252_fe* b, s252_fe* out, size_t n, int mem) {
+    if (!ctx || !a || !out || op < 0 || op > 3 || (op != 3 && !b)) return S252_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    Tmp<fe> sa(ctx), sb(ctx), so(ctx);
+    const fe *da, *db = nullptr;
+    TRY(stage_in(ctx, a, n, mem, sa, &da));
+    if (b) TRY(stage_in(ctx, b, n, mem, sb, &db));
+    fe* dout = reinterpret_cast<fe*>(out);
+    if (mem == S252_HOST) { TRY(dalloc(ctx, &so.p, n)); dout = so.p; }
+    s252::fe_binop_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(op, da, db ? db : da, dout, n);
+    LAUNCH_CHECK(ctx);
+    TRY(stage_out(ctx, dout, out, n, mem));
+    return S252_OK;
+}
+extern "C" int s252_keccak256_batch(s252_ctx* ctx, const uint8_t* msgs, size_t msg_len, size_t n, uint8_t* digests) {
+    if (!ctx || !digests || (!msgs && msg_len * n)) return S252_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    Tmp<uint8_t> dm(ctx), dd(ctx);
+    TRY(dalloc(ctx, &dm.p, msg_len * n + 8));
+    TRY(dalloc(ctx, &dd.p, 32 * n));
+    if (msg_len * n) CU(ctx, cudaMemcpyAsync(dm.p, msgs, msg_len * n, cudaMemcpyHostToDevice, ctx->stream));
+    s252::keccak_bytes_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(dm.p, msg_len, n, dd.p);
+    LAUNCH_CHECK(ctx);
+    CU(ctx, cudaMemcpyAsync(digests, dd.p, 32 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return S252_OK;
+}
+
+template <typename F>
+static int time_kernel(s252_ctx* ctx, F launch, int reps, float* ms_best) {
+    cudaEvent_t e0, e1;
+    CU(ctx, cudaEventCreate(&e0));
+    CU(ctx, cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int r = 0; r < reps + 1; ++r) {
+        CU(ctx, cudaEventRecord(e0, ctx->stream));
+        launch();
+        ctx->launches++;
+        CU(ctx, cudaEventRecord(e1, ctx->stream));
+        CU(ctx, cudaEventSynchronize(e1));
+        float ms;
+        CU(ctx, cudaEventElapsedTime(&ms, e0, e1));
+        if (r > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    CU(ctx, cudaGetLastError());
+    *ms_best = best;
+    return S252_OK;
+}
+extern "C" int s252_microbench_int_pipes(s252_ctx* ctx, double out[5]) {
+    if (!ctx || !out) return S252_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    int sms = 0;
+    CU(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+    Tmp<uint32_t> sink(ctx);
+    const int blocks = sms * 8, threads = 256, iters = 2048;
+    TRY(dalloc(ctx, &sink.p, (size_t)blocks * threads));
+    for (int which = 0; which < 5; ++which) {
+        float ms;
+        TRY(time_kernel(ctx, [&]() { s252::int_pipe_bench<<<blocks, threads, 0, ctx->stream>>>(which, iters, sink.p); }, 5, &ms));
+        const double ops = (double)blocks * threads * iters * s252::INT_BENCH_OPS_PER_ITER;
+        out[which] = ops / (ms * 1e-3) / 1e9;
+    }
+    return S252_OK;
+}
+extern "C" int s252_microbench_fe_mul(s252_ctx* ctx, double* gmuls) {
+    if (!ctx || !gmuls) return S252_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    int sms = 0;
+    CU(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+    Tmp<fe> sink(ctx);
+    const int blocks = sms * 8, threads = 256, iters = 512;
+    TRY(dalloc(ctx, &sink.p, (size_t)blocks * threads));
+    float ms;
+    TRY(time_kernel(ctx, [&]() { s252::fe_mul_bench<<<blocks, threads, 0, ctx->stream>>>(iters, sink.p); }, 5, &ms));
+    *gmuls = (double)blocks * threads * iters * 2 / (ms * 1e-3) / 1e9;
+    return S252_OK;
+}
+extern "C" int s252_microbench_keccak(s252_ctx* ctx, double* gperms) {
+    if (!ctx || !gperms) return S252_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    int sms = 0;
+    CU(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+    Tmp<uint64_t> sink(ctx);
+    const int blocks = sms * 16, threads = 128, iters = 64;
+    TRY(dalloc(ctx, &sink.p, (size_t)blocks * threads));
+    float ms;
+    TRY(time_kernel(ctx, [&]() { s252::keccak_bench<<<blocks, threads, 0, ctx->stream>>>(iters, sink.p); }, 5, &ms));
+    *gperms = (double)blocks * threads * iters / (ms * 1e-3) / 1e9;
+    return S252_OK;
+}

@@ -1,0 +1,27 @@
+"""Integer-pipe peak probes on the local GPU (roofline denominators missing from MEASURED_PEAKS.json)."""
+import ctypes as C
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import lambdaworks_cairo_prover_b200 as P
+from lambdaworks_cairo_prover_b200 import _native as N
+
+
+def main():
+    ctx = P.Context(0)
+    arr = (C.c_double * 5)()
+    ctx.check(N.lib().s252_microbench_int_pipes(ctx.handle, arr))
+    g = C.c_double()
+    ctx.check(N.lib().s252_microbench_fe_mul(ctx.handle, C.byref(g)))
+    k = C.c_double()
+    ctx.check(N.lib().s252_microbench_keccak(ctx.handle, C.byref(k)))
+    out = {"imad_wide_gops": arr[0], "lop3_gops": arr[1], "shf_gops": arr[2], "iadd_carry_gops": arr[3],
+           "imad_wide_plus_lop3_gops": arr[4], "fe_mul_gmuls": g.value, "keccak_gperms": k.value}
+    print(json.dumps(out))
+    return out
+
+
+if __name__ == "__main__":
+    main()
