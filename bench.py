@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py -- Stark252 coset-LDE + Merkle commit throughput on B200 (BASELINE.json metric).
+
+One step = the commitment phase of one Cairo fib-70k-shaped proof (BASELINE.json configs[1],
+SURVEY.md section 8 config C2): N = 2^19 rows, blowup 4 (M = 2^21), coset offset 3:
+    interpolate_and_commit(main trace, 34 columns)          prover.rs:126-159
+    interpolate_and_commit(aux trace, 18 columns)           prover.rs:208
+    round-2 LDE + commit of H1, H2 (2 columns)              prover.rs:254-276
+    fri_commit_phase(19 layers from 2^21) + grinding(20)    fri/mod.rs:20-72, grinding.rs:40-48
+`elems` = field elements that end up under a Merkle root in that step
+        = M*(34+18+2) LDE values + sum of the 19 FRI layer sizes.
+
+`value`  : elems/s with the inputs already resident in HBM (S252_DEVICE buffers).
+`e2e`    : the same step through the host-buffer C ABI: pinned host inputs are copied in inside
+           the timed region, roots / last value / nonce are read back.
+Timing   : CUDA events on the library's stream, W >= 3 warm-up steps, max over ranks; every step
+           streams ~8 GB through HBM (inputs/outputs far larger than the 126 MB L2).
+N > 1    : one process per GPU, each proving an independent trace (weak scaling, no data-path
+           collective) -- see DESIGN.md "multi-GPU".
+--impl reference : the CPU restatement of the reference (oracle/, threads over columns as under the
+           reference's `parallel` feature) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LOG_N, BLOWUP, OFFSET, GRIND = 19, 4, 3, 20
+COLS_MAIN, COLS_AUX, COLS_COMP = 34, 18, 2
+METRIC = "stark252_lde_merkle_commit_elems_per_s"
+UNIT = "elems/s"
+
+
+def workload_config(log_n):
+    n = 1 << log_n
+    m = n * BLOWUP
+    fri_elems = sum(m >> k for k in range(log_n))
+    elems = m * (COLS_MAIN + COLS_AUX + COLS_COMP) + fri_elems
+    return {
+        "workload": "C2 cairo-fib-70k commit phase: N=2^%d rows, blowup %d, 34 main + 18 aux + 2 composition columns, "
+                    "%d FRI layers + grinding %d" % (log_n, BLOWUP, log_n, GRIND),
+        "trace_rows": n, "lde_rows": m, "columns": [COLS_MAIN, COLS_AUX, COLS_COMP], "blowup": BLOWUP,
+        "coset_offset": OFFSET, "fri_layers": log_n, "grinding_factor": GRIND, "elems_per_step": elems,
+        "l2_policy": "inputs and outputs of every kernel exceed L2 (126 MB); no flush needed",
+        "parallelism": "one independent trace per GPU",
+    }
+
+
+def splitmix_felts(seed, count):
+    """count field elements in the reference's LW layout, seeded."""
+    idx = np.arange(1, 4 * count + 1, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        z = np.uint64(seed) + idx * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    z = z.reshape(count, 4)
+    z[:, 0] &= np.uint64((1 << 59) - 1)     # < 2^251 < p
+    return z
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, device):
+        super().__init__(daemon=True)
+        self.device, self.samples, self.stop_flag = device, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    import lambdaworks_cairo_prover_b200 as P
+    from lambdaworks_cairo_prover_b200 import _native as N
+    import ctypes as C
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU path)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    log_n = args.log_n
+    cfg = workload_config(log_n)
+    n, m = cfg["trace_rows"], cfg["lde_rows"]
+    ctx = P.Context(local_rank)
+    L = N.lib()
+    stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
+
+    # synthetic inputs (seed 0xB200 + config index 2; every rank its own trace)
+    seed = 0xB200 + 2 + 1000 * rank
+    host = {
+        "main": splitmix_felts(seed, n * COLS_MAIN),
+        "aux": splitmix_felts(seed + 1, n * COLS_AUX),
+        "comp": splitmix_felts(seed + 2, n * COLS_COMP),
+        "p0": splitmix_felts(seed + 3, n),
+    }
+    pinned = {}
+    for k, v in host.items():
+        t = torch.empty(v.nbytes, dtype=torch.uint8, pin_memory=True)
+        t.numpy()[:] = v.reshape(-1).view(np.uint8)
+        pinned[k] = t
+    dev = {}
+    for k, v in host.items():
+        p = ctx.device_alloc(v.nbytes)
+        ctx.to_device(p, v)
+        dev[k] = p
+    h2d_bytes = sum(v.nbytes for v in host.values())
+    from lambdaworks_cairo_prover_b200 import felt
+    offset_fe = felt.from_int(OFFSET)
+
+    def step(mem):
+        src = dev if mem == N.DEVICE else {k: t.data_ptr() for k, t in pinned.items()}
+        tr = P.DefaultTranscript()
+        root = np.empty(32, dtype=np.uint8)
+        handles = []
+        d2h = 0
+        for key, cols in (("main", COLS_MAIN), ("aux", COLS_AUX)):
+            h = C.c_void_p()
+            ctx.check(L.s252_interpolate_and_commit(ctx.handle, C.c_void_p(src[key]), n, cols, BLOWUP, OFFSET, mem,
+                                                    C.byref(h), N.ptr(root)))
+            handles.append(h)
+            tr.append(root.tobytes())
+            d2h += 32
+        h = C.c_void_p()
+        ctx.check(L.s252_lde_and_commit(ctx.handle, C.c_void_p(src["comp"]), n, COLS_COMP, n, BLOWUP, OFFSET, mem,
+                                        C.byref(h), N.ptr(root)))
+        handles.append(h)
+        tr.append(root.tobytes())
+        d2h += 32
+        fh = C.c_void_p()
+        last = np.empty(4, dtype=np.uint64)
+        roots = np.empty((log_n, 32), dtype=np.uint8)
+        ctx.check(L.s252_fri_commit_phase(ctx.handle, log_n, C.c_void_p(src["p0"]), n, tr.handle, N.ptr(offset_fe), m, mem,
+                                          C.byref(fh), N.ptr(last), N.ptr(roots)))
+        d2h += 32 * log_n + 32 * BLOWUP
+        nonce = P.generate_nonce_with_grinding(tr.challenge(), GRIND, ctx)
+        d2h += 8
+        for hh in handles:
+            L.s252_commit_destroy(hh)
+        L.s252_fri_destroy(fh)
+        return root.tobytes(), last.copy(), nonce, d2h
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(mem, steps, warmup, profile):
+        for _ in range(warmup):
+            step(mem)
+        barrier()
+        if profile:
+            ctx.profile(True, reset=True)
+        launches0 = ctx.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        e0.record(stream)
+        out = None
+        for _ in range(steps):
+            out = step(mem)
+        e1.record(stream)
+        ctx.synchronize()
+        barrier()
+        sampler.stop_flag = True
+        ms = e0.elapsed_time(e1)
+        prof = ctx.profile_read() if profile else None
+        if profile:
+            ctx.profile(False)
+        sampler.join(timeout=2)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, out, prof, ctx.launch_count - launches0, sampler.summary()
+
+    ms_dev, out_dev, prof, launches, clocks = timed(N.DEVICE, args.steps, args.warmup, True)
+    ms_e2e, out_e2e, _, _, _ = timed(N.HOST, args.steps, max(args.warmup, 1), False)
+    assert out_dev[0] == out_e2e[0] and out_dev[2] == out_e2e[2], "device-resident and host-buffer paths disagree"
+
+    elems = cfg["elems_per_step"] * world
+    value = elems * args.steps / (ms_dev * 1e-3)
+    e2e_value = elems * args.steps / (ms_e2e * 1e-3)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        top = max(prof.items(), key=lambda kv: kv[1]["ms"])
+        tname, tstat = top
+        achieved = tstat["bytes"] / (tstat["ms"] * 1e-3) / 1e9 if tstat["ms"] > 0 else 0.0
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(tname)
+        except Exception:
+            pass
+        total_kernel_ms = sum(v["ms"] for v in prof.values())
+        int_peaks = {}
+        try:
+            int_peaks = json.load(open(os.path.join(ROOT, "profiles", "int_peaks.json")))
+        except Exception:
+            pass
+        imad_peak = float(int_peaks.get("imad_wide_gops", 18300.0))
+        lop_peak = float(int_peaks.get("lop3_gops", 18450.0))
+        kernels = {}
+        for name, st in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
+            sec = st["ms"] * 1e-3
+            kernels[name] = {
+                "launches_per_step": st["launches"] / args.steps, "ms_per_step": st["ms"] / args.steps,
+                "share": st["ms"] / total_kernel_ms if total_kernel_ms else 0.0,
+                "hbm_gbs": st["bytes"] / sec / 1e9 if sec else 0.0,
+                "imad_frac": (st["muls"] * 80 / sec / 1e9) / imad_peak if sec else 0.0,
+                "keccak_gperms": st["perms"] / sec / 1e9 if sec else 0.0,
+            }
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32x8 (256-bit Montgomery) / u64 Keccak lanes", "data": "synthetic (splitmix64-seeded field elements)",
+            "config": cfg,
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": out_e2e[3]},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": tname, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                         "note": "integer-pipe bound path: see int_roofline for the binding roof"},
+            "int_roofline": {"imad_wide_peak_gops": imad_peak, "lop3_peak_gops": lop_peak,
+                             "peak_source": "tools/microbench.py on this pool's B200 (profiles/int_peaks.json)",
+                             "kernels": kernels},
+            "result": {"last_root": out_dev[0].hex(), "nonce": out_dev[2]},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline_sample(args.cpu_log_n)
+        print(json.dumps(line))
+    for p in dev.values():
+        ctx.device_free(p)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_commit_sample(log_n, threads):
+    """The same step on the CPU restatement, at a reduced trace length (bounded sample)."""
+    from oracle import pyoracle as O
+    n = 1 << log_n
+    m = n * BLOWUP
+    t0 = time.perf_counter()
+    tr = O.Transcript()
+    for seed, cols in ((11, COLS_MAIN), (12, COLS_AUX)):
+        trace = splitmix_felts(seed, n * cols).reshape(n, cols, 4)
+        r = O.interpolate_and_commit(trace, BLOWUP, OFFSET, threads=threads, want_lde=False, want_nodes=False)
+        tr.append(r["root"])
+    comp = splitmix_felts(13, n * COLS_COMP).reshape(COLS_COMP, n, 4)
+    lde = np.stack([O.evaluate_polynomial_on_lde_domain(comp[j], BLOWUP, n, O.fe_from_u64(OFFSET)) for j in range(COLS_COMP)])
+    _, root = O.commit_columns(lde)
+    tr.append(root)
+    p0 = splitmix_felts(14, n)
+    O.fri_commit_phase(log_n, p0, tr, O.fe_from_u64(OFFSET), m, keep=False)
+    O.generate_nonce_with_grinding(tr.challenge(), GRIND)
+    dt = time.perf_counter() - t0
+    elems = workload_config(log_n)["elems_per_step"]
+    return elems / dt, dt
+
+
+def cpu_baseline_sample(log_n):
+    cores = os.cpu_count() or 1
+    value, dt = cpu_commit_sample(log_n, cores)
+    return {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "same step at N=2^%d rows instead of 2^%d (all 54 columns, %d FRI layers, grinding %d); "
+                      "C restatement of the reference, LDE threaded over columns like the reference's `parallel` "
+                      "feature, everything else sequential as in the reference; %.1f s" % (log_n, LOG_N, log_n, GRIND, dt)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    for _ in range(args.warmup and 1):
+        cpu_commit_sample(max(args.cpu_log_n - 3, 4), cores)
+    t0 = time.perf_counter()
+    total_elems = 0
+    for _ in range(args.steps):
+        v, dt = cpu_commit_sample(args.cpu_log_n, cores)
+        total_elems += workload_config(args.cpu_log_n)["elems_per_step"]
+    wall = time.perf_counter() - t0
+    value = total_elems / wall
+    sample = ("each step = the C2 commit phase at N=2^%d rows instead of 2^%d (54 columns, blowup %d, %d FRI layers, "
+              "grinding %d); oracle/ C restatement (the Rust reference cannot be built here: no cargo, un-vendored "
+              "git dependencies), LDE threaded over columns as under `parallel`" % (args.cpu_log_n, LOG_N, BLOWUP, args.cpu_log_n, GRIND))
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall * 1e3 / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64x4 (256-bit Montgomery)", "data": "synthetic",
+        "config": workload_config(LOG_N),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log-n", type=int, default=LOG_N, help="trace length exponent (default: the C2 size)")
+    ap.add_argument("--cpu-log-n", type=int, default=15, help="trace length exponent of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

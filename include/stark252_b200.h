@@ -60,6 +60,13 @@ int s252_ctx_synchronize(s252_ctx *ctx);
 void *s252_ctx_stream(s252_ctx *ctx);
 /* Number of kernels this library has launched on the context since creation. */
 uint64_t s252_ctx_launch_count(const s252_ctx *ctx);
+/* Return the cached (currently unused) device blocks of the context's arena to the driver. */
+int s252_ctx_trim(s252_ctx *ctx);
+/* Per-kernel device timing: enable = 1 starts recording CUDA events around every kernel launch on
+ * this context's stream, 2 also clears the accumulated totals, 0 stops.  s252_ctx_profile_read
+ * synchronises and writes a JSON object {"kernel": {"launches": n, "ms": t}, ..} into buf. */
+int s252_ctx_profile(s252_ctx *ctx, int enable);
+int s252_ctx_profile_read(s252_ctx *ctx, char *buf, size_t cap);
 /* Device allocation helpers for callers that want S252_DEVICE buffers without another runtime. */
 int s252_device_alloc(s252_ctx *ctx, size_t bytes, void **out);
 int s252_device_free(s252_ctx *ctx, void *ptr);

@@ -23,6 +23,9 @@ SIGNATURES = {
     "s252_ctx_synchronize": (_i, [_vp]),
     "s252_ctx_stream": (_vp, [_vp]),
     "s252_ctx_launch_count": (_u64, [_vp]),
+    "s252_ctx_trim": (_i, [_vp]),
+    "s252_ctx_profile": (_i, [_vp, _i]),
+    "s252_ctx_profile_read": (_i, [_vp, C.c_char_p, _sz]),
     "s252_device_alloc": (_i, [_vp, _sz, C.POINTER(_vp)]),
     "s252_device_free": (_i, [_vp, _vp]),
     "s252_copy_to_device": (_i, [_vp, _vp, _vp, _sz]),
@@ -157,6 +160,15 @@ class Context:
     @property
     def launch_count(self):
         return int(lib().s252_ctx_launch_count(self.handle))
+
+    def profile(self, enable=True, reset=False):
+        self.check(lib().s252_ctx_profile(self.handle, 2 if (enable and reset) else int(bool(enable))))
+
+    def profile_read(self):
+        import json
+        buf = C.create_string_buffer(1 << 16)
+        self.check(lib().s252_ctx_profile_read(self.handle, buf, len(buf)))
+        return json.loads(buf.value.decode())
 
     # raw device buffers for S252_DEVICE calls (bench / multi-GPU plumbing)
     def device_alloc(self, nbytes):

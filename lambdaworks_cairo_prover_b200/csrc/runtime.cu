@@ -1,8 +1,8 @@
 // runtime.cu -- host runtime + C ABI (include/stark252_b200.h) over the sm_100a kernels.
 //
-// One context = one device + one stream + a cache of twiddle tables.  Device memory comes from
-// the stream-ordered pool (cudaMallocAsync) with the release threshold raised, so the multi-GB
-// LDE / scratch buffers of consecutive commits are recycled without going back to the driver.
+// One context = one device + one stream + a cache of twiddle tables + a device-memory arena that
+// recycles the multi-GB LDE / scratch buffers of consecutive commits without going back to the
+// driver.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -30,7 +30,69 @@ struct s252_ctx {
     std::map<std::string, fe*> tables;   // cached twiddle tables (device)
     size_t table_bytes = 0;
     unsigned max_logl = s252::NTT_MAX_LOGL;
+    // Device memory arena: freed blocks are kept and handed back to later requests of (nearly) the
+    // same size.  Everything runs on one stream, so reuse needs no synchronisation, and a prover
+    // that commits traces of the same shape over and over never goes back to the driver.
+    std::multimap<size_t, void*> arena_free;
+    std::map<void*, size_t> arena_size;
+    size_t arena_bytes = 0;
+    // per-kernel device timing (s252_ctx_profile*): events around every launch
+    bool prof = false;
+    // work = algorithmic HBM bytes (one read + one write of the data the kernel must touch),
+    // field multiplications and Keccak-f permutations of the launch ("work accounting")
+    struct Work { double bytes = 0, muls = 0, perms = 0; };
+    struct Pending { const char* name; cudaEvent_t e0, e1; Work w; };
+    struct Acc { uint64_t launches = 0; double ms = 0; Work w; };
+    std::vector<Pending> prof_pending;
+    std::vector<cudaEvent_t> prof_free;
+    std::map<std::string, Acc> prof_acc;
+    cudaEvent_t prof_e0 = nullptr;
+    const char* prof_name = nullptr;
+    Work prof_work;
 };
+
+static cudaEvent_t prof_event(s252_ctx* ctx) {
+    if (!ctx->prof_free.empty()) { cudaEvent_t e = ctx->prof_free.back(); ctx->prof_free.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+static inline void prof_begin(s252_ctx* ctx, const char* name) {
+    if (!ctx->prof) return;
+    ctx->prof_e0 = prof_event(ctx);
+    ctx->prof_name = name;
+    ctx->prof_work = s252_ctx::Work();
+    cudaEventRecord(ctx->prof_e0, ctx->stream);
+}
+static inline void prof_work(s252_ctx* ctx, double bytes, double muls, double perms) {
+    ctx->prof_work.bytes = bytes;
+    ctx->prof_work.muls = muls;
+    ctx->prof_work.perms = perms;
+}
+static inline void prof_end(s252_ctx* ctx) {
+    if (!ctx->prof || !ctx->prof_e0) return;
+    cudaEvent_t e1 = prof_event(ctx);
+    cudaEventRecord(e1, ctx->stream);
+    ctx->prof_pending.push_back({ctx->prof_name, ctx->prof_e0, e1, ctx->prof_work});
+    ctx->prof_e0 = nullptr;
+}
+static void prof_drain(s252_ctx* ctx) {
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& pnd : ctx->prof_pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, pnd.e0, pnd.e1) == cudaSuccess) {
+            auto& acc = ctx->prof_acc[pnd.name];
+            acc.launches += 1;
+            acc.ms += ms;
+            acc.w.bytes += pnd.w.bytes;
+            acc.w.muls += pnd.w.muls;
+            acc.w.perms += pnd.w.perms;
+        }
+        ctx->prof_free.push_back(pnd.e0);
+        ctx->prof_free.push_back(pnd.e1);
+    }
+    ctx->prof_pending.clear();
+}
 
 struct s252_commit {
     s252_ctx* ctx = nullptr;
@@ -72,6 +134,7 @@ struct s252_fri {
 #define LAUNCH_CHECK(ctx)           \
     do {                            \
         (ctx)->launches++;          \
+        prof_end(ctx);              \
         CU(ctx, cudaGetLastError()); \
     } while (0)
 
@@ -79,16 +142,52 @@ static inline bool is_pow2(size_t n) { return n && !(n & (n - 1)); }
 static inline unsigned ilog2(size_t n) { unsigned k = 0; while (((size_t)1 << k) < n) ++k; return k; }
 static inline size_t next_pow2(size_t n) { size_t r = 1; while (r < n) r <<= 1; return r; }
 
-template <typename T>
-static int dalloc(s252_ctx* ctx, T** p, size_t count) {
-    *p = nullptr;
-    if (count == 0) count = 1;
-    CU(ctx, cudaMallocAsync((void**)p, count * sizeof(T), ctx->stream));
+static void arena_trim(s252_ctx* ctx) {
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& kv : ctx->arena_free) {
+        cudaFree(kv.second);
+        ctx->arena_bytes -= kv.first;
+        ctx->arena_size.erase(kv.second);
+    }
+    ctx->arena_free.clear();
+}
+static int arena_alloc(s252_ctx* ctx, void** p, size_t bytes) {
+    bytes = (bytes + 511) & ~(size_t)511;
+    if (bytes == 0) bytes = 512;
+    auto it = ctx->arena_free.lower_bound(bytes);
+    if (it != ctx->arena_free.end() && it->first <= bytes + bytes / 8) {
+        *p = it->second;
+        ctx->arena_free.erase(it);
+        return S252_OK;
+    }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        arena_trim(ctx);
+        e = cudaMalloc(p, bytes);
+    }
+    if (e != cudaSuccess) {
+        char b[256];
+        std::snprintf(b, sizeof b, "cudaMalloc(%zu bytes): %s", bytes, cudaGetErrorString(e));
+        ctx->err = b;
+        cudaGetLastError();
+        return S252_ERR_CUDA;
+    }
+    ctx->arena_size[*p] = bytes;
+    ctx->arena_bytes += bytes;
     return S252_OK;
 }
 template <typename T>
+static int dalloc(s252_ctx* ctx, T** p, size_t count) {
+    *p = nullptr;
+    return arena_alloc(ctx, (void**)p, count * sizeof(T));
+}
+template <typename T>
 static void dfree(s252_ctx* ctx, T* p) {
-    if (p) cudaFreeAsync((void*)p, ctx->stream);
+    if (!p) return;
+    auto it = ctx->arena_size.find((void*)p);
+    if (it == ctx->arena_size.end()) return;
+    ctx->arena_free.emplace(it->second, (void*)p);
 }
 // RAII for temporaries
 template <typename T>
@@ -112,11 +211,6 @@ extern "C" int s252_ctx_create(int device, s252_ctx** out) {
     s252_ctx* ctx = new s252_ctx();
     ctx->device = device;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return S252_ERR_CUDA; }
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-        uint64_t thr = ~0ull;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-    }
     cudaFuncSetAttribute(s252::ntt_pass_strided, cudaFuncAttributeMaxDynamicSharedMemorySize, s252::NTT_TILE * 32);
     cudaFuncSetAttribute(s252::ntt_pass_final, cudaFuncAttributeMaxDynamicSharedMemorySize, s252::NTT_TILE * 32);
     if (const char* e = std::getenv("S252_MAX_LOGL")) {
@@ -130,6 +224,8 @@ extern "C" void s252_ctx_destroy(s252_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    arena_trim(ctx);
+    for (auto& kv : ctx->arena_size) cudaFree(kv.first);   // blocks still owned by live handles
     for (auto& kv : ctx->tables) cudaFree(kv.second);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -141,6 +237,39 @@ extern "C" int s252_ctx_synchronize(s252_ctx* ctx) {
 }
 extern "C" void* s252_ctx_stream(s252_ctx* ctx) { return (void*)ctx->stream; }
 extern "C" uint64_t s252_ctx_launch_count(const s252_ctx* ctx) { return ctx->launches; }
+extern "C" int s252_ctx_trim(s252_ctx* ctx) {
+    if (!ctx) return S252_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    arena_trim(ctx);
+    return S252_OK;
+}
+extern "C" int s252_ctx_profile(s252_ctx* ctx, int enable) {
+    if (!ctx) return S252_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    prof_drain(ctx);
+    ctx->prof = enable != 0;
+    if (enable == 2) ctx->prof_acc.clear();
+    return S252_OK;
+}
+extern "C" int s252_ctx_profile_read(s252_ctx* ctx, char* buf, size_t cap) {
+    if (!ctx || !buf || cap == 0) return S252_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    prof_drain(ctx);
+    std::string out = "{";
+    bool first = true;
+    for (auto& kv : ctx->prof_acc) {
+        char line[384];
+        std::snprintf(line, sizeof line, "%s\"%s\": {\"launches\": %llu, \"ms\": %.6f, \"bytes\": %.0f, \"muls\": %.0f, \"perms\": %.0f}",
+                      first ? "" : ", ", kv.first.c_str(), (unsigned long long)kv.second.launches, kv.second.ms,
+                      kv.second.w.bytes, kv.second.w.muls, kv.second.w.perms);
+        out += line;
+        first = false;
+    }
+    out += "}";
+    if (out.size() + 1 > cap) FAIL(ctx, S252_ERR_INVALID, "profile buffer too small (%zu needed)", out.size() + 1);
+    std::memcpy(buf, out.c_str(), out.size() + 1);
+    return S252_OK;
+}
 extern "C" int s252_device_alloc(s252_ctx* ctx, size_t bytes, void** out) {
     CU(ctx, cudaSetDevice(ctx->device));
     CU(ctx, cudaMalloc(out, bytes ? bytes : 1));
@@ -188,6 +317,7 @@ static int get_level_table(s252_ctx* ctx, unsigned logL, unsigned ncosets, const
     const size_t count = ((size_t)1 << logL) * ncosets;
     TRY(table_alloc(ctx, key, count, &t, &fresh));
     if (fresh) {
+        prof_begin(ctx, "gen_level_twiddles");
         s252::gen_level_twiddles<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(t, logL, ncosets, wL, shift, step);
         LAUNCH_CHECK(ctx);
     }
@@ -202,6 +332,7 @@ static int get_pass_table(s252_ctx* ctx, unsigned logL, unsigned logInner, unsig
     const size_t count = ((size_t)1 << (logL + logInner)) * ncosets;
     TRY(table_alloc(ctx, key, count, &t, &fresh));
     if (fresh) {
+        prof_begin(ctx, "gen_pass_twiddles");
         s252::gen_pass_twiddles<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(t, logL, logInner, ncosets, wS, shift, step, scale);
         LAUNCH_CHECK(ctx);
     }
@@ -213,6 +344,7 @@ static int get_power_table(s252_ctx* ctx, size_t n, const fe& base, const fe& sc
     fe* t; bool fresh;
     TRY(table_alloc(ctx, key, n, &t, &fresh));
     if (fresh) {
+        prof_begin(ctx, "gen_powers");
         s252::gen_powers<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(t, n, base, scale);
         LAUNCH_CHECK(ctx);
     }
@@ -273,6 +405,8 @@ static int run_ntt(s252_ctx* ctx, const Xform& X, const fe* in, size_t in_col_st
         P.logL = logn; P.logT = logT; P.logN1 = 0; P.logN2 = 0;
         P.lvl_per_coset = X.ncosets > 1; P.rows_are_cols = 1; P.in_lw = in_lw; P.out_lw = out_lw;
         const unsigned tiles = (ncols + (1u << logT) - 1) >> logT;
+        prof_begin(ctx, "ntt_pass_final");
+        prof_work(ctx, 32.0 * N * ncols * (1 + X.ncosets), 0.5 * N * logn * X.ncosets * ncols + (oscale ? (double)N * ncols : 0.0), 0);
         s252::ntt_pass_final<<<dim3(tiles * X.ncosets, 1), s252::NTT_THREADS, smem, ctx->stream>>>(P);
         LAUNCH_CHECK(ctx);
         return S252_OK;
@@ -308,6 +442,8 @@ static int run_ntt(s252_ctx* ctx, const Xform& X, const fe* in, size_t in_col_st
         P.logL = l1; P.logT = logT; P.logInner = logInner; P.logOuter = 0;
         P.lvl_per_coset = X.ncosets > 1; P.ptw_per_coset = X.ncosets > 1; P.rows_are_cols = 0; P.in_lw = 0; P.out_lw = 0;
         const size_t tiles = (size_t)1 << (logInner - logT);
+        prof_begin(ctx, "ntt_pass_strided");
+        prof_work(ctx, 32.0 * N * ncols * (1 + X.ncosets), (0.5 * l1 + 1.0) * N * X.ncosets * ncols, 0);
         s252::ntt_pass_strided<<<dim3((unsigned)(tiles * X.ncosets), ncols), s252::NTT_THREADS, smem, ctx->stream>>>(P);
         LAUNCH_CHECK(ctx);
     }
@@ -324,6 +460,8 @@ static int run_ntt(s252_ctx* ctx, const Xform& X, const fe* in, size_t in_col_st
         P.logL = l2; P.logT = logT; P.logInner = l3; P.logOuter = l1;
         P.lvl_per_coset = 0; P.ptw_per_coset = 0;
         const size_t tiles = (size_t)1 << (l1 + l3 - logT);
+        prof_begin(ctx, "ntt_pass_strided");
+        prof_work(ctx, 64.0 * N * ncols * X.ncosets, (0.5 * l2 + 1.0) * N * X.ncosets * ncols, 0);
         s252::ntt_pass_strided<<<dim3((unsigned)(tiles * X.ncosets), ncols), s252::NTT_THREADS, smem, ctx->stream>>>(P);
         LAUNCH_CHECK(ctx);
     }
@@ -339,6 +477,8 @@ static int run_ntt(s252_ctx* ctx, const Xform& X, const fe* in, size_t in_col_st
         P.logL = l3; P.logT = logT; P.logN1 = l1; P.logN2 = l2;
         P.lvl_per_coset = 0; P.ptw_per_coset = 0; P.rows_are_cols = 0; P.in_lw = 0; P.out_lw = out_lw;
         const size_t tiles = (size_t)1 << (l1 + l2 - logT);
+        prof_begin(ctx, "ntt_pass_final");
+        prof_work(ctx, 64.0 * N * ncols * X.ncosets, 0.5 * l3 * N * X.ncosets * ncols + (oscale ? (double)N * ncols : 0.0), 0);
         s252::ntt_pass_final<<<dim3((unsigned)(tiles * X.ncosets), ncols), s252::NTT_THREADS, smem, ctx->stream>>>(P);
         LAUNCH_CHECK(ctx);
     }
@@ -349,6 +489,8 @@ static int run_ntt(s252_ctx* ctx, const Xform& X, const fe* in, size_t in_col_st
 static int build_tree(s252_ctx* ctx, const fe* cols, size_t col_stride, unsigned ncols, size_t n_rows, uint64_t* nodes) {
     if (!is_pow2(n_rows)) FAIL(ctx, S252_ERR_INVALID, "merkle tree needs a power-of-two number of leaves (got %zu)", n_rows);
     const unsigned depth = ilog2(n_rows);
+    prof_begin(ctx, "merkle_leaves");
+    prof_work(ctx, 32.0 * n_rows * ncols + 32.0 * n_rows, 0.2 * n_rows * ncols, (double)n_rows * ((32 * ncols) / 136 + 1));
     s252::merkle_leaves<<<(unsigned)((n_rows + 127) / 128), 128, 0, ctx->stream>>>(cols, col_stride, ncols, n_rows,
                                                                                 nodes + 4 * (n_rows - 1));
     LAUNCH_CHECK(ctx);
@@ -357,6 +499,8 @@ static int build_tree(s252_ctx* ctx, const fe* cols, size_t col_stride, unsigned
         const unsigned levels = std::min<unsigned>(s252::MERKLE_FUSED_LEVELS, level);
         const size_t nchildren = (size_t)1 << level;
         const unsigned blocks = (unsigned)std::max<size_t>(1, nchildren / (2 * s252::MERKLE_BLOCK));
+        prof_begin(ctx, "merkle_nodes");
+        prof_work(ctx, 32.0 * nchildren + 32.0 * (nchildren - (nchildren >> levels)), 0, (double)(nchildren - (nchildren >> levels)));
         s252::merkle_nodes<<<blocks, s252::MERKLE_BLOCK, 0, ctx->stream>>>(nodes, level, levels);
         LAUNCH_CHECK(ctx);
         level -= levels;
@@ -370,6 +514,8 @@ static int build_tree_nodes(s252_ctx* ctx, size_t n_rows, uint64_t* nodes) {
         const unsigned levels = std::min<unsigned>(s252::MERKLE_FUSED_LEVELS, level);
         const size_t nchildren = (size_t)1 << level;
         const unsigned blocks = (unsigned)std::max<size_t>(1, nchildren / (2 * s252::MERKLE_BLOCK));
+        prof_begin(ctx, "merkle_nodes");
+        prof_work(ctx, 32.0 * nchildren + 32.0 * (nchildren - (nchildren >> levels)), 0, (double)(nchildren - (nchildren >> levels)));
         s252::merkle_nodes<<<blocks, s252::MERKLE_BLOCK, 0, ctx->stream>>>(nodes, level, levels);
         LAUNCH_CHECK(ctx);
         level -= levels;
@@ -392,6 +538,7 @@ static int stage_out(s252_ctx* ctx, const fe* dev_lw, s252_fe* dst, size_t count
     return S252_OK;
 }
 static int convert_lw_to_internal(s252_ctx* ctx, const fe* in, fe* out, size_t n) {
+    prof_begin(ctx, "lw_to_internal");
     s252::lw_to_internal<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(in, out, n);
     LAUNCH_CHECK(ctx);
     return S252_OK;
@@ -506,6 +653,7 @@ extern "C" int s252_evaluate_polynomial_on_lde_domain(s252_ctx* ctx, const s252_
         // prover.rs:118-122: evaluate on the larger domain and keep every step-th point
         TRY(dalloc(ctx, &full.p, len));
         TRY(evaluate_from_lw(ctx, din, n_coeffs, len, H::from_lw(offset->limbs), full.p, true));
+        prof_begin(ctx, "subsample");
         s252::subsample<<<(unsigned)((want + 255) / 256), 256, 0, ctx->stream>>>(full.p, dout, want, step);
         LAUNCH_CHECK(ctx);
     }
@@ -546,6 +694,8 @@ extern "C" int s252_interpolate_and_commit(s252_ctx* ctx, const s252_fe* trace, 
         TRY(stage_in(ctx, trace, N * c, mem, staged, &dtrace));
         // TraceTable::cols(): row-major LW -> column-major internal
         TRY(dalloc(ctx, &cols.p, N * c));
+        prof_begin(ctx, "rows_lw_to_cols");
+        prof_work(ctx, 64.0 * N * c, 0, 0);
         s252::rows_lw_to_cols<<<dim3((unsigned)((N + 31) / 32), (c + 31) / 32), 256, 0, ctx->stream>>>(dtrace, N, c, cols.p, N);
         LAUNCH_CHECK(ctx);
         // compute_trace_polys: interpolate_fft per column
@@ -617,6 +767,7 @@ extern "C" int s252_merkle_build(s252_ctx* ctx, const s252_fe* rows, size_t n_ro
         const fe* drows;
         TRY(stage_in(ctx, rows, n_rows * c, mem, staged, &drows));
         TRY(dalloc(ctx, &cm->lde, n_rows * c));
+        prof_begin(ctx, "rows_lw_to_cols");
         s252::rows_lw_to_cols<<<dim3((unsigned)((n_rows + 31) / 32), (c + 31) / 32), 256, 0, ctx->stream>>>(drows, n_rows, c, cm->lde, n_rows);
         LAUNCH_CHECK(ctx);
         TRY(dalloc(ctx, &cm->nodes, 4 * (2 * n_rows - 1)));
@@ -644,6 +795,7 @@ extern "C" int s252_commit_root(const s252_commit* c, uint8_t root[32]) {
 static int read_internal_as_lw(s252_ctx* ctx, const fe* src, size_t count, s252_fe* out) {
     Tmp<fe> tmp(ctx);
     TRY(dalloc(ctx, &tmp.p, count));
+    prof_begin(ctx, "internal_to_lw");
     s252::internal_to_lw<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(src, tmp.p, count);
     LAUNCH_CHECK(ctx);
     CU(ctx, cudaMemcpyAsync(out, tmp.p, count * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
@@ -684,12 +836,14 @@ static int open_common(s252_ctx* ctx, const fe* cols, size_t col_stride, unsigne
     CU(ctx, cudaMemcpyAsync(didx.p, indices, n_idx * 8, cudaMemcpyHostToDevice, ctx->stream));
     if (rows_out) {
         TRY(dalloc(ctx, &drows.p, n_idx * ncols));
+        prof_begin(ctx, "gather_rows");
         s252::gather_rows<<<(unsigned)((n_idx * ncols + 127) / 128), 128, 0, ctx->stream>>>(cols, col_stride, ncols, didx.p, (unsigned)n_idx, drows.p);
         LAUNCH_CHECK(ctx);
         CU(ctx, cudaMemcpyAsync(rows_out, drows.p, n_idx * ncols * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
     }
     if (paths_out && depth) {
         TRY(dalloc(ctx, &dpaths.p, n_idx * depth * 4));
+        prof_begin(ctx, "gather_paths");
         s252::gather_paths<<<(unsigned)((n_idx * depth + 127) / 128), 128, 0, ctx->stream>>>(nodes, depth, didx.p, (unsigned)n_idx, dpaths.p);
         LAUNCH_CHECK(ctx);
         CU(ctx, cudaMemcpyAsync(paths_out, dpaths.p, n_idx * depth * 32, cudaMemcpyDeviceToHost, ctx->stream));
@@ -766,6 +920,8 @@ extern "C" int s252_fri_commit_phase(s252_ctx* ctx, size_t number_layers, const 
             f->layers.push_back(nxt);
             FriLayerDev& L = f->layers.back();
             if (commit) TRY(dalloc(ctx, &L.nodes, 4 * (2 * half - 1)));
+            prof_begin(ctx, "fri_fold_commit");
+            prof_work(ctx, 32.0 * size + 32.0 * half + (commit ? 32.0 * half : 0.0), 3.2 * half, commit ? (double)half : 0.0);
             s252::fri_fold_commit<<<(unsigned)((half + 127) / 128), 128, 0, ctx->stream>>>(
                 f->layers[k - 1].evals, half, inv_tw, (unsigned long long)(domain_size / size), cfac, inv2, L.evals,
                 commit ? L.nodes + 4 * (half - 1) : nullptr);
@@ -789,6 +945,7 @@ extern "C" int s252_fri_commit_phase(s252_ctx* ctx, size_t number_layers, const 
             nxt.size = half;
             TRY(dalloc(ctx, &nxt.evals, half));
             f->layers.push_back(nxt);
+            prof_begin(ctx, "fri_fold_commit");
             s252::fri_fold_commit<<<(unsigned)((half + 127) / 128), 128, 0, ctx->stream>>>(
                 f->layers[0].evals, half, inv_tw, 1ull, cfac, inv2, f->layers.back().evals, nullptr);
             LAUNCH_CHECK(ctx);
@@ -887,6 +1044,7 @@ extern "C" int s252_generate_nonce_with_grinding(s252_ctx* ctx, const uint8_t ch
     while (base < limit) {
         const unsigned long long count = std::min<unsigned long long>(window, limit - base);
         CU(ctx, cudaMemsetAsync(best.p, 0xff, 8, ctx->stream));
+        prof_begin(ctx, "grind_kernel");
         s252::grind_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(lanes[0], lanes[1], lanes[2], lanes[3], base, count,
                                                                                    grinding_factor, best.p);
         LAUNCH_CHECK(ctx);
@@ -920,6 +1078,7 @@ extern "C" int s252_fe_binop(s252_ctx* ctx, int op, const s252_fe* a, const s252
     if (b) TRY(stage_in(ctx, b, n, mem, sb, &db));
     fe* dout = reinterpret_cast<fe*>(out);
     if (mem == S252_HOST) { TRY(dalloc(ctx, &so.p, n)); dout = so.p; }
+    prof_begin(ctx, "fe_binop_kernel");
     s252::fe_binop_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(op, da, db ? db : da, dout, n);
     LAUNCH_CHECK(ctx);
     TRY(stage_out(ctx, dout, out, n, mem));
@@ -932,6 +1091,7 @@ extern "C" int s252_keccak256_batch(s252_ctx* ctx, const uint8_t* msgs, size_t m
     TRY(dalloc(ctx, &dm.p, msg_len * n + 8));
     TRY(dalloc(ctx, &dd.p, 32 * n));
     if (msg_len * n) CU(ctx, cudaMemcpyAsync(dm.p, msgs, msg_len * n, cudaMemcpyHostToDevice, ctx->stream));
+    prof_begin(ctx, "keccak_bytes_kernel");
     s252::keccak_bytes_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(dm.p, msg_len, n, dd.p);
     LAUNCH_CHECK(ctx);
     CU(ctx, cudaMemcpyAsync(digests, dd.p, 32 * n, cudaMemcpyDeviceToHost, ctx->stream));
