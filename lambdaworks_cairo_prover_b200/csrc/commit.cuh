@@ -99,6 +99,62 @@ __device__ __forceinline__ void hash_pair(const uint64_t* __restrict__ children,
     out[0] = st[0]; out[1] = st[1]; out[2] = st[2]; out[3] = st[3];
 }
 
+__device__ __forceinline__ void hash_two(const uint64_t l[4], const uint64_t r[4], uint64_t out[4]) {
+    uint64_t st[25];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { st[k] = l[k]; st[4 + k] = r[k]; }
+#pragma unroll
+    for (int k = 8; k < 25; ++k) st[k] = 0;
+    st[8] ^= 0x01ULL;
+    st[16] ^= 0x8000000000000000ULL;
+    keccak_f1600(st);
+    out[0] = st[0]; out[1] = st[1]; out[2] = st[2]; out[3] = st[3];
+}
+__device__ __forceinline__ void store_digest(uint64_t* dst, const uint64_t d[4]) {
+    ulonglong2* q = reinterpret_cast<ulonglong2*>(dst);
+    q[0] = make_ulonglong2(d[0], d[1]);
+    q[1] = make_ulonglong2(d[2], d[3]);
+}
+// Wide levels: one thread builds a whole LV-level subtree (2^LV children -> 2^LV - 1 ancestors), so
+// every thread of the launch stays busy on every level (a per-level halving scheme idles 3/4 of
+// its warps).  LV levels per launch; digests of all intermediate levels are written to the heap.
+template <int LV>
+__global__ void __launch_bounds__(128) merkle_subtrees(uint64_t* __restrict__ nodes, unsigned child_level) {
+    const unsigned long long q = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= (1ull << (child_level - LV))) return;
+    const uint64_t* ch = nodes + 4 * (((1ull << child_level) - 1) + (q << LV));
+    uint64_t* l1 = nodes + 4 * (((1ull << (child_level - 1)) - 1) + (q << (LV - 1)));
+    if constexpr (LV == 1) {
+        uint64_t p[4];
+        hash_pair(ch, p);
+        store_digest(l1, p);
+    } else if constexpr (LV == 2) {
+        uint64_t p0[4], p1[4], g[4];
+        hash_pair(ch, p0);
+        hash_pair(ch + 8, p1);
+        store_digest(l1, p0);
+        store_digest(l1 + 4, p1);
+        hash_two(p0, p1, g);
+        store_digest(nodes + 4 * (((1ull << (child_level - 2)) - 1) + q), g);
+    } else {
+        uint64_t* l2 = nodes + 4 * (((1ull << (child_level - 2)) - 1) + (q << 1));
+        uint64_t g0[4], g1[4], t[4];
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            uint64_t p0[4], p1[4];
+            hash_pair(ch + 16 * half, p0);
+            hash_pair(ch + 16 * half + 8, p1);
+            store_digest(l1 + 8 * half, p0);
+            store_digest(l1 + 8 * half + 4, p1);
+            if (half == 0) hash_two(p0, p1, g0); else hash_two(p0, p1, g1);
+        }
+        store_digest(l2, g0);
+        store_digest(l2 + 4, g1);
+        hash_two(g0, g1, t);
+        store_digest(nodes + 4 * (((1ull << (child_level - 3)) - 1) + q), t);
+    }
+}
+
 // Builds up to MERKLE_FUSED_LEVELS levels above `child_level` (the level whose 2^child_level
 // digests already exist).  nodes: heap array of 4 x u64 digests.  Block b owns children
 // [b*2*BLOCK, (b+1)*2*BLOCK) of child_level and every ancestor that lies entirely above them.

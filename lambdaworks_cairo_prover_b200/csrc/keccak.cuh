@@ -32,10 +32,23 @@ __device__ __forceinline__ uint64_t rol64(uint64_t x, int n) {
     }
     return ((uint64_t)rhi << 32) | rlo;
 }
-__device__ __forceinline__ uint64_t xor5(uint64_t a, uint64_t b, uint64_t c, uint64_t d, uint64_t e) {
-    return a ^ b ^ c ^ d ^ e;
+
+__device__ __forceinline__ uint64_t xor3(uint64_t a, uint64_t b, uint64_t c) {
+    uint32_t lo, hi;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(lo) : "r"((uint32_t)a), "r"((uint32_t)b), "r"((uint32_t)c));
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(hi) : "r"((uint32_t)(a >> 32)), "r"((uint32_t)(b >> 32)), "r"((uint32_t)(c >> 32)));
+    return ((uint64_t)hi << 32) | lo;
 }
-__device__ __forceinline__ uint64_t chi(uint64_t a, uint64_t b, uint64_t c) { return a ^ (~b & c); }
+__device__ __forceinline__ uint64_t xor5(uint64_t a, uint64_t b, uint64_t c, uint64_t d, uint64_t e) {
+    return xor3(xor3(a, b, c), d, e);
+}
+__device__ __forceinline__ uint64_t chi(uint64_t a, uint64_t b, uint64_t c) {
+    // a ^ (~b & c): truth table 0xD2 with (a, b, c) as the three LOP3 inputs
+    uint32_t lo, hi;
+    asm("lop3.b32 %0, %1, %2, %3, 0xD2;" : "=r"(lo) : "r"((uint32_t)a), "r"((uint32_t)b), "r"((uint32_t)c));
+    asm("lop3.b32 %0, %1, %2, %3, 0xD2;" : "=r"(hi) : "r"((uint32_t)(a >> 32)), "r"((uint32_t)(b >> 32)), "r"((uint32_t)(c >> 32)));
+    return ((uint64_t)hi << 32) | lo;
+}
 
 __device__ __forceinline__ void keccak_f1600(uint64_t s[25]) {
 #pragma unroll 1
@@ -45,19 +58,23 @@ __device__ __forceinline__ void keccak_f1600(uint64_t s[25]) {
         uint64_t C2 = xor5(s[2], s[7], s[12], s[17], s[22]);
         uint64_t C3 = xor5(s[3], s[8], s[13], s[18], s[23]);
         uint64_t C4 = xor5(s[4], s[9], s[14], s[19], s[24]);
-        uint64_t D0 = C4 ^ rol64(C1, 1), D1 = C0 ^ rol64(C2, 1), D2 = C1 ^ rol64(C3, 1), D3 = C2 ^ rol64(C4, 1),
-                 D4 = C3 ^ rol64(C0, 1);
-        // theta + rho + pi: B[y][(2x+3y)%5] = rol(s[x][y] ^ D[x], r[x][y])
-        uint64_t B00 = s[0] ^ D0;
-        uint64_t B10 = rol64(s[1] ^ D1, 1), B20 = rol64(s[2] ^ D2, 62), B05 = rol64(s[3] ^ D3, 28), B15 = rol64(s[4] ^ D4, 27);
-        uint64_t B16 = rol64(s[5] ^ D0, 36), B01 = rol64(s[6] ^ D1, 44), B11 = rol64(s[7] ^ D2, 6), B21 = rol64(s[8] ^ D3, 55),
-                 B06 = rol64(s[9] ^ D4, 20);
-        uint64_t B07 = rol64(s[10] ^ D0, 3), B17 = rol64(s[11] ^ D1, 10), B02 = rol64(s[12] ^ D2, 43), B12 = rol64(s[13] ^ D3, 25),
-                 B22 = rol64(s[14] ^ D4, 39);
-        uint64_t B23 = rol64(s[15] ^ D0, 41), B08 = rol64(s[16] ^ D1, 45), B18 = rol64(s[17] ^ D2, 15), B03 = rol64(s[18] ^ D3, 21),
-                 B13 = rol64(s[19] ^ D4, 8);
-        uint64_t B14 = rol64(s[20] ^ D0, 18), B24 = rol64(s[21] ^ D1, 2), B09 = rol64(s[22] ^ D2, 61), B19 = rol64(s[23] ^ D3, 56),
-                 B04 = rol64(s[24] ^ D4, 14);
+        // theta folded into the rho/pi load: s ^ D[x] = s ^ C[x-1] ^ rol(C[x+1], 1) is ONE 3-input LOP3
+        // per 32-bit half (the five rotated columns R are shared by the 25 lanes).
+        const uint64_t R0 = rol64(C0, 1), R1 = rol64(C1, 1), R2 = rol64(C2, 1), R3 = rol64(C3, 1), R4 = rol64(C4, 1);
+#define S252_TH(i, Ca, Rb) xor3(s[i], Ca, Rb)
+        // theta + rho + pi: B[y][(2x+3y)%5] = rol(s[x][y] ^ D[x], r[x][y]),  D[x] = C[x-1] ^ R[x+1]
+        uint64_t B00 = S252_TH(0, C4, R1);
+        uint64_t B10 = rol64(S252_TH(1, C0, R2), 1), B20 = rol64(S252_TH(2, C1, R3), 62), B05 = rol64(S252_TH(3, C2, R4), 28),
+                 B15 = rol64(S252_TH(4, C3, R0), 27);
+        uint64_t B16 = rol64(S252_TH(5, C4, R1), 36), B01 = rol64(S252_TH(6, C0, R2), 44), B11 = rol64(S252_TH(7, C1, R3), 6),
+                 B21 = rol64(S252_TH(8, C2, R4), 55), B06 = rol64(S252_TH(9, C3, R0), 20);
+        uint64_t B07 = rol64(S252_TH(10, C4, R1), 3), B17 = rol64(S252_TH(11, C0, R2), 10), B02 = rol64(S252_TH(12, C1, R3), 43),
+                 B12 = rol64(S252_TH(13, C2, R4), 25), B22 = rol64(S252_TH(14, C3, R0), 39);
+        uint64_t B23 = rol64(S252_TH(15, C4, R1), 41), B08 = rol64(S252_TH(16, C0, R2), 45), B18 = rol64(S252_TH(17, C1, R3), 15),
+                 B03 = rol64(S252_TH(18, C2, R4), 21), B13 = rol64(S252_TH(19, C3, R0), 8);
+        uint64_t B14 = rol64(S252_TH(20, C4, R1), 18), B24 = rol64(S252_TH(21, C0, R2), 2), B09 = rol64(S252_TH(22, C1, R3), 61),
+                 B19 = rol64(S252_TH(23, C2, R4), 56), B04 = rol64(S252_TH(24, C3, R0), 14);
+#undef S252_TH
         // names above are B<index> with index = x' + 5*y' already; rows of five:
         // row 0: B00 B01 B02 B03 B04 ; row 1: B05 B06 B07 B08 B09 ; row 2: B10..B14 ; row 3: B15..B19 ; row 4: B20..B24
         s[0] = chi(B00, B01, B02) ^ KECCAK_RC[r];

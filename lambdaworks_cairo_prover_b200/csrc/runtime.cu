@@ -485,42 +485,44 @@ static int run_ntt(s252_ctx* ctx, const Xform& X, const fe* in, size_t in_col_st
     return S252_OK;
 }
 
+// Node levels of a tree whose 2^depth leaf digests are in place.  Wide levels go three at a time
+// through merkle_subtrees (every thread busy); the last MERKLE_TOP levels, where there is no
+// parallelism left to lose, are finished by one block.
+static const unsigned MERKLE_TOP = 9;
+static int build_tree_nodes(s252_ctx* ctx, size_t n_rows, uint64_t* nodes) {
+    unsigned level = ilog2(n_rows);
+    while (level > MERKLE_TOP) {
+        const unsigned lv = std::min(3u, level - MERKLE_TOP);
+        const size_t groups = (size_t)1 << (level - lv);
+        const unsigned blocks = (unsigned)((groups + 127) / 128);
+        const double parents = (double)((size_t)1 << level) - (double)groups;
+        prof_begin(ctx, "merkle_subtrees");
+        prof_work(ctx, 32.0 * ((size_t)1 << level) + 32.0 * parents, 0, parents);
+        if (lv == 3) s252::merkle_subtrees<3><<<blocks, 128, 0, ctx->stream>>>(nodes, level);
+        else if (lv == 2) s252::merkle_subtrees<2><<<blocks, 128, 0, ctx->stream>>>(nodes, level);
+        else s252::merkle_subtrees<1><<<blocks, 128, 0, ctx->stream>>>(nodes, level);
+        LAUNCH_CHECK(ctx);
+        level -= lv;
+    }
+    if (level > 0) {
+        const size_t nchildren = (size_t)1 << level;
+        prof_begin(ctx, "merkle_nodes");
+        prof_work(ctx, 64.0 * nchildren, 0, (double)(nchildren - 1));
+        s252::merkle_nodes<<<1, s252::MERKLE_BLOCK, 0, ctx->stream>>>(nodes, level, level);
+        LAUNCH_CHECK(ctx);
+    }
+    return S252_OK;
+}
+
 // Batched Merkle tree over `n_rows` rows of column-major `cols`.
 static int build_tree(s252_ctx* ctx, const fe* cols, size_t col_stride, unsigned ncols, size_t n_rows, uint64_t* nodes) {
     if (!is_pow2(n_rows)) FAIL(ctx, S252_ERR_INVALID, "merkle tree needs a power-of-two number of leaves (got %zu)", n_rows);
-    const unsigned depth = ilog2(n_rows);
     prof_begin(ctx, "merkle_leaves");
     prof_work(ctx, 32.0 * n_rows * ncols + 32.0 * n_rows, 0.2 * n_rows * ncols, (double)n_rows * ((32 * ncols) / 136 + 1));
     s252::merkle_leaves<<<(unsigned)((n_rows + 127) / 128), 128, 0, ctx->stream>>>(cols, col_stride, ncols, n_rows,
                                                                                 nodes + 4 * (n_rows - 1));
     LAUNCH_CHECK(ctx);
-    unsigned level = depth;
-    while (level > 0) {
-        const unsigned levels = std::min<unsigned>(s252::MERKLE_FUSED_LEVELS, level);
-        const size_t nchildren = (size_t)1 << level;
-        const unsigned blocks = (unsigned)std::max<size_t>(1, nchildren / (2 * s252::MERKLE_BLOCK));
-        prof_begin(ctx, "merkle_nodes");
-        prof_work(ctx, 32.0 * nchildren + 32.0 * (nchildren - (nchildren >> levels)), 0, (double)(nchildren - (nchildren >> levels)));
-        s252::merkle_nodes<<<blocks, s252::MERKLE_BLOCK, 0, ctx->stream>>>(nodes, level, levels);
-        LAUNCH_CHECK(ctx);
-        level -= levels;
-    }
-    return S252_OK;
-}
-// only the node levels (leaves already hashed)
-static int build_tree_nodes(s252_ctx* ctx, size_t n_rows, uint64_t* nodes) {
-    unsigned level = ilog2(n_rows);
-    while (level > 0) {
-        const unsigned levels = std::min<unsigned>(s252::MERKLE_FUSED_LEVELS, level);
-        const size_t nchildren = (size_t)1 << level;
-        const unsigned blocks = (unsigned)std::max<size_t>(1, nchildren / (2 * s252::MERKLE_BLOCK));
-        prof_begin(ctx, "merkle_nodes");
-        prof_work(ctx, 32.0 * nchildren + 32.0 * (nchildren - (nchildren >> levels)), 0, (double)(nchildren - (nchildren >> levels)));
-        s252::merkle_nodes<<<blocks, s252::MERKLE_BLOCK, 0, ctx->stream>>>(nodes, level, levels);
-        LAUNCH_CHECK(ctx);
-        level -= levels;
-    }
-    return S252_OK;
+    return build_tree_nodes(ctx, n_rows, nodes);
 }
 
 // Bring a caller buffer of `count` LW elements onto the device (no format change).
