@@ -1,0 +1,56 @@
+"""The C++ host layer (include/stark252_b200.hpp): compiles and links on CPU; on the GPU its
+results are compared with the oracle."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from lambdaworks_cairo_prover_b200 import _native as N
+from oracle import pyoracle as O
+
+SRC = os.path.join(ROOT, "tests", "cpp", "host_api_demo.cpp")
+EXE = os.path.join(ROOT, "tests", "cpp", "host_api_demo")
+
+
+def build_demo():
+    N.lib()
+    libdir = os.path.dirname(N.library_path())
+    if not os.path.exists(EXE) or os.path.getmtime(EXE) < max(os.path.getmtime(SRC), os.path.getmtime(N.library_path())):
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), SRC, "-o", EXE,
+                               "-L", libdir, "-lstark252_b200", "-Wl,-rpath," + libdir])
+    return EXE
+
+
+def test_cpp_layer_compiles_and_links():
+    exe = build_demo()
+    out = subprocess.run([exe, "--link-only"], capture_output=True, text=True, check=True).stdout
+    assert out.strip() == "len 16"
+
+
+@pytest.mark.gpu
+def test_cpp_layer_matches_oracle():
+    exe = build_demo()
+    res = subprocess.run([exe], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    got = dict(line.split(" ", 1) for line in res.stdout.strip().splitlines())
+    n, c, blowup = 16, 3, 4
+    M64 = 2**64 - 1
+    trace = np.zeros((n * c, 4), dtype=np.uint64)
+    for i in range(n * c):
+        trace[i, 0] = ((0x0123456789abcdef ^ ((i * 0x9e3779b97f4a7c15 & M64) >> 8))) & ((1 << 59) - 1)
+        trace[i, 1] = (i * 0xbf58476d1ce4e5b9) & M64
+        trace[i, 2] = (~i) & M64
+        trace[i, 3] = i + 7
+    want = O.interpolate_and_commit(trace.reshape(n, c, 4), blowup, 3)
+    assert got["root"] == want["root"].hex()
+    assert got["lde_1_5"] == "".join("%016x" % int(x) for x in want["lde"][1][5])
+    assert got["path0"] == O.merkle_path(want["nodes"], 9)[0].tobytes().hex()
+    assert got["none"] == "1" and got["fft_error"] == "1"
+    t = O.Transcript()
+    t.append(want["root"])
+    last, roots, _, _ = O.fri_commit_phase(4, want["coeffs"][2], t, trace[0], n * blowup)
+    assert got["fri_last"] == "".join("%016x" % int(x) for x in last)
+    assert got["fri_root3"] == roots[3].tobytes().hex()
+    assert int(got["nonce"]) == O.generate_nonce_with_grinding(t.challenge(), 9)
