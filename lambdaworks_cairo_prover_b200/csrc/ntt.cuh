@@ -85,9 +85,13 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_strided(NttPass P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     fe* sm = reinterpret_cast<fe*>(smem_raw);
     const unsigned L = 1u << P.logL, T = 1u << P.logT;
-    const unsigned coset = blockIdx.x % P.ncosets;
-    const unsigned tile = blockIdx.x / P.ncosets;
-    const unsigned col = blockIdx.y;
+    // block order: column fastest, then coset, then tile -- the blocks that share an inter-pass
+    // twiddle slice (same tile and coset, different columns) run together, so the slice is read from
+    // HBM once and served from L2 to the other columns
+    const unsigned col = blockIdx.x % P.ncols;
+    const unsigned rest = blockIdx.x / P.ncols;
+    const unsigned coset = rest % P.ncosets;
+    const unsigned tile = rest / P.ncosets;
     const unsigned tiles_per_outer = 1u << (P.logInner - P.logT);
     const unsigned long long o = tile / tiles_per_outer;
     const unsigned long long i0 = (unsigned long long)(tile % tiles_per_outer) << P.logT;
@@ -116,13 +120,15 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_final(NttPass P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     fe* sm = reinterpret_cast<fe*>(smem_raw);
     const unsigned L = 1u << P.logL, T = 1u << P.logT;
-    const unsigned coset = blockIdx.x % P.ncosets;
-    const unsigned tile = blockIdx.x / P.ncosets;
+    unsigned bid = blockIdx.x, col0 = 0;
+    if (!P.rows_are_cols) { col0 = bid % P.ncols; bid /= P.ncols; }
+    const unsigned coset = bid % P.ncosets;
+    const unsigned tile = bid / P.ncosets;
     const unsigned n = L << P.logT;
     unsigned long long out_base;     // natural output index of (row t = 0, k = 0)
     const fe* in;
     fe* out;
-    unsigned col0 = blockIdx.y, live = T;     // live: rows of the tile that exist
+    unsigned live = T;     // live: rows of the tile that exist
     if (P.rows_are_cols) {
         col0 = tile << P.logT;
         live = min(T, P.ncols - col0);

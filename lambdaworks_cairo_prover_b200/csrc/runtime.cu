@@ -444,7 +444,7 @@ static int run_ntt(s252_ctx* ctx, const Xform& X, const fe* in, size_t in_col_st
         const size_t tiles = (size_t)1 << (logInner - logT);
         prof_begin(ctx, "ntt_pass_strided");
         prof_work(ctx, 32.0 * N * ncols * (1 + X.ncosets), (0.5 * l1 + 1.0) * N * X.ncosets * ncols, 0);
-        s252::ntt_pass_strided<<<dim3((unsigned)(tiles * X.ncosets), ncols), s252::NTT_THREADS, smem, ctx->stream>>>(P);
+        s252::ntt_pass_strided<<<(unsigned)(tiles * X.ncosets * ncols), s252::NTT_THREADS, smem, ctx->stream>>>(P);
         LAUNCH_CHECK(ctx);
     }
     if (npass == 3) {
@@ -462,7 +462,7 @@ static int run_ntt(s252_ctx* ctx, const Xform& X, const fe* in, size_t in_col_st
         const size_t tiles = (size_t)1 << (l1 + l3 - logT);
         prof_begin(ctx, "ntt_pass_strided");
         prof_work(ctx, 64.0 * N * ncols * X.ncosets, (0.5 * l2 + 1.0) * N * X.ncosets * ncols, 0);
-        s252::ntt_pass_strided<<<dim3((unsigned)(tiles * X.ncosets), ncols), s252::NTT_THREADS, smem, ctx->stream>>>(P);
+        s252::ntt_pass_strided<<<(unsigned)(tiles * X.ncosets * ncols), s252::NTT_THREADS, smem, ctx->stream>>>(P);
         LAUNCH_CHECK(ctx);
     }
     {
@@ -479,7 +479,7 @@ static int run_ntt(s252_ctx* ctx, const Xform& X, const fe* in, size_t in_col_st
         const size_t tiles = (size_t)1 << (l1 + l2 - logT);
         prof_begin(ctx, "ntt_pass_final");
         prof_work(ctx, 64.0 * N * ncols * X.ncosets, 0.5 * l3 * N * X.ncosets * ncols + (oscale ? (double)N * ncols : 0.0), 0);
-        s252::ntt_pass_final<<<dim3((unsigned)(tiles * X.ncosets), ncols), s252::NTT_THREADS, smem, ctx->stream>>>(P);
+        s252::ntt_pass_final<<<(unsigned)(tiles * X.ncosets * ncols), s252::NTT_THREADS, smem, ctx->stream>>>(P);
         LAUNCH_CHECK(ctx);
     }
     return S252_OK;
