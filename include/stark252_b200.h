@@ -99,6 +99,16 @@ int s252_evaluate_polynomial_on_lde_domain(s252_ctx *ctx, const s252_fe *coeffs,
  * batch_commit (prover.rs:96-104); the caller appends `root` to its transcript (prover.rs:151). */
 int s252_interpolate_and_commit(s252_ctx *ctx, const s252_fe *trace, size_t n_rows, size_t n_cols, size_t blowup,
                                 uint64_t coset_offset, int mem, s252_commit **out, uint8_t root[32]);
+/* The first two steps of interpolate_and_commit only (compute_trace_polys, trace.rs:104, and
+ * compute_lde_trace_evaluations, prover.rs:161-185): the handle holds coefficients and LDE columns
+ * but no tree.  One rank of a column-sharded commit calls this on its columns. */
+int s252_interpolate_and_lde(s252_ctx *ctx, const s252_fe *trace, size_t n_rows, size_t n_cols, size_t blowup,
+                             uint64_t coset_offset, int mem, s252_commit **out);
+/* batch_commit (prover.rs:96-104) over column-major columns already resident on this device in the
+ * library's internal element format (cols[j*col_stride + i], as returned by
+ * s252_commit_device_lde): e.g. a row block assembled from the LDE shards of several GPUs. */
+int s252_commit_device_columns(s252_ctx *ctx, const void *cols, size_t col_stride, size_t n_cols, size_t n_rows,
+                               s252_commit **out, uint8_t root[32]);
 /* Round 2 (src/starks/prover.rs:254-276): evaluate_polynomial_on_lde_domain for each of n_polys
  * polynomials (polys: n_polys x n_coeffs, polynomial-major; n_coeffs <= domain_size) and
  * batch_commit over the zipped rows. */
@@ -156,6 +166,9 @@ int s252_fri_query(s252_fri *f, const uint64_t *iotas, size_t n_queries, s252_fe
  * Returns the SMALLEST nonce; S252_ERR_NOT_FOUND if none below `limit` (0 = 2^64-1). */
 int s252_generate_nonce_with_grinding(s252_ctx *ctx, const uint8_t challenge[32], uint8_t grinding_factor,
                                       uint64_t limit, uint64_t *nonce);
+
+/* Keccak256 on the host (node rule of the Merkle back-ends: Keccak256(left || right)). */
+void s252_keccak256(const uint8_t *data, size_t len, uint8_t out[32]);
 
 /* ---- transcript (host) -------------------------------------------------------------------------- */
 /* DefaultTranscript (lambdaworks-crypto) and the helpers of src/starks/transcript.rs:13-51 */

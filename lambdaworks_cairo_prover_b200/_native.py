@@ -36,6 +36,8 @@ SIGNATURES = {
     "s252_evaluate_offset_fft": (_i, [_vp, _vp, _sz, _sz, _sz, _vp, _vp, _sz, _i]),
     "s252_evaluate_polynomial_on_lde_domain": (_i, [_vp, _vp, _sz, _sz, _sz, _vp, _vp, _i]),
     "s252_interpolate_and_commit": (_i, [_vp, _vp, _sz, _sz, _sz, _u64, _i, C.POINTER(_vp), _vp]),
+    "s252_interpolate_and_lde": (_i, [_vp, _vp, _sz, _sz, _sz, _u64, _i, C.POINTER(_vp)]),
+    "s252_commit_device_columns": (_i, [_vp, _vp, _sz, _sz, _sz, C.POINTER(_vp), _vp]),
     "s252_lde_and_commit": (_i, [_vp, _vp, _sz, _sz, _sz, _sz, _u64, _i, C.POINTER(_vp), _vp]),
     "s252_merkle_build": (_i, [_vp, _vp, _sz, _sz, _i, C.POINTER(_vp), _vp]),
     "s252_commit_destroy": (None, [_vp]),
@@ -57,6 +59,7 @@ SIGNATURES = {
     "s252_fri_read_nodes": (_i, [_vp, _sz, _sz, _sz, _vp]),
     "s252_fri_query": (_i, [_vp, _vp, _sz, _vp, _vp, _vp, _vp, _sz]),
     "s252_generate_nonce_with_grinding": (_i, [_vp, _vp, _u8, _u64, C.POINTER(_u64)]),
+    "s252_keccak256": (None, [_vp, _sz, _vp]),
     "s252_transcript_new": (_vp, []),
     "s252_transcript_free": (None, [_vp]),
     "s252_transcript_append": (None, [_vp, _vp, _sz]),

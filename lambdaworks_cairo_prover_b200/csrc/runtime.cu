@@ -678,9 +678,12 @@ static int fetch_root(s252_ctx* ctx, const uint64_t* nodes, uint8_t root[32]) {
     return S252_OK;
 }
 
-extern "C" int s252_interpolate_and_commit(s252_ctx* ctx, const s252_fe* trace, size_t n_rows, size_t n_cols, size_t blowup,
-                                           uint64_t coset_offset, int mem, s252_commit** out, uint8_t root[32]) {
-    if (!ctx || !trace || !out || !root) return S252_ERR_INVALID;
+// compute_trace_polys + compute_lde_trace_evaluations of interpolate_and_commit; with_tree adds
+// batch_commit.  Without the tree the handle is what one rank of a column-sharded commit holds
+// before the exchange (DESIGN.md "multi-GPU").
+static int interpolate_lde_impl(s252_ctx* ctx, const s252_fe* trace, size_t n_rows, size_t n_cols, size_t blowup,
+                                uint64_t coset_offset, int mem, bool with_tree, s252_commit** out, uint8_t root[32]) {
+    if (!ctx || !trace || !out || (with_tree && !root)) return S252_ERR_INVALID;
     *out = nullptr;
     CU(ctx, cudaSetDevice(ctx->device));
     if (!is_pow2(n_rows) || n_cols == 0) FAIL(ctx, S252_ERR_INVALID, "FFTError: trace length %zu is not a power of two", n_rows);
@@ -709,9 +712,46 @@ extern "C" int s252_interpolate_and_commit(s252_ctx* ctx, const s252_fe* trace, 
         // compute_lde_trace_evaluations: evaluate_offset_fft(blowup, Some(N), h) per column
         TRY(dalloc(ctx, &cm->lde, M * c));
         TRY(evaluate_cosets(ctx, cm->coeffs, N, false, ilog2(N), (unsigned)blowup, H::from_u64(coset_offset), cm->lde, M, false, c));
-        // batch_commit over the rows of the LDE table
-        TRY(dalloc(ctx, &cm->nodes, 4 * (2 * M - 1)));
-        TRY(build_tree(ctx, cm->lde, M, c, M, cm->nodes));
+        if (with_tree) {
+            // batch_commit over the rows of the LDE table
+            TRY(dalloc(ctx, &cm->nodes, 4 * (2 * M - 1)));
+            TRY(build_tree(ctx, cm->lde, M, c, M, cm->nodes));
+            TRY(fetch_root(ctx, cm->nodes, root));
+        } else {
+            CU(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+        return S252_OK;
+    }();
+    if (rc != S252_OK) { commit_free(cm); return rc; }
+    *out = cm;
+    return S252_OK;
+}
+extern "C" int s252_interpolate_and_commit(s252_ctx* ctx, const s252_fe* trace, size_t n_rows, size_t n_cols, size_t blowup,
+                                           uint64_t coset_offset, int mem, s252_commit** out, uint8_t root[32]) {
+    return interpolate_lde_impl(ctx, trace, n_rows, n_cols, blowup, coset_offset, mem, true, out, root);
+}
+extern "C" int s252_interpolate_and_lde(s252_ctx* ctx, const s252_fe* trace, size_t n_rows, size_t n_cols, size_t blowup,
+                                        uint64_t coset_offset, int mem, s252_commit** out) {
+    return interpolate_lde_impl(ctx, trace, n_rows, n_cols, blowup, coset_offset, mem, false, out, nullptr);
+}
+// batch_commit over column-major columns that are already on this device in the library's internal
+// element format (e.g. a row block assembled from the LDE shards of several GPUs).  The columns
+// are copied into the handle.
+extern "C" int s252_commit_device_columns(s252_ctx* ctx, const void* cols, size_t col_stride, size_t n_cols, size_t n_rows,
+                                          s252_commit** out, uint8_t root[32]) {
+    if (!ctx || !cols || !out || !root) return S252_ERR_INVALID;
+    *out = nullptr;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (!is_pow2(n_rows) || n_cols == 0 || col_stride < n_rows)
+        FAIL(ctx, S252_ERR_INVALID, "merkle tree needs a power-of-two number of leaves (got %zu)", n_rows);
+    s252_commit* cm = new s252_commit();
+    cm->ctx = ctx; cm->n_cols = n_cols; cm->n_rows = n_rows; cm->n_coeffs = 0;
+    int rc = [&]() -> int {
+        TRY(dalloc(ctx, &cm->lde, n_rows * n_cols));
+        CU(ctx, cudaMemcpy2DAsync(cm->lde, n_rows * sizeof(fe), cols, col_stride * sizeof(fe), n_rows * sizeof(fe), n_cols,
+                                  cudaMemcpyDeviceToDevice, ctx->stream));
+        TRY(dalloc(ctx, &cm->nodes, 4 * (2 * n_rows - 1)));
+        TRY(build_tree(ctx, cm->lde, n_rows, (unsigned)n_cols, n_rows, cm->nodes));
         TRY(fetch_root(ctx, cm->nodes, root));
         return S252_OK;
     }();
@@ -792,6 +832,7 @@ extern "C" size_t s252_commit_n_coeffs(const s252_commit* c) { return c->n_coeff
 extern "C" int s252_commit_root(const s252_commit* c, uint8_t root[32]) {
     s252_ctx* ctx = c->ctx;
     CU(ctx, cudaSetDevice(ctx->device));
+    if (!c->nodes) FAIL(ctx, S252_ERR_INVALID, "this handle has no Merkle tree");
     return fetch_root(ctx, c->nodes, root);
 }
 static int read_internal_as_lw(s252_ctx* ctx, const fe* src, size_t count, s252_fe* out) {
@@ -820,7 +861,7 @@ extern "C" int s252_commit_read_coeffs(s252_commit* c, size_t col, s252_fe* out)
 extern "C" int s252_commit_read_nodes(s252_commit* c, size_t first, size_t count, uint8_t* out) {
     s252_ctx* ctx = c->ctx;
     CU(ctx, cudaSetDevice(ctx->device));
-    if (first + count > 2 * c->n_rows - 1) FAIL(ctx, S252_ERR_RANGE, "node read out of range");
+    if (!c->nodes || first + count > 2 * c->n_rows - 1) FAIL(ctx, S252_ERR_RANGE, "node read out of range");
     CU(ctx, cudaMemcpyAsync(out, c->nodes + 4 * first, count * 32, cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     return S252_OK;
@@ -857,6 +898,7 @@ extern "C" int s252_commit_open(s252_commit* c, const uint64_t* indices, size_t 
     s252_ctx* ctx = c->ctx;
     CU(ctx, cudaSetDevice(ctx->device));
     if (!indices && n_idx) return S252_ERR_INVALID;
+    if (paths_out && !c->nodes) FAIL(ctx, S252_ERR_INVALID, "this handle has no Merkle tree");
     return open_common(ctx, c->lde, c->n_rows, (unsigned)c->n_cols, c->nodes, c->n_rows, indices, n_idx, rows_out, paths_out);
 }
 extern "C" const void* s252_commit_device_lde(const s252_commit* c) { return c->lde; }
@@ -1058,6 +1100,14 @@ extern "C" int s252_generate_nonce_with_grinding(s252_ctx* ctx, const uint8_t ch
         if (window < (1ull << 26)) window <<= 2;
     }
     FAIL(ctx, S252_ERR_NOT_FOUND, "nonce not found below %llu", (unsigned long long)limit);
+}
+
+// --------------------------------------------------------------------------------------------
+// host Keccak-256 (a few digests: the top levels above per-GPU subtree roots)
+extern "C" void s252_keccak256(const uint8_t* data, size_t len, uint8_t out[32]) {
+    H::Keccak256 k;
+    k.update(data, len);
+    k.finalize(out);
 }
 
 // --------------------------------------------------------------------------------------------

@@ -1,0 +1,63 @@
+"""Column-sharded commit (lambdaworks_cairo_prover_b200/distributed.py): world_size-2 and -4 gloo runs on CPU
+for the sharding logic, and an NCCL run on real GPUs when at least two are visible."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+from lambdaworks_cairo_prover_b200.distributed import build_top, column_shards
+
+WORKER = os.path.join(ROOT, "tests", "dist_worker.py")
+
+
+def free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def launch(mode, world, logn, n_cols, blowup, timeout=600):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", str(free_port()), WORKER, mode, str(logn), str(n_cols), str(blowup)]
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    assert "DIST_OK" in res.stdout
+    return res.stdout
+
+
+def test_column_shards_match_the_survey_split():
+    assert [b - a for a, b in column_shards(33, 8)] == [5, 4, 4, 4, 4, 4, 4, 4]
+    assert column_shards(34, 2) == [(0, 17), (17, 34)]
+    assert [b - a for a, b in column_shards(2, 2)] == [1, 1]
+    assert sum(b - a for a, b in column_shards(52, 4)) == 52
+
+
+def test_build_top_is_the_heap_rule():
+    from oracle import pyoracle as O
+    leaves = [bytes([i]) * 32 for i in range(4)]
+    top = build_top(leaves, O.keccak256)
+    assert top[3:] == leaves
+    assert top[1] == O.keccak256(leaves[0] + leaves[1]) and top[2] == O.keccak256(leaves[2] + leaves[3])
+    assert top[0] == O.keccak256(top[1] + top[2])
+
+
+@pytest.mark.parametrize("world,logn,n_cols,blowup", [(2, 6, 5, 4), (4, 5, 7, 2), (2, 4, 2, 8)])
+def test_sharded_commit_gloo(world, logn, n_cols, blowup):
+    launch("gloo", world, logn, n_cols, blowup)
+
+
+@pytest.mark.gpu
+def test_sharded_commit_nccl():
+    import torch
+    g = torch.cuda.device_count()
+    if g < 2:
+        pytest.skip("needs at least two GPUs")
+    world = 4 if g >= 4 else 2
+    launch("nccl", world, 12, 33, 8)
+    launch("nccl", 2, 10, 3, 4)
