@@ -72,6 +72,12 @@ int s252_device_alloc(s252_ctx *ctx, size_t bytes, void **out);
 int s252_device_free(s252_ctx *ctx, void *ptr);
 int s252_copy_to_device(s252_ctx *ctx, void *dst, const void *src, size_t bytes);
 int s252_copy_to_host(s252_ctx *ctx, void *dst, const void *src, size_t bytes);
+/* Prefetch of the NEXT trace while the current one is being committed: the copy is queued on a
+ * second stream and returns at once (pinned host memory gives a true asynchronous DMA);
+ * s252_copy_stream_wait makes all later work on the compute stream wait for the prefetches issued
+ * so far.  dst must not be read or written by work already queued on the compute stream. */
+int s252_copy_to_device_async(s252_ctx *ctx, void *dst, const void *src, size_t bytes);
+int s252_copy_stream_wait(s252_ctx *ctx);
 
 /* ---- FFTPoly: fine-grained entry points ------------------------------------------------ */
 /* Polynomial::interpolate_fft(evals)                       -- call site src/starks/trace.rs:107

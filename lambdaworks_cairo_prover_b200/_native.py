@@ -30,6 +30,8 @@ SIGNATURES = {
     "s252_device_free": (_i, [_vp, _vp]),
     "s252_copy_to_device": (_i, [_vp, _vp, _vp, _sz]),
     "s252_copy_to_host": (_i, [_vp, _vp, _vp, _sz]),
+    "s252_copy_to_device_async": (_i, [_vp, _vp, _vp, _sz]),
+    "s252_copy_stream_wait": (_i, [_vp]),
     "s252_interpolate_fft": (_i, [_vp, _vp, _sz, _vp, _i]),
     "s252_interpolate_offset_fft": (_i, [_vp, _vp, _sz, _vp, _vp, _i]),
     "s252_evaluate_offset_fft_len": (_sz, [_sz, _sz, _sz]),
@@ -185,6 +187,13 @@ class Context:
     def to_device(self, dptr, arr):
         arr = np.ascontiguousarray(arr)
         self.check(lib().s252_copy_to_device(self.handle, C.c_void_p(dptr), ptr(arr), arr.nbytes))
+
+    def to_device_async(self, dptr, host_ptr, nbytes):
+        """Prefetch on the copy stream (host_ptr: address of pinned host memory)."""
+        self.check(lib().s252_copy_to_device_async(self.handle, C.c_void_p(dptr), C.c_void_p(host_ptr), nbytes))
+
+    def copy_stream_wait(self):
+        self.check(lib().s252_copy_stream_wait(self.handle))
 
     def to_host(self, arr, dptr):
         self.check(lib().s252_copy_to_host(self.handle, ptr(arr), C.c_void_p(dptr), arr.nbytes))

@@ -38,7 +38,7 @@ def build(force=False, verbose=False):
         "-shared", "-Xcompiler", "-fPIC", "-cudart", "static",
         "-ccbin", shutil.which("g++") or "g++",
         "-o", SO,
-    ] + [os.path.join(CSRC, s) for s in SOURCES]
+    ] + os.environ.get("S252_NVCC_FLAGS", "").split() + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))

@@ -64,47 +64,12 @@ __device__ __forceinline__ void mad_row4_nc(uint32_t* acc, const uint32_t* a, ui
         : "r"(a[0]), "r"(a[2]), "r"(a[4]), "r"(a[6]), "r"(b));
 }
 
-// Montgomery product a*b/R mod p, lazily reduced.
-// Requires (a/p)*(b/p) <= 31 (e.g. a < 31p with a fully reduced twiddle b); returns a value < 2p.
-__device__ __forceinline__ fe fe_mul(const fe& a, const fe& b) {
-    // E collects 64-bit products that start on even limbs, O those that start on odd limbs
-    // (O[k] has weight 2^(32(k+1))).  The constants preloaded into E are the "+p" and "+1" terms of
-    // the two reduction steps (see below); they sit on limbs no product row uses as a carry sink
-    // in a way that could overflow.
-    uint32_t E[17] = {0, 0, 0, 0, 0, 0, S252_P6 + 1u, S252_P7, 1u, 0, 0, 0, S252_P6, S252_P7, 0, 0, 0};
-    uint32_t O[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-    for (int i = 0; i < 8; i += 2) {
-        mad_row4(&E[i], &a.l[0], b.l[i]);          // even a * b_i      -> limbs i, i+2, ..
-        mad_row4(&O[i], &a.l[1], b.l[i]);          // odd  a * b_i      -> limbs i+1, ..
-        mad_row4(&O[i], &a.l[0], b.l[i + 1]);      // even a * b_(i+1)  -> limbs i+1, ..
-        if (i < 6) mad_row4(&E[i + 2], &a.l[1], b.l[i + 1]);   // odd a * b_(i+1) -> limbs i+2, ..
-        else       mad_row4_nc(&E[i + 2], &a.l[1], b.l[i + 1]); // top row: no carry out of 2^512
-    }
-    // T = E + (O << 32): one 16-limb carry chain.
-    uint32_t T[16];
-    T[0] = E[0];
-    asm("add.cc.u32  %0, %15, %30;\n\t"
-        "addc.cc.u32 %1, %16, %31;\n\t"
-        "addc.cc.u32 %2, %17, %32;\n\t"
-        "addc.cc.u32 %3, %18, %33;\n\t"
-        "addc.cc.u32 %4, %19, %34;\n\t"
-        "addc.cc.u32 %5, %20, %35;\n\t"
-        "addc.cc.u32 %6, %21, %36;\n\t"
-        "addc.cc.u32 %7, %22, %37;\n\t"
-        "addc.cc.u32 %8, %23, %38;\n\t"
-        "addc.cc.u32 %9, %24, %39;\n\t"
-        "addc.cc.u32 %10, %25, %40;\n\t"
-        "addc.cc.u32 %11, %26, %41;\n\t"
-        "addc.cc.u32 %12, %27, %42;\n\t"
-        "addc.cc.u32 %13, %28, %43;\n\t"
-        "addc.u32    %14, %29, %44;"
-        : "=r"(T[1]), "=r"(T[2]), "=r"(T[3]), "=r"(T[4]), "=r"(T[5]), "=r"(T[6]), "=r"(T[7]), "=r"(T[8]),
-          "=r"(T[9]), "=r"(T[10]), "=r"(T[11]), "=r"(T[12]), "=r"(T[13]), "=r"(T[14]), "=r"(T[15])
-        : "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(E[8]), "r"(E[9]),
-          "r"(E[10]), "r"(E[11]), "r"(E[12]), "r"(E[13]), "r"(E[14]), "r"(E[15]),
-          "r"(O[0]), "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]), "r"(O[7]), "r"(O[8]),
-          "r"(O[9]), "r"(O[10]), "r"(O[11]), "r"(O[12]), "r"(O[13]), "r"(O[14]));
+// Montgomery reduction of a 512-bit value T (16 limbs) that ALREADY CONTAINS the constants
+//   2^192*(2^59+17+1)  (limbs 6,7: +0x12, +0x08000000)   the "+p" and "+1" of the 192-bit step
+//   2^256              (limb 8: +1)                        the "+1" of the 64-bit step
+//   2^384*(2^59+17)    (limbs 12,13)                      its "+p"
+// Returns (T_without_constants + multiples of p) / 2^256, a value < 2p when T < 31 p^2.
+__device__ __forceinline__ fe mont_reduce(uint32_t T[16]) {
     // Reduction step 1 (192-bit digit).  With n = ~T[0..5]:  T + (n+1)*p  has its low 192 bits
     // equal to 2^192 exactly (carry 1 -> preloaded into limb 6) and gains (n+1)*(2^59+17) at
     // limb 6; the "+1" copy of (2^59+17) was preloaded too, so only n*(2^59+17) is added here.
@@ -186,6 +151,50 @@ __device__ __forceinline__ fe fe_mul(const fe& a, const fe& b) {
     return r;
 }
 
+// Montgomery product a*b/R mod p, lazily reduced.
+// Requires (a/p)*(b/p) <= 31 (e.g. a < 31p with a fully reduced twiddle b); returns a value < 2p.
+__device__ __forceinline__ fe fe_mul(const fe& a, const fe& b) {
+    // E collects 64-bit products that start on even limbs, O those that start on odd limbs
+    // (O[k] has weight 2^(32(k+1))).  The constants preloaded into E are the "+p" and "+1" terms of
+    // the two reduction steps (see below); they sit on limbs no product row uses as a carry sink
+    // in a way that could overflow.
+    uint32_t E[17] = {0, 0, 0, 0, 0, 0, S252_P6 + 1u, S252_P7, 1u, 0, 0, 0, S252_P6, S252_P7, 0, 0, 0};
+    uint32_t O[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+        mad_row4(&E[i], &a.l[0], b.l[i]);          // even a * b_i      -> limbs i, i+2, ..
+        mad_row4(&O[i], &a.l[1], b.l[i]);          // odd  a * b_i      -> limbs i+1, ..
+        mad_row4(&O[i], &a.l[0], b.l[i + 1]);      // even a * b_(i+1)  -> limbs i+1, ..
+        if (i < 6) mad_row4(&E[i + 2], &a.l[1], b.l[i + 1]);   // odd a * b_(i+1) -> limbs i+2, ..
+        else       mad_row4_nc(&E[i + 2], &a.l[1], b.l[i + 1]); // top row: no carry out of 2^512
+    }
+    // T = E + (O << 32): one 16-limb carry chain.
+    uint32_t T[16];
+    T[0] = E[0];
+    asm("add.cc.u32  %0, %15, %30;\n\t"
+        "addc.cc.u32 %1, %16, %31;\n\t"
+        "addc.cc.u32 %2, %17, %32;\n\t"
+        "addc.cc.u32 %3, %18, %33;\n\t"
+        "addc.cc.u32 %4, %19, %34;\n\t"
+        "addc.cc.u32 %5, %20, %35;\n\t"
+        "addc.cc.u32 %6, %21, %36;\n\t"
+        "addc.cc.u32 %7, %22, %37;\n\t"
+        "addc.cc.u32 %8, %23, %38;\n\t"
+        "addc.cc.u32 %9, %24, %39;\n\t"
+        "addc.cc.u32 %10, %25, %40;\n\t"
+        "addc.cc.u32 %11, %26, %41;\n\t"
+        "addc.cc.u32 %12, %27, %42;\n\t"
+        "addc.cc.u32 %13, %28, %43;\n\t"
+        "addc.u32    %14, %29, %44;"
+        : "=r"(T[1]), "=r"(T[2]), "=r"(T[3]), "=r"(T[4]), "=r"(T[5]), "=r"(T[6]), "=r"(T[7]), "=r"(T[8]),
+          "=r"(T[9]), "=r"(T[10]), "=r"(T[11]), "=r"(T[12]), "=r"(T[13]), "=r"(T[14]), "=r"(T[15])
+        : "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(E[8]), "r"(E[9]),
+          "r"(E[10]), "r"(E[11]), "r"(E[12]), "r"(E[13]), "r"(E[14]), "r"(E[15]),
+          "r"(O[0]), "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]), "r"(O[7]), "r"(O[8]),
+          "r"(O[9]), "r"(O[10]), "r"(O[11]), "r"(O[12]), "r"(O[13]), "r"(O[14]));
+    return mont_reduce(T);
+}
+
 // a + b without reduction (caller tracks the bound; everything must stay below 2^256 ~ 31.99p)
 __device__ __forceinline__ fe fe_add_lazy(const fe& a, const fe& b) {
     fe r;
@@ -259,10 +268,21 @@ __device__ __forceinline__ fe fe_reduce(const fe& x) {
 __device__ __forceinline__ fe fe_mul_full(const fe& a, const fe& b) { return fe_reduce(fe_mul(a, b)); }
 __device__ __forceinline__ fe fe_add_full(const fe& a, const fe& b) { return fe_reduce(fe_add_lazy(a, b)); }
 __device__ __forceinline__ fe fe_sub_full(const fe& a, const fe& b) { return fe_reduce(fe_sub_lazy<1>(a, b)); }
-// Montgomery form -> canonical representative in [0, p)
+// Montgomery form -> canonical representative in [0, p): a Montgomery product with 1 is the
+// reduction alone (16 wide MADs instead of 80) -- used once per element by the leaf hashers.
 __device__ __forceinline__ fe fe_from_mont(const fe& a) {
-    fe one = fe{{1, 0, 0, 0, 0, 0, 0, 0}};
-    return fe_reduce(fe_mul(a, one));
+    uint32_t T[16];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) T[i] = a.l[i];
+    // limbs 6.. : a's top two limbs plus the reduction constants (see mont_reduce)
+    asm("add.cc.u32  %0, %4, %6;\n\t"
+        "addc.cc.u32 %1, %5, %7;\n\t"
+        "addc.cc.u32 %2, 1, 0;\n\t"
+        "addc.u32    %3, 0, 0;"
+        : "=r"(T[6]), "=r"(T[7]), "=r"(T[8]), "=r"(T[9])
+        : "r"(a.l[6]), "r"(a.l[7]), "r"(S252_P6 + 1u), "r"(S252_P7));
+    T[10] = 0; T[11] = 0; T[12] = S252_P6; T[13] = S252_P7; T[14] = 0; T[15] = 0;
+    return fe_reduce(mont_reduce(T));
 }
 __device__ __forceinline__ fe fe_to_mont(const fe& a) { return fe_reduce(fe_mul(a, fe_r2())); }
 __device__ __forceinline__ bool fe_is_zero(const fe& a) {

@@ -51,39 +51,98 @@ struct NttPass {
     unsigned rows_are_cols;   // kind B single-pass: the T rows of a tile are T different columns
     unsigned in_lw;           // kind B single-pass: input is in the reference's LW element format
     unsigned out_lw;          // kind B: store outputs in LW format
+    unsigned first_unit;      // the level-1 twiddle of this pass is 1 (no coset shift): skip that multiply
 };
 
 __device__ __forceinline__ unsigned bitrev32(unsigned x, unsigned bits) { return bits ? __brev(x) >> (32 - bits) : 0u; }
 
-// All levels of a size-L DIT transform on every one of the T sequences held in sm[pos*T + t]
-// (input already in bit-reversed position order).
-__device__ __forceinline__ void block_dit(fe* sm, const fe* __restrict__ lvl, unsigned logL, unsigned logT) {
+// Shared-memory tile: 2^logE elements (E = L*T), element e = pos*T + t, stored as two planes of
+// 16-byte halves (lo limbs 0-3, hi limbs 4-7) so that a quarter-warp touching 8 consecutive elements
+// covers all 32 banks, and XOR-swizzled with the top three index bits so that the bit-reversed
+// scatter of the load phase (which walks the TOP bits) is conflict-free as well.
+struct Tile {
+    uint4* lo;
+    uint4* hi;
+    unsigned swz_shift, swz_mask;
+    __device__ __forceinline__ unsigned phys(unsigned e) const { return e ^ ((e >> swz_shift) & swz_mask); }
+    __device__ __forceinline__ fe ld(unsigned e) const {
+        const unsigned q = phys(e);
+        const uint4 a = lo[q], b = hi[q];
+        return fe{{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w}};
+    }
+    __device__ __forceinline__ void st(unsigned e, const fe& v) const {
+        const unsigned q = phys(e);
+        lo[q] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+        hi[q] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+    }
+};
+__device__ __forceinline__ Tile make_tile(unsigned char* smem, unsigned logE) {
+    Tile t;
+    t.lo = reinterpret_cast<uint4*>(smem);
+    t.hi = t.lo + (1u << logE);
+    t.swz_shift = logE >= 6 ? logE - 3 : 0;
+    t.swz_mask = logE >= 6 ? 7u : 0u;
+    return t;
+}
+
+// (a, b) -> (a + w*b, a - w*b + 2p); `plain` skips the multiplication when w is known to be 1
+__device__ __forceinline__ void bfly(fe& a, fe& b, const fe* __restrict__ tw, bool unit) {
+    const fe v = unit ? b : fe_mul(b, ldg_fe(tw));
+    const fe s = fe_add_lazy(a, v);
+    b = fe_sub_lazy<2>(a, v);
+    a = s;
+}
+
+// All levels of a size-L DIT transform on every one of the T sequences held in the tile (input
+// already in bit-reversed position order).  Levels are taken two at a time in registers (four
+// elements, four butterflies, three twiddle loads per work item), which halves the shared-memory
+// traffic and the number of barriers of a level-by-level radix-2 loop.  first_unit: the level-1
+// twiddle is 1 (every transform except the first pass of a coset evaluation), so that level is
+// add/sub only.
+__device__ __forceinline__ void block_dit(const Tile& sm, const fe* __restrict__ lvl, unsigned logL, unsigned logT,
+                                          bool first_unit) {
     const unsigned T = 1u << logT;
-    const unsigned items = (1u << (logL - 1)) << logT;
-    for (unsigned lev = 0; lev < logL; ++lev) {
+    unsigned lev = 0;
+    for (; lev + 1 < logL; lev += 2) {
         const unsigned half = 1u << lev;
+        const unsigned items = (1u << (logL - 2)) << logT;
+        for (unsigned w = threadIdx.x; w < items; w += NTT_THREADS) {
+            const unsigned t = w & (T - 1);
+            const unsigned j = w >> logT;
+            const unsigned jj = j & (half - 1);
+            const unsigned i0 = ((j >> lev) << (lev + 2)) + jj;
+            const unsigned e0 = (i0 << logT) + t, es = half << logT;
+            fe x0 = sm.ld(e0), x1 = sm.ld(e0 + es), x2 = sm.ld(e0 + 2 * es), x3 = sm.ld(e0 + 3 * es);
+            const bool unit = first_unit && lev == 0;
+            bfly(x0, x1, lvl + half + jj, unit);
+            bfly(x2, x3, lvl + half + jj, unit);
+            bfly(x0, x2, lvl + 2 * half + jj, false);
+            bfly(x1, x3, lvl + 3 * half + jj, false);
+            sm.st(e0, x0); sm.st(e0 + es, x1); sm.st(e0 + 2 * es, x2); sm.st(e0 + 3 * es, x3);
+        }
+        __syncthreads();
+    }
+    if (lev < logL) {   // odd number of levels: one radix-2 level remains
+        const unsigned half = 1u << lev;
+        const unsigned items = (1u << (logL - 1)) << logT;
         for (unsigned w = threadIdx.x; w < items; w += NTT_THREADS) {
             const unsigned t = w & (T - 1);
             const unsigned j = w >> logT;
             const unsigned jj = j & (half - 1);
             const unsigned i0 = ((j >> lev) << (lev + 1)) + jj;
-            fe* pa = sm + ((i0 << logT) + t);
-            fe* pb = sm + (((i0 + half) << logT) + t);
-            const fe a = ld_fe(pa);
-            const fe b = ld_fe(pb);
-            const fe tw = ldg_fe(lvl + half + jj);
-            const fe v = fe_mul(b, tw);
-            st_fe(pa, fe_add_lazy(a, v));
-            st_fe(pb, fe_sub_lazy<2>(a, v));
+            const unsigned e0 = (i0 << logT) + t, es = half << logT;
+            fe a = sm.ld(e0), b = sm.ld(e0 + es);
+            bfly(a, b, lvl + half + jj, first_unit && lev == 0);
+            sm.st(e0, a); sm.st(e0 + es, b);
         }
         __syncthreads();
     }
 }
 
 // ---- kind A: strided pass -------------------------------------------------------------------
-__global__ void __launch_bounds__(NTT_THREADS) ntt_pass_strided(NttPass P) {
+__global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_strided(NttPass P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    fe* sm = reinterpret_cast<fe*>(smem_raw);
+    const Tile sm = make_tile(smem_raw, P.logL + P.logT);
     const unsigned L = 1u << P.logL, T = 1u << P.logT;
     // block order: column fastest, then coset, then tile -- the blocks that share an inter-pass
     // twiddle slice (same tile and coset, different columns) run together, so the slice is read from
@@ -98,17 +157,19 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_strided(NttPass P) {
     const fe* in = P.in + col * P.in_col_stride + coset * P.in_coset_stride + ((o << P.logL) << P.logInner) + i0;
     fe* out = P.out + col * P.out_col_stride + coset * P.out_coset_stride + ((o << P.logL) << P.logInner) + i0;
     const unsigned n = L << P.logT;
+#pragma unroll 4
     for (unsigned e = threadIdx.x; e < n; e += NTT_THREADS) {
         const unsigned t = e & (T - 1), pos = e >> P.logT;
         const fe v = ld_fe(in + ((unsigned long long)pos << P.logInner) + t);
-        st_fe(sm + ((bitrev32(pos, P.logL) << P.logT) + t), v);
+        sm.st((bitrev32(pos, P.logL) << P.logT) + t, v);
     }
     __syncthreads();
-    block_dit(sm, P.lvl + (P.lvl_per_coset ? (size_t)coset << P.logL : 0), P.logL, P.logT);
+    block_dit(sm, P.lvl + (P.lvl_per_coset ? (size_t)coset << P.logL : 0), P.logL, P.logT, P.first_unit != 0);
     const fe* ptw = P.ptw + (P.ptw_per_coset ? (size_t)coset << (P.logL + P.logInner) : 0) + i0;
+#pragma unroll 2
     for (unsigned e = threadIdx.x; e < n; e += NTT_THREADS) {
         const unsigned t = e & (T - 1), k = e >> P.logT;
-        fe v = ld_fe(sm + e);
+        fe v = sm.ld(e);
         const fe w = ldg_fe(ptw + ((unsigned long long)k << P.logInner) + t);
         v = fe_reduce(fe_mul(v, w));
         st_fe(out + ((unsigned long long)k << P.logInner) + t, v);
@@ -116,9 +177,9 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_strided(NttPass P) {
 }
 
 // ---- kind B: final pass ----------------------------------------------------------------------
-__global__ void __launch_bounds__(NTT_THREADS) ntt_pass_final(NttPass P) {
+__global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_final(NttPass P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    fe* sm = reinterpret_cast<fe*>(smem_raw);
+    const Tile sm = make_tile(smem_raw, P.logL + P.logT);
     const unsigned L = 1u << P.logL, T = 1u << P.logT;
     unsigned bid = blockIdx.x, col0 = 0;
     if (!P.rows_are_cols) { col0 = bid % P.ncols; bid /= P.ncols; }
@@ -147,6 +208,7 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_final(NttPass P) {
     }
     // row t of the tile starts at in + t*row_stride
     const unsigned long long row_stride = P.rows_are_cols ? P.in_col_stride : (1ull << (P.logN2 + P.logL));
+#pragma unroll 4
     for (unsigned e = threadIdx.x; e < n; e += NTT_THREADS) {
         const unsigned pos = e & (L - 1), t = e >> P.logL;
         fe v = fe_zero();
@@ -154,15 +216,15 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_final(NttPass P) {
             const fe* src = in + t * row_stride + pos;
             v = P.in_lw ? ld_lw(src) : ld_fe(src);
         }
-        st_fe(sm + ((bitrev32(pos, P.logL) << P.logT) + t), v);
+        sm.st((bitrev32(pos, P.logL) << P.logT) + t, v);
     }
     __syncthreads();
-    block_dit(sm, P.lvl + (P.lvl_per_coset ? (size_t)coset << P.logL : 0), P.logL, P.logT);
+    block_dit(sm, P.lvl + (P.lvl_per_coset ? (size_t)coset << P.logL : 0), P.logL, P.logT, P.first_unit != 0);
     const unsigned logRows = P.logN1 + P.logN2;
     for (unsigned e = threadIdx.x; e < n; e += NTT_THREADS) {
         const unsigned t = e & (T - 1), k = e >> P.logT;
         if (t >= live) continue;
-        fe v = ld_fe(sm + e);
+        fe v = sm.ld(e);
         unsigned long long oi;     // natural output index within the column
         fe* dst;
         if (P.rows_are_cols) {

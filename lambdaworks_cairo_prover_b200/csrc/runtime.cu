@@ -25,6 +25,8 @@ namespace H = s252::host;
 struct s252_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // host->device prefetch of the next trace, overlapping compute
+    cudaEvent_t copy_event = nullptr;
     std::string err;
     uint64_t launches = 0;
     std::map<std::string, fe*> tables;   // cached twiddle tables (device)
@@ -211,6 +213,8 @@ extern "C" int s252_ctx_create(int device, s252_ctx** out) {
     s252_ctx* ctx = new s252_ctx();
     ctx->device = device;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return S252_ERR_CUDA; }
+    if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->copy_event, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return S252_ERR_CUDA; }
     cudaFuncSetAttribute(s252::ntt_pass_strided, cudaFuncAttributeMaxDynamicSharedMemorySize, s252::NTT_TILE * 32);
     cudaFuncSetAttribute(s252::ntt_pass_final, cudaFuncAttributeMaxDynamicSharedMemorySize, s252::NTT_TILE * 32);
     if (const char* e = std::getenv("S252_MAX_LOGL")) {
@@ -227,6 +231,9 @@ extern "C" void s252_ctx_destroy(s252_ctx* ctx) {
     arena_trim(ctx);
     for (auto& kv : ctx->arena_size) cudaFree(kv.first);   // blocks still owned by live handles
     for (auto& kv : ctx->tables) cudaFree(kv.second);
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaEventDestroy(ctx->copy_event);
+    cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -283,6 +290,23 @@ extern "C" int s252_device_free(s252_ctx* ctx, void* ptr) {
 extern "C" int s252_copy_to_device(s252_ctx* ctx, void* dst, const void* src, size_t bytes) {
     CU(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return S252_OK;
+}
+// Prefetch: enqueue a host->device copy on the context's copy stream (returns immediately; use
+// pinned host memory for a true asynchronous DMA).  The destination must not be in use by work
+// already queued on the compute stream.
+extern "C" int s252_copy_to_device_async(s252_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (!ctx || !dst || !src) return S252_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+    return S252_OK;
+}
+// Make everything issued on the compute stream from now on wait for the prefetches issued so far.
+extern "C" int s252_copy_stream_wait(s252_ctx* ctx) {
+    if (!ctx) return S252_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaEventRecord(ctx->copy_event, ctx->copy_stream));
+    CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_event, 0));
     return S252_OK;
 }
 extern "C" int s252_copy_to_host(s252_ctx* ctx, void* dst, const void* src, size_t bytes) {
@@ -404,6 +428,7 @@ static int run_ntt(s252_ctx* ctx, const Xform& X, const fe* in, size_t in_col_st
         P.in_coset_stride = 0; P.out_coset_stride = 0;
         P.logL = logn; P.logT = logT; P.logN1 = 0; P.logN2 = 0;
         P.lvl_per_coset = X.ncosets > 1; P.rows_are_cols = 1; P.in_lw = in_lw; P.out_lw = out_lw;
+        P.first_unit = (X.ncosets == 1 && H::eq(X.shift, H::one())) ? 1 : 0;
         const unsigned tiles = (ncols + (1u << logT) - 1) >> logT;
         prof_begin(ctx, "ntt_pass_final");
         prof_work(ctx, 32.0 * N * ncols * (1 + X.ncosets), 0.5 * N * logn * X.ncosets * ncols + (oscale ? (double)N * ncols : 0.0), 0);
@@ -441,6 +466,7 @@ static int run_ntt(s252_ctx* ctx, const Xform& X, const fe* in, size_t in_col_st
         P.in_coset_stride = 0; P.out_coset_stride = N;
         P.logL = l1; P.logT = logT; P.logInner = logInner; P.logOuter = 0;
         P.lvl_per_coset = X.ncosets > 1; P.ptw_per_coset = X.ncosets > 1; P.rows_are_cols = 0; P.in_lw = 0; P.out_lw = 0;
+        P.first_unit = (X.ncosets == 1 && H::eq(X.shift, H::one())) ? 1 : 0;
         const size_t tiles = (size_t)1 << (logInner - logT);
         prof_begin(ctx, "ntt_pass_strided");
         prof_work(ctx, 32.0 * N * ncols * (1 + X.ncosets), (0.5 * l1 + 1.0) * N * X.ncosets * ncols, 0);
@@ -458,7 +484,7 @@ static int run_ntt(s252_ctx* ctx, const Xform& X, const fe* in, size_t in_col_st
         P.in_col_stride = (size_t)X.ncosets * N; P.out_col_stride = (size_t)X.ncosets * N;
         P.in_coset_stride = N; P.out_coset_stride = N;
         P.logL = l2; P.logT = logT; P.logInner = l3; P.logOuter = l1;
-        P.lvl_per_coset = 0; P.ptw_per_coset = 0;
+        P.lvl_per_coset = 0; P.ptw_per_coset = 0; P.first_unit = 1;
         const size_t tiles = (size_t)1 << (l1 + l3 - logT);
         prof_begin(ctx, "ntt_pass_strided");
         prof_work(ctx, 64.0 * N * ncols * X.ncosets, (0.5 * l2 + 1.0) * N * X.ncosets * ncols, 0);
@@ -475,7 +501,7 @@ static int run_ntt(s252_ctx* ctx, const Xform& X, const fe* in, size_t in_col_st
         P.in_col_stride = (size_t)X.ncosets * N; P.out_col_stride = out_col_stride;
         P.in_coset_stride = N; P.out_coset_stride = 0;
         P.logL = l3; P.logT = logT; P.logN1 = l1; P.logN2 = l2;
-        P.lvl_per_coset = 0; P.ptw_per_coset = 0; P.rows_are_cols = 0; P.in_lw = 0; P.out_lw = out_lw;
+        P.lvl_per_coset = 0; P.ptw_per_coset = 0; P.rows_are_cols = 0; P.in_lw = 0; P.out_lw = out_lw; P.first_unit = 1;
         const size_t tiles = (size_t)1 << (l1 + l2 - logT);
         prof_begin(ctx, "ntt_pass_final");
         prof_work(ctx, 64.0 * N * ncols * X.ncosets, 0.5 * l3 * N * X.ncosets * ncols + (oscale ? (double)N * ncols : 0.0), 0);
