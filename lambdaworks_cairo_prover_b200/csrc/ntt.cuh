@@ -116,7 +116,7 @@ __device__ __forceinline__ void block_dit(const Tile& sm, const fe* __restrict__
             const bool unit = first_unit && lev == 0;
             bfly(x0, x1, lvl + half + jj, unit);
             bfly(x2, x3, lvl + half + jj, unit);
-            bfly(x0, x2, lvl + 2 * half + jj, false);
+            bfly(x0, x2, lvl + 2 * half + jj, unit);      // level-2 twiddles are {1, w_4}: the first is 1 too
             bfly(x1, x3, lvl + 3 * half + jj, false);
             sm.st(e0, x0); sm.st(e0 + es, x1); sm.st(e0 + 2 * es, x2); sm.st(e0 + 3 * es, x3);
         }
