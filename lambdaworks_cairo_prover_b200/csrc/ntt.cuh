@@ -63,8 +63,11 @@ __device__ __forceinline__ unsigned bitrev32(unsigned x, unsigned bits) { return
 struct Tile {
     uint4* lo;
     uint4* hi;
-    unsigned swz_shift, swz_mask;
-    __device__ __forceinline__ unsigned phys(unsigned e) const { return e ^ ((e >> swz_shift) & swz_mask); }
+    unsigned swz_shift, swz_mask;      // top three index bits -> bank bits (bit-reversed load scatter)
+    unsigned f2_shift, f2_mask, f2_lsh;   // item index bits of the first radix-4 step -> free bank bits
+    __device__ __forceinline__ unsigned phys(unsigned e) const {
+        return e ^ ((e >> swz_shift) & swz_mask) ^ (((e >> f2_shift) & f2_mask) << f2_lsh);
+    }
     __device__ __forceinline__ fe ld(unsigned e) const {
         const unsigned q = phys(e);
         const uint4 a = lo[q], b = hi[q];
@@ -76,12 +79,21 @@ struct Tile {
         hi[q] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
     }
 };
-__device__ __forceinline__ Tile make_tile(unsigned char* smem, unsigned logE) {
+__device__ __forceinline__ Tile make_tile(unsigned char* smem, unsigned logE, unsigned logT) {
     Tile t;
     t.lo = reinterpret_cast<uint4*>(smem);
     t.hi = t.lo + (1u << logE);
-    t.swz_shift = logE >= 6 ? logE - 3 : 0;
-    t.swz_mask = logE >= 6 ? 7u : 0u;
+    t.swz_shift = logE >= 9 ? logE - 3 : 0;
+    t.swz_mask = logE >= 9 ? 7u : 0u;
+    // In the first radix-4 step element e = (4j + r)*T + t: the 8 threads of a shared-memory phase
+    // differ in t (low logT bits) and in j (bits 2+logT and up), which would all land on the same
+    // banks; fold the j bits that sit above bit 2 into the bank bits t leaves free.
+    t.f2_shift = 0; t.f2_mask = 0; t.f2_lsh = 0;
+    if (logE >= 9) {
+        if (logT == 0) { t.f2_shift = 3; t.f2_mask = 3; t.f2_lsh = 0; }
+        else if (logT == 1) { t.f2_shift = 3; t.f2_mask = 3; t.f2_lsh = 1; }
+        else if (logT == 2) { t.f2_shift = 4; t.f2_mask = 1; t.f2_lsh = 2; }
+    }
     return t;
 }
 
@@ -142,7 +154,7 @@ __device__ __forceinline__ void block_dit(const Tile& sm, const fe* __restrict__
 // ---- kind A: strided pass -------------------------------------------------------------------
 __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_strided(NttPass P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const Tile sm = make_tile(smem_raw, P.logL + P.logT);
+    const Tile sm = make_tile(smem_raw, P.logL + P.logT, P.logT);
     const unsigned L = 1u << P.logL, T = 1u << P.logT;
     // block order: column fastest, then coset, then tile -- the blocks that share an inter-pass
     // twiddle slice (same tile and coset, different columns) run together, so the slice is read from
@@ -179,7 +191,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_strided(NttPass P) {
 // ---- kind B: final pass ----------------------------------------------------------------------
 __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_final(NttPass P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const Tile sm = make_tile(smem_raw, P.logL + P.logT);
+    const Tile sm = make_tile(smem_raw, P.logL + P.logT, P.logT);
     const unsigned L = 1u << P.logL, T = 1u << P.logT;
     unsigned bid = blockIdx.x, col0 = 0;
     if (!P.rows_are_cols) { col0 = bid % P.ncols; bid /= P.ncols; }
