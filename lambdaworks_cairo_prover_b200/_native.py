@@ -4,6 +4,7 @@ There is no CPU fallback: creating a Context without a CUDA device raises.
 """
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -139,9 +140,15 @@ class Context:
             raise Stark252Error(rc, "s252_ctx_create failed: no usable CUDA device %d (there is no CPU fallback)" % device)
         self.handle = h
         self.device = device
+        self._children = weakref.WeakSet()    # live commit / FRI handles: they must not outlive the context
+
+    def adopt(self, child):
+        self._children.add(child)
 
     def close(self):
         if getattr(self, "handle", None):
+            for child in list(self._children):
+                child.free()
             lib().s252_ctx_destroy(self.handle)
             self.handle = None
 

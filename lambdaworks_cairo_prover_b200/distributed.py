@@ -55,6 +55,7 @@ class GpuBackend:
         commit = DeviceCommit.__new__(DeviceCommit)
         commit.ctx, commit.handle, commit.root = self.ctx, h, b""
         commit.n_cols, commit.n_rows, commit.n_coeffs = n_cols, n_rows * blowup, n_rows
+        self.ctx.adopt(commit)
         ptr = N.lib().s252_commit_device_lde(h)
         t = torch.as_tensor(_DevicePointer(ptr, n_cols * n_rows * blowup * 4), device=self.device)
         return commit, t.view(n_cols, n_rows * blowup, 4)

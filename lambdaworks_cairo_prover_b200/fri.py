@@ -30,6 +30,7 @@ class FriLayers:
     def __init__(self, ctx, handle, domain_size, roots):
         self.ctx, self.handle, self.domain_size = ctx, handle, domain_size
         self.layers = [FriLayer(self, k, domain_size >> k, roots[k].tobytes()) for k in range(roots.shape[0])]
+        ctx.adopt(self)
 
     def __len__(self):
         return len(self.layers)

@@ -24,6 +24,7 @@ class DeviceCommit:
         self.n_cols = L.s252_commit_n_cols(handle)
         self.n_rows = L.s252_commit_n_rows(handle)
         self.n_coeffs = L.s252_commit_n_coeffs(handle)
+        ctx.adopt(self)
 
     def free(self):
         if getattr(self, "handle", None):
