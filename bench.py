@@ -193,7 +193,8 @@ def run_gpu(args):
         launches0 = ctx.launch_count
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         sampler = ClockSampler(local_rank)
-        sampler.start()
+        if rank == 0:
+            sampler.start()            # one sampler per job: N nvidia-smi pollers would perturb the run
         e0.record(stream)
         out = None
         for _ in range(steps):
@@ -206,7 +207,8 @@ def run_gpu(args):
         prof = ctx.profile_read() if profile else None
         if profile:
             ctx.profile(False)
-        sampler.join(timeout=2)
+        if rank == 0:
+            sampler.join(timeout=2)
         if world > 1:
             t = torch.tensor([ms], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -399,7 +401,8 @@ def run_gpu_sharded(args):
     dist.barrier()
     torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if rank == 0:
+        sampler.start()
     launches0 = ctx.launch_count
     t0 = time.perf_counter()
     out = None
@@ -413,7 +416,8 @@ def run_gpu_sharded(args):
     tt = torch.tensor([ms], device="cuda", dtype=torch.float64)
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     ms = float(tt.item())
-    sampler.join(timeout=2)
+    if rank == 0:
+        sampler.join(timeout=2)
     if rank == 0:
         value = cfg["elems_per_step"] * args.steps / (ms * 1e-3)
         h2d = sum(t.numel() for t, _, _ in shards.values()) + comp.nbytes + p0.nbytes
