@@ -155,6 +155,26 @@ const void *s252_commit_device_nodes(const s252_commit *c);
 int s252_fri_commit_phase(s252_ctx *ctx, size_t number_layers, const s252_fe *p0, size_t n_coeffs,
                           s252_transcript *transcript, const s252_fe *coset_offset, size_t domain_size, int mem,
                           s252_fri **out, s252_fe *last_value, uint8_t *roots_out);
+/* Round 3 reads: Frame::get_trace_evaluations (src/starks/frame.rs:67-83) and
+ * H1(z^2), H2(z^2) (prover.rs:296-300) from the coefficients resident in a commit:
+ * out[p*out_stride + col_offset + j] = poly_j(points[p]).  Several commits (main, aux) fill one
+ * frame by using different col_offset. */
+int s252_commit_evaluate_at(s252_commit *c, const s252_fe *points, size_t n_points, s252_fe *out, size_t out_stride,
+                            size_t col_offset);
+/* Round 4 from the resident commits (src/starks/prover.rs:327-404 minus the challenge sampling, which
+ * the caller does): builds the DEEP composition polynomial (compute_deep_composition_poly,
+ * prover.rs:410-482) directly as evaluations on the LDE coset,
+ *   p0(x) = sum_k [sum_j gammas[j*K+k] (t_j(x) - trace_ood[k*cols+j])] / (x - z g^offset_k)
+ *         + [gamma (H1(x) - h1_z2) + gamma_p (H2(x) - h2_z2)] / (x - z^2),
+ * and runs fri_commit_phase on it.  trace_commits: the round-1 commits in column order (main, aux);
+ * trace_ood: K x total_cols (Frame data, row-major); trace_gammas: total_cols x K in the
+ * reference's sampling order (prover.rs:352-355, index i*K + k). */
+int s252_fri_commit_phase_deep(s252_ctx *ctx, size_t number_layers, s252_commit *const *trace_commits,
+                               size_t n_trace_commits, s252_commit *composition_commit, const s252_fe *z,
+                               const uint64_t *transition_offsets, size_t n_offsets, const s252_fe *trace_ood,
+                               const s252_fe *h1_z2, const s252_fe *h2_z2, const s252_fe *gamma, const s252_fe *gamma_p,
+                               const s252_fe *trace_gammas, s252_transcript *transcript, uint64_t coset_offset,
+                               s252_fri **out, s252_fe *last_value, uint8_t *roots_out);
 void s252_fri_destroy(s252_fri *f);
 size_t s252_fri_n_layers(const s252_fri *f);
 /* FriLayer.evaluation[first..first+count) of layer k */

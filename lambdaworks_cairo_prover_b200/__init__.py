@@ -10,5 +10,6 @@ from .grinding import generate_nonce_with_grinding  # noqa: F401
 from .merkle import BatchedMerkleTree, DeviceCommit, FriMerkleTree, Proof, batch_commit  # noqa: F401
 from .options import ProofOptions  # noqa: F401
 from .polynomial import Polynomial, evaluate_polynomial_on_lde_domain  # noqa: F401
-from .prover import Domain, TraceTable, interpolate_and_commit, lde_and_commit  # noqa: F401
+from .prover import (Domain, TraceTable, evaluate_at, fri_commit_phase_deep, get_trace_evaluations,  # noqa: F401
+                     interpolate_and_commit, lde_and_commit)
 from .transcript import DefaultTranscript, batch_sample_challenges, transcript_to_field, transcript_to_usize  # noqa: F401

@@ -9,7 +9,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 SO = os.path.join(LIBDIR, "libstark252_b200.so")
 SOURCES = ["runtime.cu"]
-HEADERS = ["fe.cuh", "ntt.cuh", "keccak.cuh", "commit.cuh", "microbench.cuh", "host_field.hpp"]
+HEADERS = ["fe.cuh", "ntt.cuh", "keccak.cuh", "commit.cuh", "deep.cuh", "microbench.cuh", "host_field.hpp"]
 
 
 def nvcc_path():

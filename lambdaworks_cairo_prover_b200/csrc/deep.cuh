@@ -1,0 +1,165 @@
+// deep.cuh -- out-of-domain evaluations and the DEEP composition polynomial on the GPU
+// (first "next" row).
+//
+// Reference (CPU, coefficient form):
+//   Frame::get_trace_evaluations             src/starks/frame.rs:67-83      Horner per polynomial and point
+//   compute_deep_composition_poly            src/starks/prover.rs:410-482   cols*offsets Ruffini divisions
+// Here p0 is produced directly as evaluations on the LDE coset from the resident LDE columns,
+//   p0(x) = sum_k [ sum_j g_jk * (t_j(x) - t_j(z g^k)) ] / (x - z g^k)
+//         + [ g (H1(x) - H1(z^2)) + g' (H2(x) - H2(z^2)) ] / (x - z^2)
+// (the verifier's own formula, src/starks/verifier.rs:526-557): same polynomial, same values, and
+// FRI layer 0 no longer needs an NTT.
+#pragma once
+#include "fe.cuh"
+
+namespace s252 {
+
+constexpr int EVAL_THREADS = 256;
+
+// out[p * out_stride + col_offset + j] = sum_i coeffs[j][i] * xs[p]^i      (LW format output)
+__global__ void __launch_bounds__(EVAL_THREADS) poly_eval_points(const fe* __restrict__ coeffs, unsigned long long col_stride,
+                                                                  unsigned long long n, const fe* __restrict__ xs,
+                                                                  fe* __restrict__ out, unsigned out_stride, unsigned col_offset) {
+    __shared__ fe part[EVAL_THREADS];
+    const unsigned j = blockIdx.x, p = blockIdx.y, t = threadIdx.x;
+    const fe x = ld_fe(xs + p);
+    fe y = x;                                   // y = x^256
+#pragma unroll 1
+    for (int s = 0; s < 8; ++s) y = fe_mul_full(y, y);
+    const fe* c = coeffs + (unsigned long long)j * col_stride;
+    fe acc = fe_zero();
+    if (t < n) {
+        unsigned long long i = t + ((n - 1 - t) / EVAL_THREADS) * EVAL_THREADS;    // largest index = t (mod 256) below n
+        for (;;) {
+            acc = fe_add_lazy(fe_mul(acc, y), ld_fe(c + i));                        // < 3p
+            if (i < EVAL_THREADS) break;
+            i -= EVAL_THREADS;
+        }
+        fe xt = fe_one(), b = x;                 // x^t
+#pragma unroll 1
+        for (unsigned e = t; e; e >>= 1) {
+            if (e & 1) xt = fe_mul_full(xt, b);
+            b = fe_mul_full(b, b);
+        }
+        acc = fe_reduce(fe_mul(acc, xt));
+    }
+    part[t] = acc;
+    __syncthreads();
+    for (unsigned s = EVAL_THREADS / 2; s > 0; s >>= 1) {
+        if (t < s) part[t] = fe_add_full(part[t], part[t + s]);
+        __syncthreads();
+    }
+    if (t == 0) st_lw(out + (unsigned long long)p * out_stride + col_offset + j, part[0]);
+}
+
+constexpr int DEEP_THREADS = 128;
+constexpr int DEEP_ROWS = 4;          // rows per thread (batch size of the Montgomery inversion = ROWS*(K+1))
+constexpr int DEEP_MAX_TABLES = 4;
+constexpr int DEEP_MAX_K = 4;
+
+struct DeepParams {
+    const fe* cols[DEEP_MAX_TABLES];             // column-major LDE tables: trace tables first, composition table last
+    unsigned long long strides[DEEP_MAX_TABLES];
+    unsigned ncols[DEEP_MAX_TABLES];
+    unsigned ntables;                            // the last one is the composition table (H1, H2)
+    unsigned K;                                  // frame rows (transition offsets)
+    const fe* gammas;                            // device: [trace_cols][K] trace-term coefficients, then gamma, gamma'
+    fe zg[DEEP_MAX_K];                           // z * g^offset_k
+    fe ck[DEEP_MAX_K];                           // sum_j gamma_jk * t_j(z g^k)
+    fe z2, cz2;                                  // z^2 ; gamma*H1(z^2) + gamma'*H2(z^2)
+    fe h, w, wstep;                              // coset offset, w_M, w_M^DEEP_THREADS
+    unsigned long long m;                        // LDE rows
+    fe* out;                                     // [m] evaluations of p0 (internal format)
+};
+
+// a^(p-2)
+__device__ inline fe fe_inverse(const fe& a) {
+    fe r = fe_one(), base = a;
+    for (int bit = 0; bit < 252; ++bit) {
+        const bool set = bit < 192 || bit == 196 || bit == 251;
+        if (set) r = fe_mul_full(r, base);
+        base = fe_mul_full(base, base);
+    }
+    return r;
+}
+
+template <int K>
+__global__ void __launch_bounds__(DEEP_THREADS) deep_composition_kernel(DeepParams P) {
+    extern __shared__ __align__(16) unsigned char deep_smem[];
+    // per thread: ROWS*(K+1) prefix products, laid out [slot][thread] so a warp touches consecutive elements
+    fe* pre = reinterpret_cast<fe*>(deep_smem);
+    constexpr int D = K + 1;
+    const unsigned t = threadIdx.x;
+    const unsigned long long base = (unsigned long long)blockIdx.x * (DEEP_THREADS * DEEP_ROWS) + t;
+    // x of this thread's first row, then step by w^DEEP_THREADS
+    fe x0;
+    {
+        fe acc = P.h, b = P.w;
+        for (unsigned long long e = base; e; e >>= 1) {
+            if (e & 1) acc = fe_mul_full(acc, b);
+            b = fe_mul_full(b, b);
+        }
+        x0 = acc;
+    }
+    // forward pass: denominators and their running product
+    fe run = fe_one();
+    fe x = x0;
+#pragma unroll 1
+    for (int r = 0; r < DEEP_ROWS; ++r) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const fe d = fe_sub_full(x, k < K ? P.zg[k] : P.z2);
+            st_fe(pre + ((r * D + k) * DEEP_THREADS + t), run);     // product of everything before this slot
+            run = fe_mul_full(run, d);
+        }
+        x = fe_mul_full(x, P.wstep);
+    }
+    fe inv_run = fe_inverse(run);
+    // backward pass, row by row (last row first): inverse of each denominator, then the row's value
+    // x of the last row
+    fe xr = x0;
+#pragma unroll 1
+    for (int r = 1; r < DEEP_ROWS; ++r) xr = fe_mul_full(xr, P.wstep);
+    fe wstep_inv_unused = fe_zero();
+    (void)wstep_inv_unused;
+#pragma unroll 1
+    for (int r = DEEP_ROWS - 1; r >= 0; --r) {
+        // recompute x for row r (cheap: ROWS is tiny)
+        fe xx = x0;
+#pragma unroll 1
+        for (int q = 0; q < r; ++q) xx = fe_mul_full(xx, P.wstep);
+        fe inv[D];
+#pragma unroll
+        for (int k = D - 1; k >= 0; --k) {
+            const fe before = ld_fe(pre + ((r * D + k) * DEEP_THREADS + t));
+            inv[k] = fe_mul_full(inv_run, before);                  // 1/d = (1/prod_through) * prod_before
+            const fe d = fe_sub_full(xx, k < K ? P.zg[k] : P.z2);
+            inv_run = fe_mul_full(inv_run, d);                      // drop this denominator
+        }
+        const unsigned long long row = base + (unsigned long long)r * DEEP_THREADS;
+        if (row < P.m) {
+            fe s[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) s[k] = fe_zero();
+            const fe* g = P.gammas;
+            for (unsigned tb = 0; tb + 1 < P.ntables; ++tb) {
+                const fe* col = P.cols[tb] + row;
+                for (unsigned j = 0; j < P.ncols[tb]; ++j) {
+                    const fe v = ld_fe(col + (unsigned long long)j * P.strides[tb]);
+#pragma unroll
+                    for (int k = 0; k < K; ++k) s[k] = fe_reduce(fe_add_lazy(s[k], fe_mul(v, ldg_fe(g + k))));
+                    g += K;
+                }
+            }
+            const unsigned ct = P.ntables - 1;
+            const fe h1 = ld_fe(P.cols[ct] + row), h2 = ld_fe(P.cols[ct] + P.strides[ct] + row);
+            const fe sz = fe_reduce(fe_add_lazy(fe_mul(h1, ldg_fe(g)), fe_mul(h2, ldg_fe(g + 1))));
+            fe acc = fe_mul_full(fe_sub_full(sz, P.cz2), inv[K]);
+#pragma unroll
+            for (int k = 0; k < K; ++k) acc = fe_add_full(acc, fe_mul_full(fe_sub_full(s[k], P.ck[k]), inv[k]));
+            st_fe(P.out + row, acc);
+        }
+    }
+}
+
+}  // namespace s252

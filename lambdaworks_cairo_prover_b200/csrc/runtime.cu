@@ -12,6 +12,7 @@
 
 #include "../../include/stark252_b200.h"
 #include "commit.cuh"
+#include "deep.cuh"
 #include "fe.cuh"
 #include "host_field.hpp"
 #include "keccak.cuh"
@@ -938,6 +939,74 @@ static void fri_free(s252_fri* f) {
     for (auto& l : f->layers) { dfree(f->ctx, l.evals); dfree(f->ctx, l.nodes); }
     delete f;
 }
+// FRI commit phase once layer 0 (f->layers[0].evals, domain_size evaluations on the coset h*<w>) is
+// resident: trees, transcript, folds, last value (fri/mod.rs:33-69).
+static int fri_from_layer0(s252_ctx* ctx, s252_fri* f, size_t number_layers, s252_transcript* transcript, fe h,
+                           size_t domain_size, s252_fe* last_value, uint8_t* roots_out) {
+    const unsigned logM = ilog2(domain_size);
+    fe wM, w_inv;
+    H::primitive_root(logM, &wM);
+    w_inv = H::inv(wM);
+    const fe* inv_tw = nullptr;
+    if (domain_size >= 2) TRY(get_power_table(ctx, domain_size / 2, w_inv, H::one(), &inv_tw));
+    const fe inv2 = H::inv(H::from_u64(2));
+    uint8_t root[32];
+    if (number_layers > 0) {
+        TRY(dalloc(ctx, &f->layers[0].nodes, 4 * (2 * domain_size - 1)));
+        TRY(build_tree(ctx, f->layers[0].evals, domain_size, 1, domain_size, f->layers[0].nodes));
+        TRY(fetch_root(ctx, f->layers[0].nodes, root));
+        transcript->append(root, 32);                       // fri/mod.rs:37
+        if (roots_out) std::memcpy(roots_out, root, 32);
+    }
+    size_t size = domain_size;
+    const size_t folds = number_layers == 0 ? 1 : number_layers;
+    for (size_t k = 1; k <= folds; ++k) {
+        // fri/mod.rs:43-54 (k < number_layers) and :58-60 (the last fold)
+        const fe zeta = transcript->to_field();
+        const fe cfac = H::mul(zeta, H::mul(inv2, H::inv(h)));   // zeta / (2 h_k)
+        const size_t half = size / 2;
+        if (half == 0) FAIL(ctx, S252_ERR_INVALID, "FRI layer of size %zu cannot be folded", size);
+        const bool commit = k < number_layers;
+        FriLayerDev nxt;
+        nxt.size = half;
+        TRY(dalloc(ctx, &nxt.evals, half));
+        f->layers.push_back(nxt);
+        FriLayerDev& L = f->layers.back();
+        if (commit) TRY(dalloc(ctx, &L.nodes, 4 * (2 * half - 1)));
+        prof_begin(ctx, "fri_fold_commit");
+        prof_work(ctx, 32.0 * size + 32.0 * half + (commit ? 32.0 * half : 0.0), 3.2 * half, commit ? (double)half : 0.0);
+        s252::fri_fold_commit<<<(unsigned)((half + 127) / 128), 128, 0, ctx->stream>>>(
+            f->layers[k - 1].evals, half, inv_tw, (unsigned long long)(domain_size / size), cfac, inv2, L.evals,
+            commit ? L.nodes + 4 * (half - 1) : nullptr);
+        LAUNCH_CHECK(ctx);
+        h = H::sqr(h);
+        size = half;
+        if (commit) {
+            TRY(build_tree_nodes(ctx, half, L.nodes));
+            TRY(fetch_root(ctx, L.nodes, root));
+            transcript->append(root, 32);                   // fri/mod.rs:54
+            if (roots_out) std::memcpy(roots_out + 32 * k, root, 32);
+        }
+    }
+    // last_value = coefficient 0 of the fully folded polynomial = mean of its evaluations on the
+    // remaining coset (it has at most `size` coefficients because p0 has at most domain_size).
+    std::vector<fe> tail(size);
+    CU(ctx, cudaMemcpyAsync(tail.data(), f->layers.back().evals, size * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    fe acc = H::zero();
+    for (size_t i = 0; i < size; ++i) acc = H::add(acc, tail[i]);
+    const fe lv = H::mul(acc, H::inv(H::from_u64((uint64_t)size)));
+    H::to_lw(lv, last_value->limbs);
+    uint8_t be[32];
+    H::to_bytes_be(lv, be);
+    transcript->append(be, 32);                             // fri/mod.rs:69
+    // the folded tail is not a FriLayer of the reference: drop it
+    dfree(ctx, f->layers.back().evals);
+    f->layers.pop_back();
+    if (number_layers == 0) { dfree(ctx, f->layers.back().evals); f->layers.pop_back(); }
+    return S252_OK;
+}
+
 extern "C" int s252_fri_commit_phase(s252_ctx* ctx, size_t number_layers, const s252_fe* p0, size_t n_coeffs,
                                      s252_transcript* transcript, const s252_fe* coset_offset, size_t domain_size, int mem,
                                      s252_fri** out, s252_fe* last_value, uint8_t* roots_out) {
@@ -946,9 +1015,8 @@ extern "C" int s252_fri_commit_phase(s252_ctx* ctx, size_t number_layers, const 
     CU(ctx, cudaSetDevice(ctx->device));
     if (!is_pow2(domain_size)) FAIL(ctx, S252_ERR_INVALID, "FRI domain size %zu is not a power of two", domain_size);
     if (n_coeffs > domain_size) FAIL(ctx, S252_ERR_INVALID, "p0 has %zu coefficients, more than the domain size %zu", n_coeffs, domain_size);
-    const unsigned logM = ilog2(domain_size);
-    if (number_layers > logM) FAIL(ctx, S252_ERR_INVALID, "%zu FRI layers do not fit a domain of size %zu", number_layers, domain_size);
-    fe h = H::from_lw(coset_offset->limbs);
+    if (number_layers > ilog2(domain_size)) FAIL(ctx, S252_ERR_INVALID, "%zu FRI layers do not fit a domain of size %zu", number_layers, domain_size);
+    const fe h = H::from_lw(coset_offset->limbs);
     if (H::is_zero(h)) FAIL(ctx, S252_ERR_INVALID, "coset offset must be non-zero");
     s252_fri* f = new s252_fri();
     f->ctx = ctx; f->domain_size = domain_size;
@@ -962,82 +1030,127 @@ extern "C" int s252_fri_commit_phase(s252_ctx* ctx, size_t number_layers, const 
         TRY(dalloc(ctx, &cur.evals, domain_size));
         f->layers.push_back(cur);   // owned by f from here on
         TRY(evaluate_from_lw(ctx, dp0, n_coeffs, domain_size, h, f->layers[0].evals, false));
-        fe wM, w_inv;
-        H::primitive_root(logM, &wM);
-        w_inv = H::inv(wM);
-        const fe* inv_tw = nullptr;
-        if (domain_size >= 2) TRY(get_power_table(ctx, domain_size / 2, w_inv, H::one(), &inv_tw));
-        const fe inv2 = H::inv(H::from_u64(2));
-        uint8_t root[32];
-        if (number_layers > 0) {
-            TRY(dalloc(ctx, &f->layers[0].nodes, 4 * (2 * domain_size - 1)));
-            TRY(build_tree(ctx, f->layers[0].evals, domain_size, 1, domain_size, f->layers[0].nodes));
-            TRY(fetch_root(ctx, f->layers[0].nodes, root));
-            transcript->append(root, 32);                       // fri/mod.rs:37
-            if (roots_out) std::memcpy(roots_out, root, 32);
-        }
-        size_t size = domain_size;
-        for (size_t k = 1; k <= number_layers; ++k) {
-            // fri/mod.rs:43-54 (k < number_layers) and :58-60 (the last fold)
-            const fe zeta = transcript->to_field();
-            const fe cfac = H::mul(zeta, H::mul(inv2, H::inv(h)));   // zeta / (2 h_k)
-            const size_t half = size / 2;
-            if (half == 0) FAIL(ctx, S252_ERR_INVALID, "FRI layer of size %zu cannot be folded", size);
-            const bool commit = k < number_layers;
-            FriLayerDev nxt;
-            nxt.size = half;
-            TRY(dalloc(ctx, &nxt.evals, half));
-            f->layers.push_back(nxt);
-            FriLayerDev& L = f->layers.back();
-            if (commit) TRY(dalloc(ctx, &L.nodes, 4 * (2 * half - 1)));
-            prof_begin(ctx, "fri_fold_commit");
-            prof_work(ctx, 32.0 * size + 32.0 * half + (commit ? 32.0 * half : 0.0), 3.2 * half, commit ? (double)half : 0.0);
-            s252::fri_fold_commit<<<(unsigned)((half + 127) / 128), 128, 0, ctx->stream>>>(
-                f->layers[k - 1].evals, half, inv_tw, (unsigned long long)(domain_size / size), cfac, inv2, L.evals,
-                commit ? L.nodes + 4 * (half - 1) : nullptr);
-            LAUNCH_CHECK(ctx);
-            h = H::sqr(h);
-            size = half;
-            if (commit) {
-                TRY(build_tree_nodes(ctx, half, L.nodes));
-                TRY(fetch_root(ctx, L.nodes, root));
-                transcript->append(root, 32);                   // fri/mod.rs:54
-                if (roots_out) std::memcpy(roots_out + 32 * k, root, 32);
-            }
-        }
-        if (number_layers == 0) {
-            // degenerate: no committed layer, a single fold (fri/mod.rs:58-60)
-            const fe zeta = transcript->to_field();
-            const fe cfac = H::mul(zeta, H::mul(inv2, H::inv(h)));
-            const size_t half = size / 2;
-            if (half == 0) FAIL(ctx, S252_ERR_INVALID, "FRI domain of size %zu cannot be folded", size);
-            FriLayerDev nxt;
-            nxt.size = half;
-            TRY(dalloc(ctx, &nxt.evals, half));
-            f->layers.push_back(nxt);
-            prof_begin(ctx, "fri_fold_commit");
-            s252::fri_fold_commit<<<(unsigned)((half + 127) / 128), 128, 0, ctx->stream>>>(
-                f->layers[0].evals, half, inv_tw, 1ull, cfac, inv2, f->layers.back().evals, nullptr);
-            LAUNCH_CHECK(ctx);
-            size = half;
-        }
-        // last_value = coefficient 0 of the fully folded polynomial = mean of its evaluations on the
-        // remaining coset (it has at most `size` coefficients because n_coeffs <= domain_size).
-        std::vector<fe> tail(size);
-        CU(ctx, cudaMemcpyAsync(tail.data(), f->layers.back().evals, size * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
-        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        return fri_from_layer0(ctx, f, number_layers, transcript, h, domain_size, last_value, roots_out);
+    }();
+    if (rc != S252_OK) { fri_free(f); return rc; }
+    *out = f;
+    return S252_OK;
+}
+
+// Frame::get_trace_evaluations (src/starks/frame.rs:67-83) and the H1/H2 evaluations of round 3
+// (prover.rs:296-300) from the coefficients resident in a commit handle.
+extern "C" int s252_commit_evaluate_at(s252_commit* c, const s252_fe* points, size_t n_points, s252_fe* out, size_t out_stride,
+                                       size_t col_offset) {
+    if (!c || !points || !out) return S252_ERR_INVALID;
+    s252_ctx* ctx = c->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (!c->coeffs) FAIL(ctx, S252_ERR_INVALID, "this handle keeps no coefficients");
+    if (col_offset + c->n_cols > out_stride) FAIL(ctx, S252_ERR_INVALID, "output row of %zu elements cannot hold columns %zu..%zu", out_stride, col_offset, col_offset + c->n_cols);
+    if (n_points == 0) return S252_OK;
+    Tmp<fe> dx(ctx), dxi(ctx), dout(ctx);
+    TRY(dalloc(ctx, &dx.p, n_points));
+    TRY(dalloc(ctx, &dxi.p, n_points));
+    TRY(dalloc(ctx, &dout.p, n_points * c->n_cols));
+    CU(ctx, cudaMemcpyAsync(dx.p, points, n_points * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
+    TRY(convert_lw_to_internal(ctx, dx.p, dxi.p, n_points));
+    prof_begin(ctx, "poly_eval_points");
+    prof_work(ctx, 32.0 * c->n_coeffs * c->n_cols * n_points, (double)c->n_coeffs * c->n_cols * n_points, 0);
+    s252::poly_eval_points<<<dim3((unsigned)c->n_cols, (unsigned)n_points), s252::EVAL_THREADS, 0, ctx->stream>>>(
+        c->coeffs, c->n_coeffs, c->n_coeffs, dxi.p, dout.p, (unsigned)c->n_cols, 0);
+    LAUNCH_CHECK(ctx);
+    CU(ctx, cudaMemcpy2DAsync(out + col_offset, out_stride * sizeof(fe), dout.p, c->n_cols * sizeof(fe), c->n_cols * sizeof(fe),
+                              n_points, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return S252_OK;
+}
+
+// Round 4 from the resident commits: DEEP composition polynomial as evaluations on the LDE coset
+// (replaces compute_deep_composition_poly, prover.rs:410-482, and FRI layer 0's transform), then
+// fri_commit_phase (fri/mod.rs:20-72).
+extern "C" int s252_fri_commit_phase_deep(s252_ctx* ctx, size_t number_layers, s252_commit* const* trace_commits,
+                                          size_t n_trace_commits, s252_commit* composition_commit, const s252_fe* z,
+                                          const uint64_t* transition_offsets, size_t n_offsets, const s252_fe* trace_ood,
+                                          const s252_fe* h1_z2, const s252_fe* h2_z2, const s252_fe* gamma,
+                                          const s252_fe* gamma_p, const s252_fe* trace_gammas, s252_transcript* transcript,
+                                          uint64_t coset_offset, s252_fri** out, s252_fe* last_value, uint8_t* roots_out) {
+    if (!ctx || !trace_commits || !composition_commit || !z || !transition_offsets || !trace_ood || !h1_z2 || !h2_z2 || !gamma ||
+        !gamma_p || !trace_gammas || !transcript || !out || !last_value)
+        return S252_ERR_INVALID;
+    *out = nullptr;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (n_trace_commits == 0 || n_trace_commits + 1 > s252::DEEP_MAX_TABLES) FAIL(ctx, S252_ERR_INVALID, "between 1 and %d trace tables are supported", s252::DEEP_MAX_TABLES - 1);
+    if (n_offsets == 0 || n_offsets > (size_t)s252::DEEP_MAX_K) FAIL(ctx, S252_ERR_INVALID, "between 1 and %d frame rows are supported", s252::DEEP_MAX_K);
+    if (composition_commit->n_cols != 2) FAIL(ctx, S252_ERR_INVALID, "the composition commit must hold H1 and H2");
+    if (coset_offset == 0) FAIL(ctx, S252_ERR_INVALID, "coset offset must be non-zero");
+    const size_t M = composition_commit->n_rows, Ntrace = trace_commits[0]->n_coeffs;
+    if (!is_pow2(M) || Ntrace == 0 || number_layers > ilog2(M)) FAIL(ctx, S252_ERR_INVALID, "bad domain sizes for FRI");
+    s252::DeepParams P{};
+    size_t total_cols = 0;
+    for (size_t i = 0; i < n_trace_commits; ++i) {
+        const s252_commit* tc = trace_commits[i];
+        if (tc->n_rows != M || tc->ctx != ctx) FAIL(ctx, S252_ERR_INVALID, "trace commit %zu does not share the LDE domain / context", i);
+        P.cols[i] = tc->lde; P.strides[i] = tc->n_rows; P.ncols[i] = (unsigned)tc->n_cols;
+        total_cols += tc->n_cols;
+    }
+    P.cols[n_trace_commits] = composition_commit->lde;
+    P.strides[n_trace_commits] = M;
+    P.ncols[n_trace_commits] = 2;
+    P.ntables = (unsigned)n_trace_commits + 1;
+    P.K = (unsigned)n_offsets;
+    P.m = M;
+    const unsigned K = (unsigned)n_offsets;
+    fe g;
+    if (!H::primitive_root(ilog2(Ntrace), &g)) FAIL(ctx, S252_ERR_INVALID, "no trace root of unity");
+    const fe zz = H::from_lw(z->limbs);
+    const fe gam = H::from_lw(gamma->limbs), gamp = H::from_lw(gamma_p->limbs);
+    std::vector<fe> gammas(total_cols * K + 2);
+    for (size_t i = 0; i < total_cols * K; ++i) gammas[i] = H::from_lw(trace_gammas[i].limbs);
+    gammas[total_cols * K] = gam;
+    gammas[total_cols * K + 1] = gamp;
+    for (unsigned k = 0; k < K; ++k) {
+        P.zg[k] = H::mul(zz, H::pow_u64(g, transition_offsets[k]));
         fe acc = H::zero();
-        for (size_t i = 0; i < size; ++i) acc = H::add(acc, tail[i]);
-        const fe lv = H::mul(acc, H::inv(H::from_u64((uint64_t)size)));
-        H::to_lw(lv, last_value->limbs);
-        uint8_t be[32];
-        H::to_bytes_be(lv, be);
-        transcript->append(be, 32);                             // fri/mod.rs:69
-        // the folded tail is not a FriLayer of the reference: drop it
-        dfree(ctx, f->layers.back().evals);
-        f->layers.pop_back();
-        if (number_layers == 0) { dfree(ctx, f->layers.back().evals); f->layers.pop_back(); }
-        return S252_OK;
+        for (size_t j = 0; j < total_cols; ++j) acc = H::add(acc, H::mul(gammas[j * K + k], H::from_lw(trace_ood[k * total_cols + j].limbs)));
+        P.ck[k] = acc;
+    }
+    P.z2 = H::sqr(zz);
+    P.cz2 = H::add(H::mul(gam, H::from_lw(h1_z2->limbs)), H::mul(gamp, H::from_lw(h2_z2->limbs)));
+    const fe h = H::from_u64(coset_offset);
+    P.h = h;
+    H::primitive_root(ilog2(M), &P.w);
+    P.wstep = H::pow_u64(P.w, s252::DEEP_THREADS);
+    s252_fri* f = new s252_fri();
+    f->ctx = ctx; f->domain_size = M;
+    int rc = [&]() -> int {
+        Tmp<fe> dg(ctx);
+        TRY(dalloc(ctx, &dg.p, gammas.size()));
+        CU(ctx, cudaMemcpyAsync(dg.p, gammas.data(), gammas.size() * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
+        P.gammas = dg.p;
+        FriLayerDev cur;
+        cur.size = M;
+        TRY(dalloc(ctx, &cur.evals, M));
+        f->layers.push_back(cur);
+        P.out = f->layers[0].evals;
+        const unsigned rows_per_block = s252::DEEP_THREADS * s252::DEEP_ROWS;
+        const unsigned blocks = (unsigned)((M + rows_per_block - 1) / rows_per_block);
+        const size_t smem = (size_t)s252::DEEP_ROWS * (K + 1) * s252::DEEP_THREADS * sizeof(fe);
+        prof_begin(ctx, "deep_composition_kernel");
+        prof_work(ctx, 32.0 * M * (total_cols + 3), (double)M * (total_cols * K + 2 + 22.0 * (K + 1)), 0);
+#define S252_DEEP_LAUNCH(KK)                                                                                              \
+        case KK:                                                                                                          \
+            CU(ctx, cudaFuncSetAttribute(s252::deep_composition_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            s252::deep_composition_kernel<KK><<<blocks, s252::DEEP_THREADS, smem, ctx->stream>>>(P);                      \
+            break;
+        switch (K) {
+            S252_DEEP_LAUNCH(1)
+            S252_DEEP_LAUNCH(2)
+            S252_DEEP_LAUNCH(3)
+            S252_DEEP_LAUNCH(4)
+        }
+#undef S252_DEEP_LAUNCH
+        LAUNCH_CHECK(ctx);
+        CU(ctx, cudaStreamSynchronize(ctx->stream));   // gammas.data() / dg stay alive until the kernel is done
+        return fri_from_layer0(ctx, f, number_layers, transcript, h, M, last_value, roots_out);
     }();
     if (rc != S252_OK) { fri_free(f); return rc; }
     *out = f;

@@ -69,6 +69,8 @@ def lib():
             "o_generate_nonce_with_grinding": (i32, [vp, u8, u64, vp]),
             "o_interpolate_and_commit": (i32, [vp, sz, sz, sz, u64, i32, vp, vp, vp, vp]),
             "o_commit_columns": (i32, [vp, sz, sz, vp, vp]),
+            "o_poly_evaluate": (None, [vp, sz, vp, vp]),
+            "o_deep_composition_poly": (None, [vp, sz, sz, vp, vp, vp, vp, sz, vp, vp, vp, vp, vp, vp, vp]),
         }
         for name, (res, args) in sig.items():
             f = getattr(L, name)
@@ -366,3 +368,23 @@ def interpolate_and_commit(trace, blowup, coset_offset, threads=1, want_lde=True
     if rc:
         raise ValueError("interpolate_and_commit failed rc=%d" % rc)
     return {"coeffs": coeffs, "lde": lde, "nodes": nodes, "root": root.tobytes()}
+
+
+# ---------------------------------------------------------------- round 3 / round 4 helpers
+def poly_evaluate(coeffs, x):
+    coeffs, x = _fe_arr(coeffs).reshape(-1, 4), _fe_arr(x)
+    out = np.empty(4, dtype=np.uint64)
+    lib().o_poly_evaluate(_p(coeffs), coeffs.shape[0], _p(x), _p(out))
+    return out
+
+
+def deep_composition_poly(trace_polys, h1, h2, z, offsets, ood, h1_z2, h2_z2, gamma, gamma_p, gammas):
+    """trace_polys (c, n, 4); h1, h2 (n, 4); ood (K, c, 4); gammas (c, K, 4) -> p0 coefficients (n, 4)."""
+    trace_polys = _fe_arr(trace_polys)
+    c, n = trace_polys.shape[0], trace_polys.shape[1]
+    offs = np.ascontiguousarray(offsets, dtype=np.uint64)
+    out = np.empty((n, 4), dtype=np.uint64)
+    lib().o_deep_composition_poly(_p(trace_polys), c, n, _p(_fe_arr(h1)), _p(_fe_arr(h2)), _p(_fe_arr(z)), _p(offs), len(offs),
+                                  _p(_fe_arr(ood)), _p(_fe_arr(h1_z2)), _p(_fe_arr(h2_z2)), _p(_fe_arr(gamma)),
+                                  _p(_fe_arr(gamma_p)), _p(_fe_arr(gammas)), _p(out))
+    return out

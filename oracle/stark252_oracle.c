@@ -617,3 +617,60 @@ int o_interpolate_and_commit(const fe_lw *trace, size_t n_rows, size_t n_cols, s
     free(coeffs); free(lde);
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Round 3 / round 4 helpers (first "next" row)
+ * ------------------------------------------------------------------------------------------ */
+/* Polynomial::evaluate (Horner) -- call sites src/starks/prover.rs:296-300, frame.rs:76-80 */
+void o_poly_evaluate(const fe_lw *coeffs, size_t n, const fe_lw *x, fe_lw *out) {
+    fe acc = ZERO, xx = lw_in(x);
+    for (size_t i = n; i-- > 0;) { fe c = lw_in(&coeffs[i]); acc = fe_mul(&acc, &xx); acc = fe_add(&acc, &c); }
+    lw_out(&acc, out);
+}
+/* (p - p(b)) / (X - b) in place on n coefficients -> n-1 coefficients ([dep] ruffini_division_inplace) */
+static void ruffini(fe *c, size_t n, const fe *b) {
+    if (n == 0) return;
+    /* synthetic division from the top: q[i-1] = c[i] + b*q[i]; the remainder c[0] + b*q[0] is dropped */
+    fe carry = ZERO;
+    for (size_t i = n - 1; i > 0; --i) {
+        fe t = fe_mul(&carry, b);
+        carry = fe_add(&c[i], &t);
+        c[i] = carry;
+    }
+    for (size_t i = 0; i + 1 < n; ++i) c[i] = c[i + 1];
+    c[n - 1] = ZERO;
+}
+/* compute_deep_composition_poly -- src/starks/prover.rs:410-482.
+ * trace_polys: n_cols x n coefficients (column-major); h1, h2: n coefficients each (zero padded);
+ * ood: n_offsets x n_cols (frame rows); gammas: n_cols x n_offsets (index i*n_offsets + k);
+ * out: n coefficients of p0. */
+void o_deep_composition_poly(const fe_lw *trace_polys, size_t n_cols, size_t n, const fe_lw *h1, const fe_lw *h2,
+                             const fe_lw *z, const uint64_t *offsets, size_t n_offsets, const fe_lw *ood,
+                             const fe_lw *h1_z2, const fe_lw *h2_z2, const fe_lw *gamma, const fe_lw *gamma_p,
+                             const fe_lw *gammas, fe_lw *out) {
+    fe *acc = calloc(n, sizeof(fe)), *tmp = malloc(n * sizeof(fe));
+    fe zz = lw_in(z), z2 = fe_mul(&zz, &zz);
+    uint32_t order = ilog2(n);
+    fe g = ONE; primitive_root(order, &g);
+    /* gamma (H1 - H1(z^2)) / (X - z^2) + gamma' (H2 - H2(z^2)) / (X - z^2) */
+    for (int which = 0; which < 2; ++which) {
+        const fe_lw *hh = which ? h2 : h1;
+        fe v = lw_in(which ? h2_z2 : h1_z2), gm = lw_in(which ? gamma_p : gamma);
+        for (size_t i = 0; i < n; ++i) tmp[i] = lw_in(&hh[i]);
+        tmp[0] = fe_sub(&tmp[0], &v);
+        ruffini(tmp, n, &z2);
+        for (size_t i = 0; i < n; ++i) { fe t = fe_mul(&tmp[i], &gm); acc[i] = fe_add(&acc[i], &t); }
+    }
+    /* sum_jk gamma_jk (t_j - t_j(z g^k)) / (X - z g^k) */
+    for (size_t j = 0; j < n_cols; ++j)
+        for (size_t k = 0; k < n_offsets; ++k) {
+            fe gk = fe_pow_u64(&g, offsets[k]), zs = fe_mul(&zz, &gk);
+            fe v = lw_in(&ood[k * n_cols + j]), gm = lw_in(&gammas[j * n_offsets + k]);
+            for (size_t i = 0; i < n; ++i) tmp[i] = lw_in(&trace_polys[j * n + i]);
+            tmp[0] = fe_sub(&tmp[0], &v);
+            ruffini(tmp, n, &zs);
+            for (size_t i = 0; i < n; ++i) { fe t = fe_mul(&tmp[i], &gm); acc[i] = fe_add(&acc[i], &t); }
+        }
+    for (size_t i = 0; i < n; ++i) lw_out(&acc[i], &out[i]);
+    free(acc); free(tmp);
+}

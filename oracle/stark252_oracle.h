@@ -116,6 +116,15 @@ int o_interpolate_and_commit(const fe_lw *trace, size_t n_rows, size_t n_cols, s
  * after new_from_cols + rows(). */
 int o_commit_columns(const fe_lw *cols, size_t n_rows, size_t n_cols, uint8_t *nodes, uint8_t root[32]);
 
+/* ---- round 3 / round 4 helpers ---- */
+/* Polynomial::evaluate (Horner) */
+void o_poly_evaluate(const fe_lw *coeffs, size_t n, const fe_lw *x, fe_lw *out);
+/* compute_deep_composition_poly (src/starks/prover.rs:410-482), coefficient form with Ruffini divisions */
+void o_deep_composition_poly(const fe_lw *trace_polys, size_t n_cols, size_t n, const fe_lw *h1, const fe_lw *h2,
+                             const fe_lw *z, const uint64_t *offsets, size_t n_offsets, const fe_lw *ood,
+                             const fe_lw *h1_z2, const fe_lw *h2_z2, const fe_lw *gamma, const fe_lw *gamma_p,
+                             const fe_lw *gammas, fe_lw *out);
+
 #ifdef __cplusplus
 }
 #endif
