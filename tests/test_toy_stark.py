@@ -61,5 +61,8 @@ def test_gpu_proof_bytes_equal_oracle_proof_bytes(name, air, trace, pub, opts):
         want = TS.prove(air, trace(), pub, opts, TS.OracleBackend())
         assert got.serialize() == want.serialize()
         assert TS.verify(air, got, pub, opts)
+        # rounds 3 and 4 on the GPU as well (OOD evaluations + DEEP polynomial in the evaluation domain)
+        got2 = TS.prove(air, trace(), pub, opts, TS.GpuBackend(ctx, deep_on_device=True))
+        assert got2.serialize() == want.serialize()
     finally:
         ctx.close()

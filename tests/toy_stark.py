@@ -197,10 +197,31 @@ class OracleBackend:
 class GpuBackend:
     name = "gpu"
 
-    def __init__(self, ctx):
+    def __init__(self, ctx, deep_on_device=False):
         import lambdaworks_cairo_prover_b200 as P_
         from lambdaworks_cairo_prover_b200 import felt
         self.P, self.felt, self.ctx = P_, felt, ctx
+        self.deep_on_device = deep_on_device
+
+    def ood_evaluations(self, main, comp, z, offsets, n):
+        zf = self.felt.from_int(z)
+        ood = self.P.get_trace_evaluations([main.keep], zf, offsets, n, self.ctx)
+        hz = self.P.evaluate_at(comp.keep, self.felt.from_int(z * z % P))
+        return [self.felt.to_ints(row) for row in ood], self.felt.to_int(hz[0]), self.felt.to_int(hz[1])
+
+    def fri_deep(self, layers, main, comp, z, offsets, ood, h1z, h2z, gamma, gamma_p, tg, t, offset):
+        f = self.felt
+        ood_arr = np.stack([f.from_ints(row) for row in ood])
+        last, fl = self.P.fri_commit_phase_deep(layers, [main.keep], comp.keep, f.from_int(z), offsets, ood_arr, f.from_int(h1z),
+                                                f.from_int(h2z), f.from_int(gamma), f.from_int(gamma_p), f.from_ints(tg), t, offset)
+        return f.to_int(last), [layer.root for layer in fl], self._query_fn(fl)
+
+    def _query_fn(self, fl):
+        def query(iota):
+            q = self.P.fri_open(fl, [iota])[0]
+            return FriDecommitment([p.merkle_path for p in q.layers_auth_paths_sym], self.felt.to_ints(np.stack(q.layers_evaluations_sym)),
+                                   self.felt.to_ints(np.stack(q.layers_evaluations)), [p.merkle_path for p in q.layers_auth_paths])
+        return query
 
     def transcript(self):
         return self.P.DefaultTranscript()
@@ -327,8 +348,11 @@ def prove(air_cls, trace_cols, pub_inputs, options, be):
         if z not in lde_dom and z not in roots:
             break
     z2 = z * z % P
-    h1z, h2z = poly_eval(h1, z2), poly_eval(h2, z2)
-    ood = [[poly_eval(p, z * pow(g, k, P) % P) for p in polys] for k in air.transition_offsets]
+    if getattr(be, "deep_on_device", False):
+        ood, h1z, h2z = be.ood_evaluations(main, comp, z, air.transition_offsets, n)      # round 3 on the GPU
+    else:
+        h1z, h2z = poly_eval(h1, z2), poly_eval(h2, z2)
+        ood = [[poly_eval(p, z * pow(g, k, P) % P) for p in polys] for k in air.transition_offsets]
     t.append(_felt_bytes(h1z))
     t.append(_felt_bytes(h2z))
     for row in ood:
@@ -337,14 +361,18 @@ def prove(air_cls, trace_cols, pub_inputs, options, be):
     # ---- round 4
     gamma, gamma_p = be.to_field(t), be.to_field(t)
     tg = [be.to_field(t) for _ in range(len(air.transition_offsets) * ncols)]
-    deep = poly_add(poly_scale(ruffini(poly_sub_const(h1, h1z), z2), gamma), poly_scale(ruffini(poly_sub_const(h2, h2z), z2), gamma_p))
-    flen = len(air.transition_offsets)
-    for i, tj in enumerate(polys):
-        for r, k in enumerate(air.transition_offsets):
-            zs = z * pow(g, k, P) % P
-            deep = poly_add(deep, poly_scale(ruffini(poly_sub_const(tj, ood[r][i]), zs), tg[i * flen + r]))
     layers = n.bit_length() - 1
-    last, fri_roots, fri_query = be.fri_commit_phase(layers, deep, t, offset, m)
+    if getattr(be, "deep_on_device", False):
+        # round 4 on the GPU: DEEP polynomial in the evaluation domain straight into FRI
+        last, fri_roots, fri_query = be.fri_deep(layers, main, comp, z, air.transition_offsets, ood, h1z, h2z, gamma, gamma_p, tg, t, offset)
+    else:
+        deep = poly_add(poly_scale(ruffini(poly_sub_const(h1, h1z), z2), gamma), poly_scale(ruffini(poly_sub_const(h2, h2z), z2), gamma_p))
+        flen = len(air.transition_offsets)
+        for i, tj in enumerate(polys):
+            for r, k in enumerate(air.transition_offsets):
+                zs = z * pow(g, k, P) % P
+                deep = poly_add(deep, poly_scale(ruffini(poly_sub_const(tj, ood[r][i]), zs), tg[i * flen + r]))
+        last, fri_roots, fri_query = be.fri_commit_phase(layers, deep, t, offset, m)
     nonce = be.grinding(t.challenge(), options.grinding_factor)
     assert nonce is not None, "nonce not found"
     t.append(nonce.to_bytes(8, "big"))
