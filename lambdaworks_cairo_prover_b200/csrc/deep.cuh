@@ -16,40 +16,60 @@ namespace s252 {
 
 constexpr int EVAL_THREADS = 256;
 
-// out[p * out_stride + col_offset + j] = sum_i coeffs[j][i] * xs[p]^i      (LW format output)
+// partial[(j * splits + s) * npoints + p] = sum over i = r (mod 256*splits), r = s*256 + t, of coeffs[j][i] * xs[p]^i
+// (block s of column j).  Every thread runs one Horner chain per point in y = x^(256*splits) over its
+// residue class -- the chains of the different points share the coefficient loads and give the
+// scheduler independent multiplications -- then scales by x^r; the block adds its 256 partial sums.
+// The host adds the `splits` partials of a (column, point).
+constexpr int EVAL_MAX_POINTS = 4;
+template <int NP>
 __global__ void __launch_bounds__(EVAL_THREADS) poly_eval_points(const fe* __restrict__ coeffs, unsigned long long col_stride,
                                                                   unsigned long long n, const fe* __restrict__ xs,
-                                                                  fe* __restrict__ out, unsigned out_stride, unsigned col_offset) {
+                                                                  fe* __restrict__ partial, unsigned splits) {
     __shared__ fe part[EVAL_THREADS];
-    const unsigned j = blockIdx.x, p = blockIdx.y, t = threadIdx.x;
-    const fe x = ld_fe(xs + p);
-    fe y = x;                                   // y = x^256
-#pragma unroll 1
-    for (int s = 0; s < 8; ++s) y = fe_mul_full(y, y);
+    const unsigned j = blockIdx.x, s = blockIdx.y, t = threadIdx.x;
+    const unsigned long long stride = (unsigned long long)EVAL_THREADS * splits;
+    const unsigned long long r = (unsigned long long)s * EVAL_THREADS + t;
     const fe* c = coeffs + (unsigned long long)j * col_stride;
-    fe acc = fe_zero();
-    if (t < n) {
-        unsigned long long i = t + ((n - 1 - t) / EVAL_THREADS) * EVAL_THREADS;    // largest index = t (mod 256) below n
-        for (;;) {
-            acc = fe_add_lazy(fe_mul(acc, y), ld_fe(c + i));                        // < 3p
-            if (i < EVAL_THREADS) break;
-            i -= EVAL_THREADS;
-        }
-        fe xt = fe_one(), b = x;                 // x^t
-#pragma unroll 1
-        for (unsigned e = t; e; e >>= 1) {
-            if (e & 1) xt = fe_mul_full(xt, b);
-            b = fe_mul_full(b, b);
-        }
-        acc = fe_reduce(fe_mul(acc, xt));
+    fe x[NP], y[NP], acc[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        x[p] = ld_fe(xs + p);
+        acc[p] = fe_zero();
+        // y = x^stride (stride is a power of two times 256)
+        y[p] = x[p];
+        for (unsigned long long e = stride; e > 1; e >>= 1) y[p] = fe_mul_full(y[p], y[p]);
     }
-    part[t] = acc;
-    __syncthreads();
-    for (unsigned s = EVAL_THREADS / 2; s > 0; s >>= 1) {
-        if (t < s) part[t] = fe_add_full(part[t], part[t + s]);
+    if (r < n) {
+        unsigned long long i = r + ((n - 1 - r) / stride) * stride;    // largest index = r (mod stride) below n
+        for (;;) {
+            const fe ci = ld_fe(c + i);
+#pragma unroll
+            for (int p = 0; p < NP; ++p) acc[p] = fe_add_lazy(fe_mul(acc[p], y[p]), ci);      // < 3p
+            if (i < stride) break;
+            i -= stride;
+        }
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            fe xr = fe_one(), b = x[p];                  // x^r
+            for (unsigned long long e = r; e; e >>= 1) {
+                if (e & 1) xr = fe_mul_full(xr, b);
+                b = fe_mul_full(b, b);
+            }
+            acc[p] = fe_reduce(fe_mul(acc[p], xr));
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        part[t] = acc[p];
+        __syncthreads();
+        for (unsigned w = EVAL_THREADS / 2; w > 0; w >>= 1) {
+            if (t < w) part[t] = fe_add_full(part[t], part[t + w]);
+            __syncthreads();
+        }
+        if (t == 0) st_fe(partial + ((unsigned long long)j * splits + s) * NP + p, part[0]);
         __syncthreads();
     }
-    if (t == 0) st_lw(out + (unsigned long long)p * out_stride + col_offset + j, part[0]);
 }
 
 constexpr int DEEP_THREADS = 128;

@@ -1047,20 +1047,43 @@ extern "C" int s252_commit_evaluate_at(s252_commit* c, const s252_fe* points, si
     if (!c->coeffs) FAIL(ctx, S252_ERR_INVALID, "this handle keeps no coefficients");
     if (col_offset + c->n_cols > out_stride) FAIL(ctx, S252_ERR_INVALID, "output row of %zu elements cannot hold columns %zu..%zu", out_stride, col_offset, col_offset + c->n_cols);
     if (n_points == 0) return S252_OK;
-    Tmp<fe> dx(ctx), dxi(ctx), dout(ctx);
+    if (n_points > (size_t)s252::EVAL_MAX_POINTS) {
+        // more points than one launch handles: split
+        for (size_t p0 = 0; p0 < n_points; p0 += s252::EVAL_MAX_POINTS) {
+            const size_t cnt = std::min<size_t>(s252::EVAL_MAX_POINTS, n_points - p0);
+            TRY(s252_commit_evaluate_at(c, points + p0, cnt, out + p0 * out_stride, out_stride, col_offset));
+        }
+        return S252_OK;
+    }
+    // splits: enough blocks to fill the GPU, chains no shorter than ~32 coefficients
+    unsigned splits = 1;
+    while (splits < 64 && (size_t)c->n_cols * splits < 1024 && c->n_coeffs / ((size_t)s252::EVAL_THREADS * splits * 2) >= 32) splits *= 2;
+    Tmp<fe> dx(ctx), dxi(ctx), dpart(ctx);
+    const size_t nparts = c->n_cols * splits * n_points;
     TRY(dalloc(ctx, &dx.p, n_points));
     TRY(dalloc(ctx, &dxi.p, n_points));
-    TRY(dalloc(ctx, &dout.p, n_points * c->n_cols));
+    TRY(dalloc(ctx, &dpart.p, nparts));
     CU(ctx, cudaMemcpyAsync(dx.p, points, n_points * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
     TRY(convert_lw_to_internal(ctx, dx.p, dxi.p, n_points));
     prof_begin(ctx, "poly_eval_points");
-    prof_work(ctx, 32.0 * c->n_coeffs * c->n_cols * n_points, (double)c->n_coeffs * c->n_cols * n_points, 0);
-    s252::poly_eval_points<<<dim3((unsigned)c->n_cols, (unsigned)n_points), s252::EVAL_THREADS, 0, ctx->stream>>>(
-        c->coeffs, c->n_coeffs, c->n_coeffs, dxi.p, dout.p, (unsigned)c->n_cols, 0);
+    prof_work(ctx, 32.0 * c->n_coeffs * c->n_cols, (double)c->n_coeffs * c->n_cols * n_points, 0);
+    const dim3 grid((unsigned)c->n_cols, splits);
+    switch (n_points) {
+        case 1: s252::poly_eval_points<1><<<grid, s252::EVAL_THREADS, 0, ctx->stream>>>(c->coeffs, c->n_coeffs, c->n_coeffs, dxi.p, dpart.p, splits); break;
+        case 2: s252::poly_eval_points<2><<<grid, s252::EVAL_THREADS, 0, ctx->stream>>>(c->coeffs, c->n_coeffs, c->n_coeffs, dxi.p, dpart.p, splits); break;
+        case 3: s252::poly_eval_points<3><<<grid, s252::EVAL_THREADS, 0, ctx->stream>>>(c->coeffs, c->n_coeffs, c->n_coeffs, dxi.p, dpart.p, splits); break;
+        default: s252::poly_eval_points<4><<<grid, s252::EVAL_THREADS, 0, ctx->stream>>>(c->coeffs, c->n_coeffs, c->n_coeffs, dxi.p, dpart.p, splits); break;
+    }
     LAUNCH_CHECK(ctx);
-    CU(ctx, cudaMemcpy2DAsync(out + col_offset, out_stride * sizeof(fe), dout.p, c->n_cols * sizeof(fe), c->n_cols * sizeof(fe),
-                              n_points, cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<fe> parts(nparts);
+    CU(ctx, cudaMemcpyAsync(parts.data(), dpart.p, nparts * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
+    for (size_t j = 0; j < c->n_cols; ++j)
+        for (size_t p = 0; p < n_points; ++p) {
+            fe acc = H::zero();
+            for (unsigned s = 0; s < splits; ++s) acc = H::add(acc, parts[(j * splits + s) * n_points + p]);
+            H::to_lw(acc, out[p * out_stride + col_offset + j].limbs);
+        }
     return S252_OK;
 }
 
