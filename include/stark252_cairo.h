@@ -1,0 +1,84 @@
+/*
+ * stark252_cairo.h -- C ABI of the Cairo side of the B200-native prover: the callers and data formats
+ * on either side of the LDE + commitment path, in the same shared library as
+ * include/stark252_b200.h.
+ *
+ *   front-end (host)   a minimal Cairo-0 machine standing in for cairo-vm as the reference drives it
+ *                      (src/cairo/runner/run.rs:62-241) and build_main_trace
+ *                      (src/cairo/execution_trace.rs:57-87);
+ *   prover (GPU)       generate_cairo_proof (src/cairo/air.rs:1183-1190) = prove::<CairoAIR>
+ *                      (src/starks/prover.rs:532-776): both round-1 commits, the auxiliary (RAP) trace,
+ *                      the 49 Cairo transition constraints + 8 boundary constraints evaluated over the
+ *                      LDE coset on the device, composition polynomial, out-of-domain frame, DEEP
+ *                      composition polynomial, FRI, grinding, openings, and
+ *                      StarkProof::serialize (src/starks/proof/stark.rs:161-218).
+ *
+ * Binary formats are the reference's own: register trace = 24-byte little-endian rows (ap, fp, pc),
+ * src/cairo/register_states.rs:47-78; memory = 40-byte rows (u64 LE address, 32-byte LE value),
+ * src/cairo/cairo_mem.rs:35-61; field elements in tables = LW layout (see stark252_b200.h).
+ * Functions without a context report failures through s252_cairo_last_error() (thread local).
+ */
+#ifndef STARK252_CAIRO_H
+#define STARK252_CAIRO_H
+#include "stark252_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct s252_cairo_run s252_cairo_run;       /* relocated register trace + memory of one execution */
+typedef struct s252_cairo_trace s252_cairo_trace;   /* main trace table + PublicInputs */
+
+/* PublicInputs (src/cairo/air.rs:155-176) without the public memory map (read it with
+ * s252_cairo_trace_public_memory). */
+typedef struct {
+    uint64_t pc_init, ap_init, fp_init, pc_final, ap_final;
+    uint64_t num_steps;
+    uint64_t n_public_memory;
+    uint64_t rc_segment[2];        /* MemorySegment::RangeCheck range, valid if has_rc_segment */
+    uint64_t output_segment[2];    /* MemorySegment::Output range, valid if has_output_segment */
+    uint16_t range_check_min, range_check_max;   /* valid if has_range_check_bounds */
+    uint8_t has_range_check_bounds, has_rc_segment, has_output_segment, reserved;
+} s252_cairo_public_inputs;
+
+const char *s252_cairo_last_error(void);
+
+/* ---- front-end ---------------------------------------------------------------------------- */
+/* Runs a hint-free, builtin-free Cairo-0 program the way run_program(None, layout, .., V0) does
+ * (run.rs:62-100: proof_mode = false, relocation on): program words (32-byte big-endian each, the
+ * "data" array of the compiled JSON) are loaded at address 1, `main` is entered at
+ * 1 + entry_offset with the stack [return_fp, end], and execution stops at the final `ret`. */
+int s252_cairo_vm_run(const uint8_t *program_be, size_t n_words, uint64_t entry_offset, uint64_t max_steps,
+                      s252_cairo_run **out);
+void s252_cairo_run_destroy(s252_cairo_run *run);
+size_t s252_cairo_run_steps(const s252_cairo_run *run);
+size_t s252_cairo_run_trace_len(const s252_cairo_run *run);    /* bytes: 24 per step */
+size_t s252_cairo_run_memory_len(const s252_cairo_run *run);   /* bytes: 40 per cell */
+void s252_cairo_run_trace_bytes(const s252_cairo_run *run, uint8_t *out);
+void s252_cairo_run_memory_bytes(const s252_cairo_run *run, uint8_t *out);
+
+/* PublicInputs::from_regs_and_mem (air.rs:183-214) + build_main_trace (execution_trace.rs:57-87):
+ * execution trace, range-check holes, memory holes, public-memory dummy accesses, power-of-two
+ * padding.  rc_range / output_range: [start, end) or NULL (generate_prover_args, run.rs:243-266). */
+int s252_cairo_build_main_trace(const uint8_t *trace_le, size_t trace_len, const uint8_t *memory_le, size_t memory_len,
+                                size_t program_size, const uint64_t *rc_range, const uint64_t *output_range,
+                                s252_cairo_trace **out);
+/* The execution rows only: build_cairo_execution_trace (execution_trace.rs:261-356). */
+int s252_cairo_build_execution_trace(const uint8_t *trace_le, size_t trace_len, const uint8_t *memory_le,
+                                     size_t memory_len, size_t program_size, const uint64_t *rc_range,
+                                     const uint64_t *output_range, s252_cairo_trace **out);
+void s252_cairo_trace_destroy(s252_cairo_trace *t);
+size_t s252_cairo_trace_n_rows(const s252_cairo_trace *t);
+size_t s252_cairo_trace_n_cols(const s252_cairo_trace *t);
+const s252_fe *s252_cairo_trace_table(const s252_cairo_trace *t);   /* row-major n_rows x n_cols, LW */
+void s252_cairo_trace_public_inputs(const s252_cairo_trace *t, s252_cairo_public_inputs *out);
+/* addrs[n_public_memory], values[n_public_memory] (LW), sorted by address */
+void s252_cairo_trace_public_memory(const s252_cairo_trace *t, uint64_t *addrs, s252_fe *values);
+/* PublicInputs::serialize (air.rs:217-276); public memory in address order (the reference iterates a
+ * HashMap, so its order is not reproducible).  Returns the length; writes if out != NULL. */
+size_t s252_cairo_trace_serialize_public_inputs(const s252_cairo_trace *t, uint8_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -77,6 +77,24 @@ SIGNATURES = {
     "s252_microbench_keccak": (_i, [_vp, C.POINTER(C.c_double)]),
     "s252_fe_binop": (_i, [_vp, _i, _vp, _vp, _vp, _sz, _i]),
     "s252_keccak256_batch": (_i, [_vp, _vp, _sz, _sz, _vp]),
+    # include/stark252_cairo.h
+    "s252_cairo_last_error": (C.c_char_p, []),
+    "s252_cairo_vm_run": (_i, [_vp, _sz, _u64, _u64, C.POINTER(_vp)]),
+    "s252_cairo_run_destroy": (None, [_vp]),
+    "s252_cairo_run_steps": (_sz, [_vp]),
+    "s252_cairo_run_trace_len": (_sz, [_vp]),
+    "s252_cairo_run_memory_len": (_sz, [_vp]),
+    "s252_cairo_run_trace_bytes": (None, [_vp, _vp]),
+    "s252_cairo_run_memory_bytes": (None, [_vp, _vp]),
+    "s252_cairo_build_main_trace": (_i, [_vp, _sz, _vp, _sz, _sz, _vp, _vp, C.POINTER(_vp)]),
+    "s252_cairo_build_execution_trace": (_i, [_vp, _sz, _vp, _sz, _sz, _vp, _vp, C.POINTER(_vp)]),
+    "s252_cairo_trace_destroy": (None, [_vp]),
+    "s252_cairo_trace_n_rows": (_sz, [_vp]),
+    "s252_cairo_trace_n_cols": (_sz, [_vp]),
+    "s252_cairo_trace_table": (_vp, [_vp]),
+    "s252_cairo_trace_public_inputs": (None, [_vp, _vp]),
+    "s252_cairo_trace_public_memory": (None, [_vp, _vp, _vp]),
+    "s252_cairo_trace_serialize_public_inputs": (_sz, [_vp, _vp]),
 }
 
 

@@ -9,7 +9,8 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 SO = os.path.join(LIBDIR, "libstark252_b200.so")
 SOURCES = ["runtime.cu"]
-HEADERS = ["fe.cuh", "ntt.cuh", "keccak.cuh", "commit.cuh", "deep.cuh", "microbench.cuh", "host_field.hpp"]
+HEADERS = ["fe.cuh", "ntt.cuh", "keccak.cuh", "commit.cuh", "deep.cuh", "microbench.cuh", "host_field.hpp",
+           "cairo_host.hpp", "cairo_api.cuh"]
 
 
 def nvcc_path():
@@ -24,7 +25,7 @@ def needs_build():
         return True
     t = os.path.getmtime(SO)
     deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS]
-    deps.append(os.path.join(os.path.dirname(HERE), "include", "stark252_b200.h"))
+    deps += [os.path.join(os.path.dirname(HERE), "include", h) for h in ("stark252_b200.h", "stark252_cairo.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

@@ -1377,3 +1377,7 @@ extern "C" int s252_microbench_keccak(s252_ctx* ctx, double* gperms) {
     *gperms = (double)blocks * threads * iters / (ms * 1e-3) / 1e9;
     return S252_OK;
 }
+
+// --------------------------------------------------------------------------------------------
+// Cairo side (include/stark252_cairo.h)
+#include "cairo_api.cuh"

@@ -14,7 +14,7 @@ from oracle import pyoracle as O
 
 
 def header_symbols():
-    text = open(os.path.join(ROOT, "include", "stark252_b200.h")).read()
+    text = "".join(open(os.path.join(ROOT, "include", h)).read() for h in ("stark252_b200.h", "stark252_cairo.h"))
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(s252_[a-z0-9_]+)\s*\(", text)))
 
