@@ -22,7 +22,8 @@ R = 2**256
 
 def build(force=False):
     src = os.path.join(_HERE, "stark252_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [src, os.path.join(_HERE, "cairo_oracle.inc.c"), os.path.join(_HERE, "stark252_oracle.h")]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
     return _SO
 
@@ -71,6 +72,9 @@ def lib():
             "o_commit_columns": (i32, [vp, sz, sz, vp, vp]),
             "o_poly_evaluate": (None, [vp, sz, vp, vp]),
             "o_deep_composition_poly": (None, [vp, sz, sz, vp, vp, vp, vp, sz, vp, vp, vp, vp, vp, vp, vp]),
+            "o_cairo_build_aux_trace": (i32, [vp, sz, sz, vp, vp, sz, vp, vp]),
+            "o_cairo_compute_transition": (None, [vp, vp, sz, vp, i32, vp]),
+            "o_cairo_constraint_evaluations": (i32, [vp, sz, sz, sz, u64, i32, vp, sz, vp, vp, vp, vp, vp, i32, vp]),
         }
         for name, (res, args) in sig.items():
             f = getattr(L, name)
@@ -387,4 +391,43 @@ def deep_composition_poly(trace_polys, h1, h2, z, offsets, ood, h1_z2, h2_z2, ga
     lib().o_deep_composition_poly(_p(trace_polys), c, n, _p(_fe_arr(h1)), _p(_fe_arr(h2)), _p(_fe_arr(z)), _p(offs), len(offs),
                                   _p(_fe_arr(ood)), _p(_fe_arr(h1_z2)), _p(_fe_arr(h2_z2)), _p(_fe_arr(gamma)),
                                   _p(_fe_arr(gamma_p)), _p(_fe_arr(gammas)), _p(out))
+    return out
+
+
+# ---------------------------------------------------------------- Cairo AIR (cairo_oracle.inc.c)
+def cairo_build_aux_trace(main, pub_addrs, pub_vals, rap):
+    """main (n, c, 4) row-major; public memory in address order; rap (3, 4) -> aux (n, 18, 4)."""
+    main = _fe_arr(main)
+    n, c = main.shape[0], main.shape[1]
+    addrs = np.ascontiguousarray(pub_addrs, dtype=np.uint64)
+    vals = _fe_arr(pub_vals).reshape(-1, 4)
+    out = np.empty((n, 18, 4), dtype=np.uint64)
+    rc = lib().o_cairo_build_aux_trace(_p(main), n, c, _p(addrs), _p(vals), len(addrs), _p(_fe_arr(rap)), _p(out))
+    if rc:
+        raise ValueError("cairo_build_aux_trace failed rc=%d" % rc)
+    return out
+
+
+def cairo_compute_transition(cur, nxt, rap, has_rc=False):
+    cur, nxt = _fe_arr(cur).reshape(-1, 4), _fe_arr(nxt).reshape(-1, 4)
+    out = np.empty((50 if has_rc else 49, 4), dtype=np.uint64)
+    lib().o_cairo_compute_transition(_p(cur), _p(nxt), cur.shape[0], _p(_fe_arr(rap)), int(has_rc), _p(out))
+    return out
+
+
+def cairo_constraint_evaluations(lde, n, blowup, coset_offset, rap, boundary, boundary_coeffs, transition_coeffs, has_rc=False,
+                                 threads=1):
+    """lde (c, m, 4) column-major; boundary = [(col, step, value LW)]; coeffs (k, 2, 4) -> (m, 4)."""
+    lde = _fe_arr(lde)
+    c, m = lde.shape[0], lde.shape[1]
+    assert m == n * blowup
+    bcols = np.array([b[0] for b in boundary], dtype=np.uint64)
+    bsteps = np.array([b[1] for b in boundary], dtype=np.uint64)
+    bvals = _fe_arr(np.stack([b[2] for b in boundary]))
+    out = np.empty((m, 4), dtype=np.uint64)
+    rc = lib().o_cairo_constraint_evaluations(_p(lde), c, n, blowup, coset_offset, int(has_rc), _p(_fe_arr(rap)), len(boundary),
+                                              _p(bcols), _p(bsteps), _p(bvals), _p(_fe_arr(boundary_coeffs)),
+                                              _p(_fe_arr(transition_coeffs)), threads, _p(out))
+    if rc:
+        raise ValueError("cairo_constraint_evaluations failed rc=%d" % rc)
     return out

@@ -674,3 +674,6 @@ void o_deep_composition_poly(const fe_lw *trace_polys, size_t n_cols, size_t n, 
     for (size_t i = 0; i < n; ++i) lw_out(&acc[i], &out[i]);
     free(acc); free(tmp);
 }
+
+/* Cairo AIR pieces (aux trace, constraint evaluation): same translation unit */
+#include "cairo_oracle.inc.c"

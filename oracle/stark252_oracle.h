@@ -125,6 +125,21 @@ void o_deep_composition_poly(const fe_lw *trace_polys, size_t n_cols, size_t n, 
                              const fe_lw *h1_z2, const fe_lw *h2_z2, const fe_lw *gamma, const fe_lw *gamma_p,
                              const fe_lw *gammas, fe_lw *out);
 
+/* ---- Cairo AIR (cairo_oracle.inc.c) ---- */
+/* build_auxiliary_trace (src/cairo/air.rs:660-729): main row-major n x n_cols -> aux row-major n x 18;
+ * public memory in address order; rap = (alpha_memory, z_memory, z_range_check). */
+int o_cairo_build_aux_trace(const fe_lw *main, size_t n, size_t n_cols, const uint64_t *pub_addrs, const fe_lw *pub_vals,
+                            size_t n_pub, const fe_lw *rap, fe_lw *aux_out);
+/* CairoAIR::compute_transition (src/cairo/air.rs:743-767) on one frame (rows cur, nxt of n_cols values) */
+void o_cairo_compute_transition(const fe_lw *cur, const fe_lw *nxt, size_t n_cols, const fe_lw *rap, int has_rc, fe_lw *out);
+/* ConstraintEvaluator::evaluate for CairoAIR (src/starks/constraints/evaluator.rs:40-262): lde column-major
+ * n_cols x (n*blowup); boundary constraints (col, step, value) in CairoAIR::boundary_constraints order;
+ * coefficient arrays hold (alpha_k, beta_k) pairs. */
+int o_cairo_constraint_evaluations(const fe_lw *lde, size_t n_cols, size_t n, size_t blowup, uint64_t coset_offset, int has_rc,
+                                   const fe_lw *rap, size_t n_boundary, const uint64_t *bcols, const uint64_t *bsteps,
+                                   const fe_lw *bvalues, const fe_lw *boundary_coeffs, const fe_lw *transition_coeffs,
+                                   int threads, fe_lw *out);
+
 #ifdef __cplusplus
 }
 #endif
