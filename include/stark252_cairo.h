@@ -78,6 +78,39 @@ void s252_cairo_trace_public_memory(const s252_cairo_trace *t, uint64_t *addrs, 
  * HashMap, so its order is not reproducible).  Returns the length; writes if out != NULL. */
 size_t s252_cairo_trace_serialize_public_inputs(const s252_cairo_trace *t, uint8_t *out);
 
+/* A trace handle around a caller-built table (a Rust TraceTable + PublicInputs): table row-major LW
+ * (copied), public memory as parallel arrays. */
+int s252_cairo_trace_from_table(const s252_fe *table, size_t n_rows, size_t n_cols, const s252_cairo_public_inputs *pub,
+                                const uint64_t *pub_addrs, const s252_fe *pub_values, s252_cairo_trace **out);
+
+/* ---- prover (GPU) ------------------------------------------------------------------------- */
+/* Round 1 of prove::<CairoAIR> (round_1_randomized_air_with_preprocessing, src/starks/prover.rs:186-224):
+ * interpolate_and_commit(main) -> transcript.append(root) -> build_rap_challenges (air.rs:731-737) ->
+ * build_auxiliary_trace ON THE DEVICE (air.rs:660-729: stable sort by address, permutation-argument
+ * columns as multiplicative scans) -> interpolate_and_commit(aux) -> transcript.append(root).
+ * rap_out[3] = alpha_memory, z_memory, z_range_check. */
+int s252_cairo_round1(s252_ctx *ctx, const s252_cairo_trace *trace, size_t blowup, uint64_t coset_offset,
+                      s252_transcript *transcript, s252_commit **main_out, s252_commit **aux_out, s252_fe rap_out[3]);
+/* Trace evaluations kept in a round-1 handle (column `col`, n_coeffs values): reads the device-built
+ * auxiliary trace back for parity tests. */
+int s252_commit_read_trace(s252_commit *c, size_t col, s252_fe *out);
+/* Round 2 (prover.rs:598-640 + round_2_compute_composition_polynomial :226-283): samples the boundary
+ * and transition coefficients from the transcript, evaluates the 49 (50 with the range-check builtin)
+ * transition constraints and the 8 boundary constraints of CairoAIR over the LDE coset on the device
+ * (ConstraintEvaluator::evaluate, constraints/evaluator.rs:40-262), interpolates H
+ * (interpolate_offset_fft), splits it into H1/H2, extends and commits them, appends the root.
+ * The handle keeps the H1, H2 coefficients (s252_commit_read_coeffs).  S252_ERR_INVALID if H exceeds
+ * its degree bound 2N (the trace does not satisfy the AIR). */
+int s252_cairo_round2(s252_ctx *ctx, const s252_cairo_trace *trace, s252_commit *main_commit, s252_commit *aux_commit,
+                      const s252_fe rap[3], size_t blowup, uint64_t coset_offset, s252_transcript *transcript,
+                      s252_commit **composition_out);
+/* generate_cairo_proof (src/cairo/air.rs:1183-1190) = prove::<Stark252PrimeField, CairoAIR>: rounds 1-4
+ * on the device and StarkProof::serialize (src/starks/proof/stark.rs:161-218).  *proof_out is malloc'ed
+ * by the library; release it with s252_cairo_proof_free. */
+int s252_cairo_prove(s252_ctx *ctx, const s252_cairo_trace *trace, size_t blowup, size_t fri_number_of_queries,
+                     uint64_t coset_offset, uint8_t grinding_factor, uint8_t **proof_out, size_t *proof_len);
+void s252_cairo_proof_free(uint8_t *proof);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,6 +12,7 @@ import json
 import numpy as np
 
 from . import _native as N
+from .merkle import DeviceCommit
 from .prover import TraceTable
 
 
@@ -150,3 +151,78 @@ def fibonacci_program(n, with_assert=None):
     if with_assert is None:
         return main + [3, 0x208b7fff7fff7ffe] + fib
     return main + [5, 0x400680017fff7fff, with_assert, 0x208b7fff7fff7ffe] + fib
+
+
+# ------------------------------------------------------------------------------------------ GPU prover
+def trace_from_table(table, n_cols, pub_inputs):
+    """A MainTrace around a caller-built table (row-major LW) and PublicInputs-like object
+    (s252_cairo_trace_from_table): what a Rust caller holding TraceTable + PublicInputs would pass."""
+    L = N.lib()
+    table = N.fe_array(np.asarray(table, dtype=np.uint64).reshape(-1, 4))
+    c = _PublicInputsC()
+    for f in ("pc_init", "ap_init", "fp_init", "pc_final", "ap_final", "num_steps"):
+        setattr(c, f, getattr(pub_inputs, f))
+    if pub_inputs.range_check_min is not None:
+        c.has_range_check_bounds, c.range_check_min, c.range_check_max = 1, pub_inputs.range_check_min, pub_inputs.range_check_max
+    for name, flag, field in (("RangeCheck", "has_rc_segment", "rc_segment"), ("Output", "has_output_segment", "output_segment")):
+        if name in pub_inputs.memory_segments:
+            r = pub_inputs.memory_segments[name]
+            setattr(c, flag, 1)
+            getattr(c, field)[0], getattr(c, field)[1] = r.start, r.stop
+    addrs = np.array(sorted(pub_inputs.public_memory), dtype=np.uint64)
+    vals = np.stack([pub_inputs.public_memory[int(a)] for a in addrs]) if len(addrs) else np.zeros((0, 4), dtype=np.uint64)
+    c.n_public_memory = len(addrs)
+    h = C.c_void_p()
+    _check(L.s252_cairo_trace_from_table(N.ptr(table), table.shape[0] // n_cols, n_cols, C.byref(c), N.ptr(addrs),
+                                         N.ptr(N.fe_array(vals)), C.byref(h)))
+    return MainTrace(h)
+
+
+class Round1Commit(DeviceCommit):
+    """A round-1 handle that also keeps the trace evaluations it was built from."""
+
+    def trace_column(self, col):
+        out = np.empty((self.n_coeffs, 4), dtype=np.uint64)
+        self.ctx.check(N.lib().s252_commit_read_trace(self.handle, col, N.ptr(out)))
+        return out
+
+
+def round_1_randomized_air_with_preprocessing(trace, options, transcript, ctx=None):
+    """src/starks/prover.rs:186-224 for CairoAIR on the GPU (auxiliary trace built on the device).
+    Returns (main_commit, aux_commit, rap_challenges[3, 4])."""
+    ctx = ctx or N.default_context()
+    hm, ha = C.c_void_p(), C.c_void_p()
+    rap = np.zeros((3, 4), dtype=np.uint64)
+    ctx.check(N.lib().s252_cairo_round1(ctx.handle, trace.handle, options.blowup_factor, options.coset_offset, transcript.handle,
+                                        C.byref(hm), C.byref(ha), N.ptr(rap)))
+    mk = lambda h: Round1Commit(ctx, h, _root_of(ctx, h))
+    return mk(hm), mk(ha), rap
+
+
+def _root_of(ctx, h):
+    root = np.empty(32, dtype=np.uint8)
+    ctx.check(N.lib().s252_commit_root(h, N.ptr(root)))
+    return root.tobytes()
+
+
+def round_2_compute_composition_polynomial(trace, main_commit, aux_commit, rap, options, transcript):
+    """prover.rs:598-640 + 226-283 for CairoAIR on the GPU: samples the coefficients, evaluates the
+    constraints over the LDE coset, commits H1/H2 and appends the root.  Returns the composition commit."""
+    ctx = main_commit.ctx
+    h = C.c_void_p()
+    ctx.check(N.lib().s252_cairo_round2(ctx.handle, trace.handle, main_commit.handle, aux_commit.handle, N.ptr(N.fe_array(rap)),
+                                        options.blowup_factor, options.coset_offset, transcript.handle, C.byref(h)))
+    return DeviceCommit(ctx, h, _root_of(ctx, h))
+
+
+def generate_cairo_proof(trace, proof_options, ctx=None):
+    """src/cairo/air.rs:1183-1190: prove::<Stark252PrimeField, CairoAIR>(trace, pub_inputs, options) on
+    the GPU.  Returns StarkProof::serialize() bytes."""
+    ctx = ctx or N.default_context()
+    out, n = C.c_void_p(), C.c_size_t()
+    ctx.check(N.lib().s252_cairo_prove(ctx.handle, trace.handle, proof_options.blowup_factor, proof_options.fri_number_of_queries,
+                                       proof_options.coset_offset, proof_options.grinding_factor, C.byref(out), C.byref(n)))
+    try:
+        return C.string_at(out.value, n.value)
+    finally:
+        N.lib().s252_cairo_proof_free(out)

@@ -24,7 +24,7 @@ constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
 __global__ void __launch_bounds__(SCAN_THREADS) scan_mul_tiles(fe* __restrict__ data, unsigned long long n, fe* __restrict__ totals,
                                                                 int reverse) {
-    __shared__ fe sh[SCAN_THREADS];
+    __shared__ __align__(16) fe sh[SCAN_THREADS];
     const unsigned t = threadIdx.x;
     const unsigned long long base = (unsigned long long)blockIdx.x * SCAN_TILE + (unsigned long long)t * SCAN_ITEMS;
     fe v[SCAN_ITEMS];

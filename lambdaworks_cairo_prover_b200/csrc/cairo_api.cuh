@@ -140,3 +140,440 @@ extern "C" size_t s252_cairo_trace_serialize_public_inputs(const s252_cairo_trac
     if (out) std::memcpy(out, b.data(), b.size());
     return b.size();
 }
+
+extern "C" int s252_cairo_trace_from_table(const s252_fe* table, size_t n_rows, size_t n_cols, const s252_cairo_public_inputs* pub,
+                                           const uint64_t* pub_addrs, const s252_fe* pub_values, s252_cairo_trace** out) {
+    if (!table || !pub || !out || (pub->n_public_memory && (!pub_addrs || !pub_values))) CAIRO_FAIL(S252_ERR_INVALID, "null argument");
+    if (n_cols != CA::MAIN_COLS && n_cols != CA::MAIN_COLS + CA::RC_BUILTIN_COLS) CAIRO_FAIL(S252_ERR_INVALID, "a Cairo main trace has 34 or 43 columns");
+    s252_cairo_trace* t = new s252_cairo_trace();
+    t->n_rows = n_rows; t->n_cols = n_cols;
+    t->table.assign(table, table + n_rows * n_cols);
+    CA::PublicInputs& p = t->pi;
+    p.pc_init = pub->pc_init; p.ap_init = pub->ap_init; p.fp_init = pub->fp_init; p.pc_final = pub->pc_final; p.ap_final = pub->ap_final;
+    p.num_steps = pub->num_steps;
+    p.has_rc = pub->has_range_check_bounds; p.range_check_min = pub->range_check_min; p.range_check_max = pub->range_check_max;
+    p.has_rc_segment = pub->has_rc_segment; p.has_output_segment = pub->has_output_segment;
+    p.rc_segment[0] = pub->rc_segment[0]; p.rc_segment[1] = pub->rc_segment[1];
+    p.output_segment[0] = pub->output_segment[0]; p.output_segment[1] = pub->output_segment[1];
+    for (size_t i = 0; i < pub->n_public_memory; ++i) p.public_memory.push_back({pub_addrs[i], H::from_lw(pub_values[i].limbs)});
+    std::sort(p.public_memory.begin(), p.public_memory.end(), [](const std::pair<uint64_t, fe>& a, const std::pair<uint64_t, fe>& b) { return a.first < b.first; });
+    *out = t;
+    return S252_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// GPU prover
+#include <cub/device/device_radix_sort.cuh>
+
+// inclusive multiplicative scan of data[0..n) in place (suffix products when reverse)
+static int scan_mul(s252_ctx* ctx, fe* data, size_t n, bool reverse) {
+    const size_t tiles = (n + s252::SCAN_TILE - 1) / s252::SCAN_TILE;
+    if (tiles <= 1) {
+        prof_begin(ctx, "scan_mul_tiles");
+        s252::scan_mul_tiles<<<1, s252::SCAN_THREADS, 0, ctx->stream>>>(data, n, nullptr, reverse);
+        LAUNCH_CHECK(ctx);
+        return S252_OK;
+    }
+    Tmp<fe> totals(ctx);
+    TRY(dalloc(ctx, &totals.p, tiles));
+    prof_begin(ctx, "scan_mul_tiles");
+    prof_work(ctx, 64.0 * n, 2.0 * n, 0);
+    s252::scan_mul_tiles<<<(unsigned)tiles, s252::SCAN_THREADS, 0, ctx->stream>>>(data, n, totals.p, reverse);
+    LAUNCH_CHECK(ctx);
+    TRY(scan_mul(ctx, totals.p, tiles, false));
+    prof_begin(ctx, "scan_mul_apply");
+    prof_work(ctx, 64.0 * n, (double)n, 0);
+    s252::scan_mul_apply<<<(unsigned)((n - s252::SCAN_TILE + 255) / 256), 256, 0, ctx->stream>>>(data, n, totals.p, reverse);
+    LAUNCH_CHECK(ctx);
+    return S252_OK;
+}
+static int read_fe(s252_ctx* ctx, const fe* dev, fe* out) {
+    CU(ctx, cudaMemcpyAsync(out, dev, sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return S252_OK;
+}
+// dom[i] = h w^i and T[i] = 1/(dom[i] - 1) over the LDE coset; both cached in the context
+static int get_coset_tables(s252_ctx* ctx, size_t M, uint64_t coset_offset, const fe** dom, const fe** T) {
+    fe w;
+    if (!H::primitive_root(ilog2(M), &w)) FAIL(ctx, S252_ERR_INVALID, "no root of unity of order %zu", M);
+    const fe h = H::from_u64(coset_offset);
+    TRY(get_power_table(ctx, M, w, h, dom));
+    fe* t; bool fresh;
+    TRY(table_alloc(ctx, "cairoT:" + std::to_string(M) + ":" + fe_key(h), M, &t, &fresh));
+    if (fresh) {
+        Tmp<fe> a(ctx), b(ctx);
+        TRY(dalloc(ctx, &a.p, M));
+        TRY(dalloc(ctx, &b.p, M));
+        prof_begin(ctx, "sub_const2");
+        s252::sub_const2<<<(unsigned)((M + 255) / 256), 256, 0, ctx->stream>>>(*dom, a.p, b.p, M, H::one());
+        LAUNCH_CHECK(ctx);
+        TRY(scan_mul(ctx, a.p, M, false));
+        TRY(scan_mul(ctx, b.p, M, true));
+        fe total;
+        TRY(read_fe(ctx, a.p + (M - 1), &total));
+        if (H::is_zero(total)) FAIL(ctx, S252_ERR_INVALID, "the LDE coset contains 1 (coset offset %llu)", (unsigned long long)coset_offset);
+        prof_begin(ctx, "batch_inverse_finish");
+        s252::batch_inverse_finish<<<(unsigned)((M + 255) / 256), 256, 0, ctx->stream>>>(t, a.p, b.p, M, H::inv(total));
+        LAUNCH_CHECK(ctx);
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    *T = t;
+    return S252_OK;
+}
+
+// build_auxiliary_trace (air.rs:660-729) into aux[18][N] (column-major, internal format)
+static int cairo_build_aux(s252_ctx* ctx, const fe* main_cols, size_t N, const CA::PublicInputs& pi, const fe rap[3], fe* aux) {
+    const size_t L = 4 * N, R = 3 * N, np = pi.public_memory.size();
+    if (np > L) FAIL(ctx, S252_ERR_INVALID, "public memory (%zu words) does not fit the trace", np);
+    if (L >= (1ull << 31)) FAIL(ctx, S252_ERR_INVALID, "trace too long for the auxiliary-trace sort");
+    std::vector<unsigned long long> paddr(np);
+    std::vector<fe> paddr_fe(np), pval(np);
+    for (size_t i = 0; i < np; ++i) { paddr[i] = pi.public_memory[i].first; paddr_fe[i] = H::from_u64(paddr[i]); pval[i] = pi.public_memory[i].second; }
+    Tmp<unsigned long long> d_paddr(ctx), keys(ctx), keys2(ctx);
+    Tmp<fe> d_paddr_fe(ctx), d_pval(ctx), num(ctx), den(ctx), rnum(ctx), rden(ctx);
+    Tmp<unsigned> idx(ctx), idx2(ctx);
+    Tmp<unsigned short> okeys(ctx), okeys2(ctx);
+    Tmp<unsigned char> tmp(ctx);
+    TRY(dalloc(ctx, &d_paddr.p, np + 1)); TRY(dalloc(ctx, &d_paddr_fe.p, np + 1)); TRY(dalloc(ctx, &d_pval.p, np + 1));
+    if (np) {
+        CU(ctx, cudaMemcpyAsync(d_paddr.p, paddr.data(), np * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(d_paddr_fe.p, paddr_fe.data(), np * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(d_pval.p, pval.data(), np * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    TRY(dalloc(ctx, &keys.p, L)); TRY(dalloc(ctx, &keys2.p, L)); TRY(dalloc(ctx, &idx.p, L)); TRY(dalloc(ctx, &idx2.p, L));
+    TRY(dalloc(ctx, &okeys.p, R)); TRY(dalloc(ctx, &okeys2.p, R));
+    TRY(dalloc(ctx, &num.p, L)); TRY(dalloc(ctx, &den.p, L)); TRY(dalloc(ctx, &rnum.p, R)); TRY(dalloc(ctx, &rden.p, R));
+    s252::CairoAux P{};
+    P.main = main_cols; P.n = N; P.pub_addr = d_paddr.p; P.pub_addr_fe = d_paddr_fe.p; P.pub_val = d_pval.p; P.n_pub = (unsigned)np;
+    P.alpha = rap[0]; P.z = rap[1]; P.zrc = rap[2]; P.aux = aux;
+    const unsigned gl = (unsigned)((L + 255) / 256), gr = (unsigned)((R + 255) / 256);
+    prof_begin(ctx, "cairo_aux_keys");
+    prof_work(ctx, 32.0 * 7 * N, 7.0 * N * 0.2, 0);
+    s252::cairo_aux_keys<<<gl, 256, 0, ctx->stream>>>(P, keys.p, idx.p, okeys.p);
+    LAUNCH_CHECK(ctx);
+    // sort_columns_by_memory_address (air.rs:529-533): stable sort by address; offsets_sorted.sort() (air.rs:684-689)
+    size_t b1 = 0, b2 = 0;
+    CU(ctx, cub::DeviceRadixSort::SortPairs(nullptr, b1, keys.p, keys2.p, idx.p, idx2.p, (int)L, 0, 64, ctx->stream));
+    CU(ctx, cub::DeviceRadixSort::SortKeys(nullptr, b2, okeys.p, okeys2.p, (int)R, 0, 16, ctx->stream));
+    TRY(dalloc(ctx, &tmp.p, std::max(b1, b2) + 256));
+    prof_begin(ctx, "cub_radix_sort");
+    CU(ctx, cub::DeviceRadixSort::SortPairs(tmp.p, b1, keys.p, keys2.p, idx.p, idx2.p, (int)L, 0, 64, ctx->stream));
+    CU(ctx, cub::DeviceRadixSort::SortKeys(tmp.p, b2, okeys.p, okeys2.p, (int)R, 0, 16, ctx->stream));
+    LAUNCH_CHECK(ctx);
+    prof_begin(ctx, "cairo_aux_terms");
+    prof_work(ctx, 32.0 * 8 * L, 2.0 * L, 0);
+    s252::cairo_aux_terms<<<gl, 256, 0, ctx->stream>>>(P, idx2.p, num.p, den.p);
+    LAUNCH_CHECK(ctx);
+    prof_begin(ctx, "cairo_aux_rc_terms");
+    prof_work(ctx, 32.0 * 4 * R, 1.0 * R, 0);
+    s252::cairo_aux_rc_terms<<<gr, 256, 0, ctx->stream>>>(P, okeys2.p, rnum.p, rden.p);
+    LAUNCH_CHECK(ctx);
+    TRY(scan_mul(ctx, num.p, L, false));
+    TRY(scan_mul(ctx, den.p, L, true));
+    TRY(scan_mul(ctx, rnum.p, R, false));
+    TRY(scan_mul(ctx, rden.p, R, true));
+    fe tot[2];
+    CU(ctx, cudaMemcpyAsync(&tot[0], den.p, sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(&tot[1], rden.p, sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (H::is_zero(tot[0]) || H::is_zero(tot[1])) FAIL(ctx, S252_ERR_INVALID, "a permutation-argument challenge collides with a trace value");
+    prof_begin(ctx, "cairo_aux_finish");
+    prof_work(ctx, 32.0 * 3 * L, 2.0 * L, 0);
+    s252::cairo_aux_finish<<<gl, 256, 0, ctx->stream>>>(aux, N, 11, 4, num.p, den.p, H::inv(tot[0]));
+    LAUNCH_CHECK(ctx);
+    prof_begin(ctx, "cairo_aux_finish");
+    prof_work(ctx, 32.0 * 3 * R, 2.0 * R, 0);
+    s252::cairo_aux_finish<<<gr, 256, 0, ctx->stream>>>(aux, N, 15, 3, rnum.p, rden.p, H::inv(tot[1]));
+    LAUNCH_CHECK(ctx);
+    CU(ctx, cudaStreamSynchronize(ctx->stream));   // the host staging vectors go out of scope
+    return S252_OK;
+}
+
+extern "C" int s252_cairo_round1(s252_ctx* ctx, const s252_cairo_trace* trace, size_t blowup, uint64_t coset_offset,
+                                 s252_transcript* transcript, s252_commit** main_out, s252_commit** aux_out, s252_fe rap_out[3]) {
+    if (!ctx || !trace || !transcript || !main_out || !aux_out || !rap_out) return S252_ERR_INVALID;
+    *main_out = *aux_out = nullptr;
+    CU(ctx, cudaSetDevice(ctx->device));
+    const size_t N = trace->n_rows;
+    uint8_t root[32];
+    s252_commit* mainc = nullptr;
+    TRY(interpolate_lde_impl(ctx, trace->table.data(), N, trace->n_cols, blowup, coset_offset, S252_HOST, true, &mainc, root, true));
+    transcript->append(root, 32);                                   // prover.rs:151
+    fe rap[3];
+    for (int k = 0; k < 3; ++k) { rap[k] = transcript->to_field(); H::to_lw(rap[k], rap_out[k].limbs); }   // air.rs:731-737
+    s252_commit* auxc = new s252_commit();
+    auxc->ctx = ctx; auxc->n_cols = s252::CAIRO_AUX_COLS; auxc->n_rows = N * blowup; auxc->n_coeffs = N;
+    int rc = [&]() -> int {
+        TRY(dalloc(ctx, &auxc->trace, N * s252::CAIRO_AUX_COLS));
+        TRY(cairo_build_aux(ctx, mainc->trace, N, trace->pi, rap, auxc->trace));
+        TRY(lde_from_cols(ctx, auxc->trace, N, s252::CAIRO_AUX_COLS, blowup, coset_offset, true, auxc, root));
+        return S252_OK;
+    }();
+    if (rc != S252_OK) { commit_free(mainc); commit_free(auxc); return rc; }
+    transcript->append(root, 32);
+    *main_out = mainc;
+    *aux_out = auxc;
+    return S252_OK;
+}
+extern "C" int s252_commit_read_trace(s252_commit* c, size_t col, s252_fe* out) {
+    s252_ctx* ctx = c->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (!c->trace) FAIL(ctx, S252_ERR_INVALID, "this handle keeps no trace evaluations");
+    if (col >= c->n_cols) FAIL(ctx, S252_ERR_RANGE, "column %zu out of range", col);
+    return read_internal_as_lw(ctx, c->trace + col * c->n_coeffs, c->n_coeffs, out);
+}
+
+// CairoAIR::new (air.rs:594-625)
+static const uint8_t CAIRO_DEGREES[50] = {2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 1, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3,
+                                          2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 1};
+
+extern "C" int s252_cairo_round2(s252_ctx* ctx, const s252_cairo_trace* trace, s252_commit* mainc, s252_commit* auxc,
+                                 const s252_fe rap_lw[3], size_t blowup, uint64_t coset_offset, s252_transcript* transcript,
+                                 s252_commit** composition_out) {
+    if (!ctx || !trace || !mainc || !auxc || !rap_lw || !transcript || !composition_out) return S252_ERR_INVALID;
+    *composition_out = nullptr;
+    CU(ctx, cudaSetDevice(ctx->device));
+    const CA::PublicInputs& pi = trace->pi;
+    const size_t N = trace->n_rows, M = N * blowup, b = blowup;
+    if (mainc->n_rows != M || auxc->n_rows != M || auxc->n_cols != s252::CAIRO_AUX_COLS || mainc->n_cols != trace->n_cols)
+        FAIL(ctx, S252_ERR_INVALID, "round-1 handles do not match the trace");
+    if (!pi.has_rc) FAIL(ctx, S252_ERR_INVALID, "public inputs carry no range-check bounds (build_main_trace sets them)");
+    if (pi.num_steps == 0 || pi.num_steps > N) FAIL(ctx, S252_ERR_INVALID, "num_steps out of range");
+    const bool has_rc = trace->n_cols > CA::MAIN_COLS;
+    const unsigned mc = (unsigned)trace->n_cols;
+    const int nt = has_rc ? 50 : 49;
+    fe rap[3];
+    for (int k = 0; k < 3; ++k) rap[k] = H::from_lw(rap_lw[k].limbs);
+    fe g, w;
+    H::primitive_root(ilog2(N), &g);
+    H::primitive_root(ilog2(M), &w);
+    // CairoAIR::boundary_constraints (air.rs:777-849)
+    struct BC { unsigned col; uint64_t step; fe value; };
+    fe perm_final;
+    {
+        fe prod = H::one();
+        for (auto& kv : pi.public_memory) prod = H::mul(prod, H::sub(rap[1], H::add(H::from_u64(kv.first), H::mul(rap[0], kv.second))));
+        if (H::is_zero(prod)) FAIL(ctx, S252_ERR_INVALID, "z_memory collides with the public memory");
+        perm_final = H::mul(H::pow_u64(rap[1], pi.public_memory.size()), H::inv(prod));
+    }
+    const BC bcs[8] = {{CA::FRAME_PC, 0, H::from_u64(pi.pc_init)}, {CA::FRAME_AP, 0, H::from_u64(pi.ap_init)},
+                       {CA::FRAME_PC, pi.num_steps - 1, H::from_u64(pi.pc_final)}, {CA::FRAME_AP, pi.num_steps - 1, H::from_u64(pi.ap_final)},
+                       {mc + 14, N - 1, perm_final}, {mc + 17, N - 1, H::one()},
+                       {mc + 0, 0, H::from_u64(pi.range_check_min)}, {mc + 2, N - 1, H::from_u64(pi.range_check_max)}};
+    // <<<< challenges (prover.rs:598-626): boundary alphas, boundary betas, transition alphas, transition betas
+    fe ba[8], bb[8], ta[50], tb[50];
+    for (int k = 0; k < 8; ++k) ba[k] = transcript->to_field();
+    for (int k = 0; k < 8; ++k) bb[k] = transcript->to_field();
+    for (int k = 0; k < nt; ++k) ta[k] = transcript->to_field();
+    for (int k = 0; k < nt; ++k) tb[k] = transcript->to_field();
+    // per-residue tables: x^N takes `blowup` values over the coset (x = h w^i, i mod blowup = r)
+    std::vector<fe> tabs((8 + (size_t)nt) * b);
+    {
+        const fe hn = H::pow_u64(H::from_u64(coset_offset), N), wn = H::pow_u64(w, N);
+        const fe ginv = H::inv(g);
+        fe xn = hn;
+        for (size_t r = 0; r < b; ++r) {
+            const fe d = H::sub(xn, H::one());
+            if (H::is_zero(d)) FAIL(ctx, S252_ERR_INVALID, "the LDE coset meets the trace domain");
+            const fe zinv = H::inv(d), x2n = H::sqr(xn);
+            for (int k = 0; k < 8; ++k)
+                tabs[k * b + r] = H::mul(H::pow_u64(ginv, bcs[k].step), H::add(H::mul(ba[k], xn), bb[k]));
+            for (int k = 0; k < nt; ++k) {
+                const fe adj = CAIRO_DEGREES[k] == 1 ? x2n : CAIRO_DEGREES[k] == 2 ? xn : H::one();
+                tabs[(8 + k) * b + r] = H::mul(H::add(H::mul(ta[k], adj), tb[k]), zinv);
+            }
+            xn = H::mul(xn, wn);
+        }
+    }
+    s252::CairoEval E{};
+    E.main = mainc->lde; E.aux = auxc->lde; E.m = M; E.blowup = (unsigned)b; E.main_cols = mc; E.has_rc = has_rc;
+    E.alpha = rap[0]; E.z = rap[1]; E.zrc = rap[2];
+    E.g_last = H::pow_u64(g, N - 1);
+    E.nb = 8;
+    for (int k = 0; k < 8; ++k) { E.bcol[k] = bcs[k].col; E.bshift[k] = (b * bcs[k].step) % M; E.bval[k] = bcs[k].value; }
+    TRY(get_coset_tables(ctx, M, coset_offset, &E.dom, &E.T));
+    s252_commit* cm = new s252_commit();
+    cm->ctx = ctx; cm->n_cols = 2; cm->n_rows = M; cm->n_coeffs = N;
+    int rc = [&]() -> int {
+        Tmp<fe> dtabs(ctx), evals(ctx), hco(ctx);
+        Tmp<unsigned> flag(ctx);
+        TRY(dalloc(ctx, &dtabs.p, tabs.size()));
+        CU(ctx, cudaMemcpyAsync(dtabs.p, tabs.data(), tabs.size() * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
+        E.bcoef = dtabs.p; E.tcoef = dtabs.p + 8 * b;
+        TRY(dalloc(ctx, &evals.p, M));
+        E.out = evals.p;
+        prof_begin(ctx, "cairo_constraints_kernel");
+        prof_work(ctx, 32.0 * M * (mc + 18 + 10 + 5), 160.0 * M, 0);
+        s252::cairo_constraints_kernel<<<(unsigned)((M + s252::CAIRO_EVAL_THREADS - 1) / s252::CAIRO_EVAL_THREADS), s252::CAIRO_EVAL_THREADS, 0, ctx->stream>>>(E);
+        LAUNCH_CHECK(ctx);
+        // compute_composition_poly: interpolate_offset_fft(evaluations, offset) (evaluation_table.rs:27-33)
+        TRY(dalloc(ctx, &hco.p, M));
+        Xform X;
+        X.logn = ilog2(M);
+        X.inverse = true;
+        X.has_offset_scale = true;
+        X.oscale_base = H::inv(H::from_u64(coset_offset));
+        TRY(run_ntt(ctx, X, evals.p, M, false, hco.p, M, false, 1));
+        // even_odd_decomposition (prover.rs:252)
+        TRY(dalloc(ctx, &cm->coeffs, 2 * N));
+        TRY(dalloc(ctx, &flag.p, 1));
+        CU(ctx, cudaMemsetAsync(flag.p, 0, 4, ctx->stream));
+        prof_begin(ctx, "split_even_odd");
+        prof_work(ctx, 32.0 * (M + 2 * N), 0, 0);
+        s252::split_even_odd<<<(unsigned)((M + 255) / 256), 256, 0, ctx->stream>>>(hco.p, M, N, cm->coeffs, flag.p);
+        LAUNCH_CHECK(ctx);
+        unsigned over = 0;
+        CU(ctx, cudaMemcpyAsync(&over, flag.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        if (over) FAIL(ctx, S252_ERR_INVALID, "the composition polynomial exceeds its degree bound: the trace does not satisfy the Cairo AIR");
+        // evaluate_polynomial_on_lde_domain(H1), (H2) + batch_commit (prover.rs:254-276)
+        TRY(dalloc(ctx, &cm->lde, 2 * M));
+        TRY(evaluate_cosets(ctx, cm->coeffs, N, false, ilog2(N), (unsigned)b, H::from_u64(coset_offset), cm->lde, M, false, 2));
+        TRY(dalloc(ctx, &cm->nodes, 4 * (2 * M - 1)));
+        TRY(build_tree(ctx, cm->lde, M, 2, M, cm->nodes));
+        uint8_t root[32];
+        TRY(fetch_root(ctx, cm->nodes, root));
+        transcript->append(root, 32);                               // prover.rs:635
+        return S252_OK;
+    }();
+    if (rc != S252_OK) { commit_free(cm); return rc; }
+    *composition_out = cm;
+    return S252_OK;
+}
+
+// StarkProof::serialize helpers (proof/stark.rs:161-218; frame.rs:86-105; fri_decommit.rs:19-45; utils.rs:6-13)
+namespace {
+struct ByteSink {
+    std::vector<uint8_t> b;
+    void u64(uint64_t v) { uint8_t t[8]; put_u64_be(t, v); b.insert(b.end(), t, t + 8); }
+    void raw(const uint8_t* p, size_t n) { b.insert(b.end(), p, p + n); }
+    void felt(const s252_fe& v) { uint8_t t[32]; H::to_bytes_be(H::from_lw(v.limbs), t); raw(t, 32); }
+    void path(const uint8_t* p, size_t depth) { u64(depth); raw(p, depth * 32); }
+    void blob(const ByteSink& o) { u64(o.b.size()); raw(o.b.data(), o.b.size()); }
+};
+}  // namespace
+
+extern "C" int s252_cairo_prove(s252_ctx* ctx, const s252_cairo_trace* trace, size_t blowup, size_t n_queries, uint64_t coset_offset,
+                                uint8_t grinding_factor, uint8_t** proof_out, size_t* proof_len) {
+    if (!ctx || !trace || !proof_out || !proof_len) return S252_ERR_INVALID;
+    *proof_out = nullptr; *proof_len = 0;
+    CU(ctx, cudaSetDevice(ctx->device));
+    const size_t N = trace->n_rows, M = N * blowup;
+    if (!is_pow2(N) || N < 2) FAIL(ctx, S252_ERR_INVALID, "trace length %zu is not a power of two", N);
+    s252_transcript t;                                              // round_0_transcript_initialization
+    s252_commit *mainc = nullptr, *auxc = nullptr, *comp = nullptr;
+    s252_fri* fri = nullptr;
+    s252_fe rap[3];
+    int rc = [&]() -> int {
+        TRY(s252_cairo_round1(ctx, trace, blowup, coset_offset, &t, &mainc, &auxc, rap));
+        TRY(s252_cairo_round2(ctx, trace, mainc, auxc, rap, blowup, coset_offset, &t, &comp));
+        // ---- round 3 (prover.rs:650-690): z, H1(z^2), H2(z^2), t_j(z g^k)
+        fe g;
+        H::primitive_root(ilog2(N), &g);
+        const fe hinv = H::inv(H::from_u64(coset_offset));
+        fe z;
+        for (;;) {                                                  // sample_z_ood (transcript.rs:53-70)
+            z = t.to_field();
+            if (!H::eq(H::pow_u64(H::mul(z, hinv), M), H::one()) && !H::eq(H::pow_u64(z, N), H::one())) break;
+        }
+        const size_t cols = mainc->n_cols + auxc->n_cols;
+        s252_fe pts[2], z2, zlw, hz[2];
+        H::to_lw(z, pts[0].limbs); H::to_lw(H::mul(z, g), pts[1].limbs); H::to_lw(H::sqr(z), z2.limbs);
+        zlw = pts[0];
+        std::vector<s252_fe> ood(2 * cols);
+        TRY(s252_commit_evaluate_at(mainc, pts, 2, ood.data(), cols, 0));
+        TRY(s252_commit_evaluate_at(auxc, pts, 2, ood.data(), cols, mainc->n_cols));
+        TRY(s252_commit_evaluate_at(comp, &z2, 1, hz, 2, 0));
+        uint8_t be[32];
+        for (int k = 0; k < 2; ++k) { H::to_bytes_be(H::from_lw(hz[k].limbs), be); t.append(be, 32); }
+        for (auto& v : ood) { H::to_bytes_be(H::from_lw(v.limbs), be); t.append(be, 32); }
+        // ---- round 4 (prover.rs:327-404)
+        s252_fe gamma, gamma_p;
+        H::to_lw(t.to_field(), gamma.limbs); H::to_lw(t.to_field(), gamma_p.limbs);
+        std::vector<s252_fe> tg(2 * cols);
+        for (auto& v : tg) H::to_lw(t.to_field(), v.limbs);
+        const size_t layers = ilog2(N);
+        const uint64_t offs[2] = {0, 1};
+        s252_commit* tcs[2] = {mainc, auxc};
+        s252_fe last;
+        std::vector<uint8_t> fri_roots(32 * std::max<size_t>(layers, 1));
+        TRY(s252_fri_commit_phase_deep(ctx, layers, tcs, 2, comp, &zlw, offs, 2, ood.data(), &hz[0], &hz[1], &gamma, &gamma_p, tg.data(), &t,
+                                       coset_offset, &fri, &last, fri_roots.data()));
+        uint8_t challenge[32];
+        t.challenge(challenge);
+        uint64_t nonce = 0;
+        TRY(s252_generate_nonce_with_grinding(ctx, challenge, grinding_factor, 0, &nonce));
+        uint8_t nb[8];
+        put_u64_be(nb, nonce);
+        t.append(nb, 8);
+        const size_t Q = layers ? n_queries : 0;                   // fri_query_phase returns nothing without layers (fri/mod.rs:83)
+        std::vector<uint64_t> iotas(Q);
+        for (auto& i : iotas) i = t.to_usize() % M;
+        const size_t depth = ilog2(M);
+        std::vector<s252_fe> ev(Q * layers), evs(Q * layers), main_rows(Q * mainc->n_cols), aux_rows(Q * auxc->n_cols), comp_rows(Q * 2);
+        std::vector<uint8_t> pa(Q * layers * depth * 32), pas(Q * layers * depth * 32), main_paths(Q * depth * 32), aux_paths(Q * depth * 32),
+            comp_paths(Q * depth * 32);
+        if (Q) {
+            TRY(s252_fri_query(fri, iotas.data(), Q, ev.data(), evs.data(), pa.data(), pas.data(), depth));
+            TRY(s252_commit_open(mainc, iotas.data(), Q, main_rows.data(), main_paths.data()));
+            TRY(s252_commit_open(auxc, iotas.data(), Q, aux_rows.data(), aux_paths.data()));
+            TRY(s252_commit_open(comp, iotas.data(), Q, comp_rows.data(), comp_paths.data()));
+        }
+        // ---- StarkProof::serialize
+        ByteSink S;
+        uint8_t r32[32];
+        S.u64(N);
+        S.u64(2);
+        TRY(s252_commit_root(mainc, r32)); S.raw(r32, 32);
+        TRY(s252_commit_root(auxc, r32)); S.raw(r32, 32);
+        {
+            ByteSink F;
+            F.u64(ood.size()); F.u64(32);
+            for (auto& v : ood) F.felt(v);
+            F.u64(cols);
+            S.blob(F);
+        }
+        TRY(s252_commit_root(comp, r32)); S.raw(r32, 32);
+        S.u64(32); S.felt(hz[0]); S.felt(hz[1]);
+        S.u64(layers); S.raw(fri_roots.data(), 32 * layers);
+        S.felt(last);
+        S.u64(Q);
+        for (size_t q = 0; q < Q; ++q) {
+            ByteSink D;
+            D.u64(layers);
+            for (size_t k = 0; k < layers; ++k) D.path(pas.data() + (q * layers + k) * depth * 32, depth - k);
+            D.u64(32);
+            D.u64(layers);
+            for (size_t k = 0; k < layers; ++k) D.felt(evs[q * layers + k]);
+            D.u64(layers);
+            for (size_t k = 0; k < layers; ++k) D.felt(ev[q * layers + k]);
+            D.u64(layers);
+            for (size_t k = 0; k < layers; ++k) D.path(pa.data() + (q * layers + k) * depth * 32, depth - k);
+            S.blob(D);
+        }
+        S.u64(Q);
+        for (size_t q = 0; q < Q; ++q) {
+            ByteSink O;
+            O.path(comp_paths.data() + q * depth * 32, depth);
+            O.u64(32); O.felt(comp_rows[2 * q]); O.felt(comp_rows[2 * q + 1]);
+            O.u64(2);
+            O.path(main_paths.data() + q * depth * 32, depth);
+            O.path(aux_paths.data() + q * depth * 32, depth);
+            O.u64(cols);
+            for (size_t j = 0; j < mainc->n_cols; ++j) O.felt(main_rows[q * mainc->n_cols + j]);
+            for (size_t j = 0; j < auxc->n_cols; ++j) O.felt(aux_rows[q * auxc->n_cols + j]);
+            S.blob(O);
+        }
+        S.u64(nonce);
+        uint8_t* outp = (uint8_t*)std::malloc(S.b.size());
+        if (!outp) FAIL(ctx, S252_ERR_INVALID, "out of host memory");
+        std::memcpy(outp, S.b.data(), S.b.size());
+        *proof_out = outp;
+        *proof_len = S.b.size();
+        return S252_OK;
+    }();
+    if (fri) s252_fri_destroy(fri);
+    commit_free(mainc); commit_free(auxc); commit_free(comp);
+    return rc;
+}
+extern "C" void s252_cairo_proof_free(uint8_t* proof) { std::free(proof); }

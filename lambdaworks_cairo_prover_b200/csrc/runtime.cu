@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../include/stark252_b200.h"
+#include "cairo.cuh"
 #include "commit.cuh"
 #include "deep.cuh"
 #include "fe.cuh"
@@ -103,6 +104,7 @@ struct s252_commit {
     fe* coeffs = nullptr;       // [n_cols][n_coeffs]
     fe* lde = nullptr;          // [n_cols][n_rows]
     uint64_t* nodes = nullptr;  // [(2*n_rows-1)][4]
+    fe* trace = nullptr;        // [n_cols][n_coeffs] trace evaluations, kept only for the Cairo prover (aux-trace build)
 };
 
 struct FriLayerDev {
@@ -697,6 +699,7 @@ static void commit_free(s252_commit* c) {
     dfree(c->ctx, c->coeffs);
     dfree(c->ctx, c->lde);
     dfree(c->ctx, c->nodes);
+    dfree(c->ctx, c->trace);
     delete c;
 }
 static int fetch_root(s252_ctx* ctx, const uint64_t* nodes, uint8_t root[32]) {
@@ -708,8 +711,33 @@ static int fetch_root(s252_ctx* ctx, const uint64_t* nodes, uint8_t root[32]) {
 // compute_trace_polys + compute_lde_trace_evaluations of interpolate_and_commit; with_tree adds
 // batch_commit.  Without the tree the handle is what one rank of a column-sharded commit holds
 // before the exchange (DESIGN.md "multi-GPU").
+// compute_trace_polys + compute_lde_trace_evaluations (+ batch_commit) over trace columns that are already
+// column-major on the device in the internal format: cols[j * N + i].
+static int lde_from_cols(s252_ctx* ctx, const fe* cols, size_t N, unsigned c, size_t blowup, uint64_t coset_offset, bool with_tree,
+                         s252_commit* cm, uint8_t root[32]) {
+    const size_t M = N * blowup;
+    // compute_trace_polys: interpolate_fft per column
+    TRY(dalloc(ctx, &cm->coeffs, N * c));
+    Xform I;
+    I.logn = ilog2(N);
+    I.inverse = true;
+    TRY(run_ntt(ctx, I, cols, N, false, cm->coeffs, N, false, c));
+    // compute_lde_trace_evaluations: evaluate_offset_fft(blowup, Some(N), h) per column
+    TRY(dalloc(ctx, &cm->lde, M * c));
+    TRY(evaluate_cosets(ctx, cm->coeffs, N, false, ilog2(N), (unsigned)blowup, H::from_u64(coset_offset), cm->lde, M, false, c));
+    if (with_tree) {
+        // batch_commit over the rows of the LDE table
+        TRY(dalloc(ctx, &cm->nodes, 4 * (2 * M - 1)));
+        TRY(build_tree(ctx, cm->lde, M, c, M, cm->nodes));
+        TRY(fetch_root(ctx, cm->nodes, root));
+    } else {
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return S252_OK;
+}
 static int interpolate_lde_impl(s252_ctx* ctx, const s252_fe* trace, size_t n_rows, size_t n_cols, size_t blowup,
-                                uint64_t coset_offset, int mem, bool with_tree, s252_commit** out, uint8_t root[32]) {
+                                uint64_t coset_offset, int mem, bool with_tree, s252_commit** out, uint8_t root[32],
+                                bool keep_trace = false) {
     if (!ctx || !trace || !out || (with_tree && !root)) return S252_ERR_INVALID;
     *out = nullptr;
     CU(ctx, cudaSetDevice(ctx->device));
@@ -730,23 +758,8 @@ static int interpolate_lde_impl(s252_ctx* ctx, const s252_fe* trace, size_t n_ro
         prof_work(ctx, 64.0 * N * c, 0, 0);
         s252::rows_lw_to_cols<<<dim3((unsigned)((N + 31) / 32), (c + 31) / 32), 256, 0, ctx->stream>>>(dtrace, N, c, cols.p, N);
         LAUNCH_CHECK(ctx);
-        // compute_trace_polys: interpolate_fft per column
-        TRY(dalloc(ctx, &cm->coeffs, N * c));
-        Xform I;
-        I.logn = ilog2(N);
-        I.inverse = true;
-        TRY(run_ntt(ctx, I, cols.p, N, false, cm->coeffs, N, false, c));
-        // compute_lde_trace_evaluations: evaluate_offset_fft(blowup, Some(N), h) per column
-        TRY(dalloc(ctx, &cm->lde, M * c));
-        TRY(evaluate_cosets(ctx, cm->coeffs, N, false, ilog2(N), (unsigned)blowup, H::from_u64(coset_offset), cm->lde, M, false, c));
-        if (with_tree) {
-            // batch_commit over the rows of the LDE table
-            TRY(dalloc(ctx, &cm->nodes, 4 * (2 * M - 1)));
-            TRY(build_tree(ctx, cm->lde, M, c, M, cm->nodes));
-            TRY(fetch_root(ctx, cm->nodes, root));
-        } else {
-            CU(ctx, cudaStreamSynchronize(ctx->stream));
-        }
+        TRY(lde_from_cols(ctx, cols.p, N, c, blowup, coset_offset, with_tree, cm, root));
+        if (keep_trace) { cm->trace = cols.p; cols.p = nullptr; }
         return S252_OK;
     }();
     if (rc != S252_OK) { commit_free(cm); return rc; }
