@@ -68,6 +68,10 @@ int s252_cairo_build_execution_trace(const uint8_t *trace_le, size_t trace_len, 
                                      size_t memory_len, size_t program_size, const uint64_t *rc_range,
                                      const uint64_t *output_range, s252_cairo_trace **out);
 void s252_cairo_trace_destroy(s252_cairo_trace *t);
+/* Registers the table's pages with the CUDA driver so that round 1 uploads it by DMA (done implicitly
+ * by the first s252_cairo_round1 / s252_cairo_prove on the handle; call it earlier to keep the
+ * one-off registration cost out of the first proof). */
+int s252_cairo_trace_pin(const s252_cairo_trace *t);
 size_t s252_cairo_trace_n_rows(const s252_cairo_trace *t);
 size_t s252_cairo_trace_n_cols(const s252_cairo_trace *t);
 const s252_fe *s252_cairo_trace_table(const s252_cairo_trace *t);   /* row-major n_rows x n_cols, LW */
@@ -110,6 +114,8 @@ int s252_cairo_round2(s252_ctx *ctx, const s252_cairo_trace *trace, s252_commit 
 int s252_cairo_prove(s252_ctx *ctx, const s252_cairo_trace *trace, size_t blowup, size_t fri_number_of_queries,
                      uint64_t coset_offset, uint8_t grinding_factor, uint8_t **proof_out, size_t *proof_len);
 void s252_cairo_proof_free(uint8_t *proof);
+/* Diagnostics: host wall-clock milliseconds per stage of the last s252_cairo_prove on this thread, as JSON. */
+const char *s252_cairo_last_prove_stages(void);
 
 #ifdef __cplusplus
 }

@@ -89,6 +89,7 @@ SIGNATURES = {
     "s252_cairo_build_main_trace": (_i, [_vp, _sz, _vp, _sz, _sz, _vp, _vp, C.POINTER(_vp)]),
     "s252_cairo_build_execution_trace": (_i, [_vp, _sz, _vp, _sz, _sz, _vp, _vp, C.POINTER(_vp)]),
     "s252_cairo_trace_destroy": (None, [_vp]),
+    "s252_cairo_trace_pin": (_i, [_vp]),
     "s252_cairo_trace_n_rows": (_sz, [_vp]),
     "s252_cairo_trace_n_cols": (_sz, [_vp]),
     "s252_cairo_trace_table": (_vp, [_vp]),
@@ -101,6 +102,7 @@ SIGNATURES = {
     "s252_cairo_round2": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _u64, _vp, C.POINTER(_vp)]),
     "s252_cairo_prove": (_i, [_vp, _vp, _sz, _sz, _u64, _u8, C.POINTER(_vp), C.POINTER(_sz)]),
     "s252_cairo_proof_free": (None, [_vp]),
+    "s252_cairo_last_prove_stages": (C.c_char_p, []),
 }
 
 

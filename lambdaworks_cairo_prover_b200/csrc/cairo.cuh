@@ -185,166 +185,191 @@ struct CairoEval {
     //   tcoef = (alpha_k * x^(2n - n (deg_k - 1)) + beta_k) / (x^n - 1)
     const fe* bcoef;
     const fe* tcoef;
+    fe two, b15, b16, b32, b48;  // 2, 2^15, 2^16, 2^32, 2^48
     fe* out;                     // [m]
 };
 
-#define CMUL fe_mul_full
-#define CADD fe_add_full
-#define CSUB fe_sub_full
-
 // exemption flags of CairoAIR::new (air.rs:613-625): constraints that hold everywhere but the last row
-__device__ __forceinline__ bool cairo_exempt(int k) {
+__device__ __forceinline__ constexpr bool cairo_exempt(int k) {
     return (k >= 20 && k <= 23) || k == 34 || k == 38 || k == 42 || k == 45;
 }
 
-__global__ void __launch_bounds__(CAIRO_EVAL_THREADS) cairo_constraints_kernel(CairoEval P) {
+// One thread per LDE row.  Arithmetic is lazy (fe.cuh): products are < 2p, sums/differences carry their
+// bound in the comments (in units of p) and stay below 31p, which is what fe_mul accepts against a
+// reduced coefficient; the four accumulators are reduced after every addition.  The kernel runs in
+// phases that reload what they need (L1/L2 hits) so that few values are live at a time.
+#define LM fe_mul
+#define LA fe_add_lazy
+#define LS1 fe_sub_lazy<1>
+#define ACC(dst, a, b) dst = fe_reduce(fe_add_lazy(dst, fe_mul(a, b)))
+
+__global__ void __launch_bounds__(CAIRO_EVAL_THREADS, 3) cairo_constraints_kernel(CairoEval P) {
     const unsigned long long i = (unsigned long long)blockIdx.x * CAIRO_EVAL_THREADS + threadIdx.x;
     if (i >= P.m) return;
     const unsigned long long i2 = (i + P.blowup) & (P.m - 1);     // Frame::read_from_trace, offsets [0, 1]
     const unsigned r = (unsigned)(i & (P.blowup - 1));
     const fe* tc = P.tcoef + r;
     const unsigned bs = P.blowup;
-    // value of column j of the combined row (main columns, then auxiliary columns)
-    auto cur = [&](unsigned j) { return ld_fe(P.main + (unsigned long long)j * P.m + i); };
-    auto nxt = [&](unsigned j) { return ld_fe(P.main + (unsigned long long)j * P.m + i2); };
-    auto acur = [&](unsigned j) { return ld_fe(P.aux + (unsigned long long)j * P.m + i); };
-    auto anxt = [&](unsigned j) { return ld_fe(P.aux + (unsigned long long)j * P.m + i2); };
-    auto coef = [&](int k) { return ldg_fe(tc + (unsigned)k * bs); };
+    const fe* mrow = P.main + i;
+    const fe* mnxt = P.main + i2;
+    const fe* arow = P.aux + i;
+    const fe* anx = P.aux + i2;
+    const unsigned long long m = P.m;
+#define CUR(j) ld_fe(mrow + (unsigned long long)(j) * m)
+#define NXT(j) ld_fe(mnxt + (unsigned long long)(j) * m)
+#define ACUR(j) ld_fe(arow + (unsigned long long)(j) * m)
+#define ANXT(j) ld_fe(anx + (unsigned long long)(j) * m)
+#define COEF(k) ldg_fe(tc + (unsigned)(k) * bs)
     const fe one = fe_one();
     fe acc = fe_zero(), acc_ex = fe_zero();          // plain and exempted (times x - g^(n-1)) constraints
-    auto put = [&](int k, const fe& c) {
-        const fe t = CMUL(coef(k), c);
-        if (cairo_exempt(k)) acc_ex = CADD(acc_ex, t); else acc = CADD(acc, t);
-    };
+    fe sel = fe_zero(), sel_ex = fe_zero();          // constraints 16..30: times the selector (enforce_selector, air.rs:986-991)
 
-    // ---- flags: bit constraints and f0~ (air.rs:869-898)
-    fe f0 = fe_zero();
+    // ---- phase A: flags (air.rs:869-898), instruction decomposition, operand addresses (air.rs:900-927)
+    {
+        fe f0 = fe_zero();
 #pragma unroll 1
-    for (int j = 14; j >= 0; --j) {
-        const fe f = cur(j);
-        put(j, CMUL(f, CSUB(f, one)));
-        f0 = CADD(f, CADD(f0, f0));
+        for (int j = 14; j >= 0; --j) {
+            const fe f = CUR(j);
+            const fe c = LM(f, LS1(f, one));                                   // f (f - 1)             < 2
+            ACC(acc, COEF(j), c);
+            f0 = fe_reduce(LA(f, LA(f0, f0)));
+        }
+        ACC(acc, COEF(15), CUR(15));
+        const fe off_dst = CUR(27), off_op0 = CUR(28), off_op1 = CUR(29);
+        {
+            fe s = LA(off_dst, LM(P.b16, off_op0));                              // < 3
+            s = LA(s, LM(P.b32, off_op1));                                       // < 5
+            s = LA(s, LM(P.b48, f0));                                            // < 7
+            ACC(sel, COEF(16), LS1(s, CUR(23)));                                 // INST                  < 8
+        }
+        const fe ap = CUR(17), fp = CUR(18);
+        const fe fpap = LS1(fp, ap);                                             // < 2
+        {   // f*fp + (1-f)*ap = ap + f*(fp - ap)
+            fe s = LA(LA(ap, LM(CUR(0), fpap)), off_dst);                        // < 4
+            ACC(sel, COEF(17), LS1(LS1(s, P.b15), CUR(20)));                     // DST_ADDR              < 6
+            s = LA(LA(ap, LM(CUR(1), fpap)), off_op0);
+            ACC(sel, COEF(18), LS1(LS1(s, P.b15), CUR(21)));                     // OP0_ADDR              < 6
+        }
+        {
+            const fe f_val = CUR(2), f_fp = CUR(3), f_ap = CUR(4);
+            fe s = LA(LA(LM(f_val, CUR(19)), LM(f_ap, ap)), LM(f_fp, fp));       // < 6
+            const fe rest = LS1(LS1(LS1(one, f_val), f_ap), f_fp);               // < 4
+            s = LA(s, LM(rest, CUR(25)));                                        // < 8
+            s = LA(s, off_op1);                                                  // < 9
+            ACC(sel, COEF(19), LS1(LS1(s, P.b15), CUR(22)));                     // OP1_ADDR              < 11
+        }
     }
-    put(15, cur(15));
-
-    // ---- constraints 16..30 are multiplied by the selector (enforce_selector, air.rs:986-991)
-    fe sel = fe_zero(), sel_ex = fe_zero();
-    auto puts = [&](int k, const fe& c) {
-        const fe t = CMUL(coef(k), c);
-        if (cairo_exempt(k)) sel_ex = CADD(sel_ex, t); else sel = CADD(sel, t);
-    };
-    const fe ap = cur(17), fp = cur(18), pc = cur(19);
-    const fe dst = cur(24), op0 = cur(25), op1 = cur(26), res = cur(16);
-    const fe off_dst = cur(27), off_op0 = cur(28), off_op1 = cur(29);
-    const fe t0 = cur(30), t1 = cur(31), mul = cur(32);
-    fe b15 = fe_zero(), b16 = fe_zero(), b32 = fe_zero(), b48 = fe_zero(), two = fe_zero();
-    b15.l[0] = 1u << 15; b16.l[0] = 1u << 16; b32.l[1] = 1u; b48.l[1] = 1u << 16; two.l[0] = 2;
-    b15 = fe_to_mont(b15); b16 = fe_to_mont(b16); b32 = fe_to_mont(b32); b48 = fe_to_mont(b48); two = fe_to_mont(two);
-    {   // INST
-        fe s = CADD(off_dst, CMUL(b16, off_op0));
-        s = CADD(s, CMUL(b32, off_op1));
-        s = CADD(s, CMUL(b48, f0));
-        puts(16, CSUB(s, cur(23)));
-    }
-    {   // DST_ADDR, OP0_ADDR, OP1_ADDR (air.rs:900-927):  f*fp + (1-f)*ap = ap + f*(fp - ap)
-        const fe fpap = CSUB(fp, ap);
-        puts(17, CSUB(CADD(CADD(ap, CMUL(cur(0), fpap)), CSUB(off_dst, b15)), cur(20)));
-        puts(18, CSUB(CADD(CADD(ap, CMUL(cur(1), fpap)), CSUB(off_op0, b15)), cur(21)));
-        const fe f_val = cur(2), f_fp = cur(3), f_ap = cur(4);
-        fe s = CADD(CADD(CMUL(f_val, pc), CMUL(f_ap, ap)), CMUL(f_fp, fp));
-        s = CADD(s, CMUL(CSUB(CSUB(CSUB(one, f_val), f_ap), f_fp), op0));
-        s = CADD(s, CSUB(off_op1, b15));
-        puts(19, CSUB(s, cur(22)));
-    }
-    const fe f_jnz = cur(9), f_call = cur(12), f_ret = cur(13);
-    const fe inst_size = CADD(cur(2), one);
-    const fe pc_next = nxt(19);
-    {   // NEXT_AP, NEXT_FP, NEXT_PC_1, NEXT_PC_2, T0, T1 (air.rs:929-964)
-        fe s = CADD(ap, CMUL(cur(10), res));
-        s = CADD(s, cur(11));
-        s = CADD(s, CADD(f_call, f_call));
-        puts(20, CSUB(s, nxt(17)));
-        fe q = CADD(CMUL(f_ret, dst), CMUL(f_call, CADD(ap, two)));
-        q = CADD(q, CMUL(CSUB(CSUB(one, f_ret), f_call), fp));
-        puts(21, CSUB(q, nxt(18)));
-        const fe pc_plus = CADD(pc, inst_size);
-        puts(22, CMUL(CSUB(t1, f_jnz), CSUB(pc_next, pc_plus)));
-        const fe f_abs = cur(7), f_rel = cur(8);
-        fe lhs = CADD(CMUL(t0, CSUB(pc_next, CADD(pc, op1))), CMUL(CSUB(one, f_jnz), pc_next));
-        fe rhs = CMUL(CSUB(CSUB(CSUB(one, f_abs), f_rel), f_jnz), pc_plus);
-        rhs = CADD(rhs, CMUL(f_abs, res));
-        rhs = CADD(rhs, CMUL(f_rel, CADD(pc, res)));
-        puts(23, CSUB(lhs, rhs));
-        puts(24, CSUB(CMUL(f_jnz, dst), t0));
-        puts(25, CSUB(CMUL(t0, res), t1));
-        // opcode constraints (air.rs:966-984)
-        puts(26, CSUB(mul, CMUL(op0, op1)));
-        const fe f_add = cur(5), f_mul = cur(6);
-        fe u = CADD(CMUL(f_add, CADD(op0, op1)), CMUL(f_mul, mul));
-        u = CADD(u, CMUL(CSUB(CSUB(CSUB(one, f_add), f_mul), f_jnz), op1));
-        puts(27, CSUB(u, CMUL(CSUB(one, f_jnz), res)));
-        puts(28, CMUL(f_call, CSUB(dst, fp)));
-        puts(29, CMUL(f_call, CSUB(op0, pc_plus)));
-        puts(30, CMUL(cur(14), CSUB(dst, res)));
-    }
+    // ---- phase B: register updates (air.rs:929-964) and opcodes (air.rs:966-984)
     {
-        const fe selector = cur(33);
-        acc = CADD(acc, CMUL(sel, selector));
-        acc_ex = CADD(acc_ex, CMUL(sel_ex, selector));
+        const fe ap = CUR(17), fp = CUR(18), pc = CUR(19);
+        const fe dst = CUR(24), op0 = CUR(25), op1 = CUR(26), res = CUR(16);
+        const fe f_jnz = CUR(9), f_call = CUR(12);
+        {
+            fe s = LA(LA(ap, LM(CUR(10), res)), CUR(11));                        // < 4
+            s = LA(s, LA(f_call, f_call));                                       // < 6
+            ACC(sel_ex, COEF(20), LS1(s, NXT(17)));                              // NEXT_AP               < 7
+        }
+        {
+            const fe f_ret = CUR(13);
+            fe q = LA(LM(f_ret, dst), LM(f_call, LA(ap, P.two)));                // < 4
+            q = LA(q, LM(LS1(LS1(one, f_ret), f_call), fp));                     // < 6
+            ACC(sel_ex, COEF(21), LS1(q, NXT(18)));                              // NEXT_FP               < 7
+        }
+        const fe pc_plus = LA(pc, LA(CUR(2), one));                              // pc + instruction size  < 3
+        const fe t0 = CUR(30), t1 = CUR(31);
+        {
+            const fe pc_next = NXT(19);
+            ACC(sel_ex, COEF(22), LM(LS1(t1, f_jnz), fe_sub_lazy<3>(pc_next, pc_plus)));              // NEXT_PC_1  (2)(4)
+            const fe f_abs = CUR(7), f_rel = CUR(8);
+            fe lhs = LA(LM(t0, fe_sub_lazy<2>(pc_next, LA(pc, op1))), LM(LS1(one, f_jnz), pc_next));   // < 4
+            const fe reg = LS1(LS1(LS1(one, f_abs), f_rel), f_jnz);              // < 4
+            fe rhs = LA(LM(reg, pc_plus), LM(f_abs, res));                       // (4)(3) ok, < 4
+            rhs = LA(rhs, LM(f_rel, LA(pc, res)));                               // < 6
+            ACC(sel_ex, COEF(23), fe_sub_lazy<6>(lhs, rhs));                     // NEXT_PC_2             < 10
+        }
+        ACC(sel, COEF(24), LS1(LM(f_jnz, dst), t0));                             // T0                    < 3
+        ACC(sel, COEF(25), LS1(LM(t0, res), t1));                                // T1                    < 3
+        const fe mul = CUR(32);
+        ACC(sel, COEF(26), fe_sub_lazy<2>(mul, LM(op0, op1)));                   // MUL_1                 < 3
+        {
+            const fe f_add = CUR(5), f_mul = CUR(6);
+            fe u = LA(LM(f_add, LA(op0, op1)), LM(f_mul, mul));                  // < 4
+            u = LA(u, LM(LS1(LS1(LS1(one, f_add), f_mul), f_jnz), op1));         // < 6
+            ACC(sel, COEF(27), fe_sub_lazy<2>(u, LM(LS1(one, f_jnz), res)));     // MUL_2                 < 8
+        }
+        ACC(sel, COEF(28), LM(f_call, LS1(dst, fp)));                            // CALL_1
+        ACC(sel, COEF(29), LM(f_call, fe_sub_lazy<3>(op0, pc_plus)));            // CALL_2  (1)(4)
+        ACC(sel, COEF(30), LM(CUR(14), LS1(dst, res)));                          // ASSERT_EQ
+        const fe selector = CUR(33);
+        ACC(acc, sel, selector);
+        ACC(acc_ex, sel_ex, selector);
     }
-
-    // ---- memory: increasing addresses, single-valued, permutation argument (air.rs:993-1096)
+    // ---- phase C: memory -- increasing addresses, single-valued, permutation argument (air.rs:993-1096)
     {
-        const fe a_orig[4] = {nxt(19), cur(20), cur(21), cur(22)};     // a0_next, a1, a2, a3
-        const fe v_orig[4] = {nxt(23), dst, op0, op1};
-        fe a0 = acur(3), v0 = acur(7), p0 = acur(11);
+        fe a0 = ACUR(3), v0 = ACUR(7), p0 = ACUR(11);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const fe a1 = k < 3 ? acur(3 + k + 1) : anxt(3), v1 = k < 3 ? acur(7 + k + 1) : anxt(7), p1 = k < 3 ? acur(11 + k + 1) : anxt(11);
-            const fe step = CSUB(CSUB(a1, a0), one);
-            put(31 + k, CMUL(CSUB(a0, a1), step));
-            put(35 + k, CMUL(CSUB(v0, v1), step));
-            const int o = (k + 1) & 3;
-            const fe l = CMUL(CSUB(P.z, CADD(a1, CMUL(P.alpha, v1))), p1);
-            const fe rr = CMUL(CSUB(P.z, CADD(a_orig[o], CMUL(P.alpha, v_orig[o]))), p0);
-            put(39 + k, CSUB(l, rr));
+            const fe a1 = k < 3 ? ACUR(3 + k + 1) : ANXT(3), v1 = k < 3 ? ACUR(7 + k + 1) : ANXT(7), p1 = k < 3 ? ACUR(11 + k + 1) : ANXT(11);
+            const fe step = LS1(LS1(a1, a0), one);                               // < 3
+            const fe c_inc = LM(LS1(a0, a1), step), c_val = LM(LS1(v0, v1), step);
+            // original (address, value) of slot k+1; slot 4 is slot 0 of the next row
+            const fe ao = k == 0 ? CUR(20) : k == 1 ? CUR(21) : k == 2 ? CUR(22) : NXT(19);
+            const fe vo = k == 0 ? CUR(24) : k == 1 ? CUR(25) : k == 2 ? CUR(26) : NXT(23);
+            const fe l = LM(fe_sub_lazy<3>(P.z, LA(a1, LM(P.alpha, v1))), p1);    // (4)(1)
+            const fe rr = LM(fe_sub_lazy<3>(P.z, LA(ao, LM(P.alpha, vo))), p0);
+            const fe c_perm = fe_sub_lazy<2>(l, rr);                             // < 4
+            if (k < 3) {
+                ACC(acc, COEF(31 + k), c_inc);
+                ACC(acc, COEF(35 + k), c_val);
+                ACC(acc, COEF(39 + k), c_perm);
+            } else {
+                ACC(acc_ex, COEF(31 + k), c_inc);
+                ACC(acc_ex, COEF(35 + k), c_val);
+                ACC(acc_ex, COEF(39 + k), c_perm);
+            }
             a0 = a1; v0 = v1; p0 = p1;
         }
     }
-    // ---- range check: increasing offsets and permutation argument (air.rs:1098-1139)
+    // ---- phase D: range check -- increasing offsets and permutation argument (air.rs:1098-1139)
     {
-        const fe o_orig[3] = {nxt(27), off_op0, off_op1};
-        fe a0 = acur(0), p0 = acur(15);
+        fe a0 = ACUR(0), p0 = ACUR(15);
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            const fe a1 = k < 2 ? acur(k + 1) : anxt(0), p1 = k < 2 ? acur(15 + k + 1) : anxt(15);
-            put(43 + k, CMUL(CSUB(a0, a1), CSUB(CSUB(a1, a0), one)));
-            const int o = (k + 1) % 3;
-            put(46 + k, CSUB(CMUL(CSUB(P.zrc, a1), p1), CMUL(CSUB(P.zrc, o_orig[o]), p0)));
+            const fe a1 = k < 2 ? ACUR(k + 1) : ANXT(0), p1 = k < 2 ? ACUR(15 + k + 1) : ANXT(15);
+            const fe c_inc = LM(LS1(a0, a1), LS1(LS1(a1, a0), one));
+            const fe oo = k == 0 ? CUR(28) : k == 1 ? CUR(29) : NXT(27);
+            const fe c_perm = fe_sub_lazy<2>(LM(LS1(P.zrc, a1), p1), LM(LS1(P.zrc, oo), p0));        // < 4
+            if (k < 2) ACC(acc, COEF(43 + k), c_inc); else ACC(acc_ex, COEF(43 + k), c_inc);
+            ACC(acc, COEF(46 + k), c_perm);
             a0 = a1; p0 = p1;
         }
     }
     if (P.has_rc) {   // range_check_builtin (air.rs:1141-1160)
         fe s = fe_zero();
 #pragma unroll 1
-        for (int k = 7; k >= 0; --k) s = CADD(cur(34 + k), CMUL(b16, s));
-        put(49, CSUB(s, cur(42)));
+        for (int k = 7; k >= 0; --k) s = fe_reduce(LA(CUR(34 + k), LM(P.b16, s)));
+        ACC(acc, COEF(49), LS1(s, CUR(42)));
     }
-    const fe x = ld_fe(P.dom + i);
-    acc = CADD(acc, CMUL(acc_ex, CSUB(x, P.g_last)));
+    ACC(acc, acc_ex, LS1(ld_fe(P.dom + i), P.g_last));
 
     // ---- boundary constraints (evaluator.rs:58-122): 1/(x - g^s) = g^(-s) * T[i - blowup*s]
     for (unsigned k = 0; k < P.nb; ++k) {
         const unsigned j = P.bcol[k];
-        const fe v = j < P.main_cols ? cur(j) : acur(j - P.main_cols);
-        const fe zi = ld_fe(P.T + ((i + P.m - P.bshift[k]) & (P.m - 1)));
-        acc = CADD(acc, CMUL(CMUL(zi, ldg_fe(P.bcoef + k * bs + r)), CSUB(v, P.bval[k])));
+        const fe v = j < P.main_cols ? CUR(j) : ACUR(j - P.main_cols);
+        const fe zi = ld_fe(P.T + ((i + m - P.bshift[k]) & (m - 1)));
+        ACC(acc, LM(zi, ldg_fe(P.bcoef + k * bs + r)), LS1(v, P.bval[k]));        // (2)(2)
     }
     st_fe(P.out + i, acc);
+#undef CUR
+#undef NXT
+#undef ACUR
+#undef ANXT
+#undef COEF
 }
-#undef CMUL
-#undef CADD
-#undef CSUB
+#undef LM
+#undef LA
+#undef LS1
+#undef ACC
 
 // H(x) coefficients -> even / odd parts (Polynomial::even_odd_decomposition, prover.rs:252): out[j][k] = h[2k + j];
 // *overflow is set when a coefficient of degree >= 2*half is non-zero.

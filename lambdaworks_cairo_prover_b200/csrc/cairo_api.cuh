@@ -16,6 +16,8 @@ struct s252_cairo_trace {
     std::vector<s252_fe> table;   // row-major, LW
     size_t n_rows = 0, n_cols = 0;
     CA::PublicInputs pi;
+    mutable bool pinned = false;  // table pages registered with the CUDA driver (true DMA for the upload of round 1)
+    ~s252_cairo_trace() { if (pinned) cudaHostUnregister((void*)table.data()); }
 };
 
 extern "C" const char* s252_cairo_last_error(void) { return g_cairo_err.c_str(); }
@@ -88,6 +90,17 @@ extern "C" int s252_cairo_build_execution_trace(const uint8_t* trace_le, size_t 
     return cairo_build_common(false, trace_le, trace_len, memory_le, memory_len, program_size, rc_range, output_range, out);
 }
 extern "C" void s252_cairo_trace_destroy(s252_cairo_trace* t) { delete t; }
+extern "C" int s252_cairo_trace_pin(const s252_cairo_trace* t) {
+    if (!t) return S252_ERR_INVALID;
+    if (!t->pinned && !t->table.empty()) {
+        if (cudaHostRegister((void*)t->table.data(), t->table.size() * sizeof(s252_fe), cudaHostRegisterDefault) != cudaSuccess) {
+            cudaGetLastError();
+            CAIRO_FAIL(S252_ERR_CUDA, "cudaHostRegister failed");
+        }
+        t->pinned = true;
+    }
+    return S252_OK;
+}
 extern "C" size_t s252_cairo_trace_n_rows(const s252_cairo_trace* t) { return t->n_rows; }
 extern "C" size_t s252_cairo_trace_n_cols(const s252_cairo_trace* t) { return t->n_cols; }
 extern "C" const s252_fe* s252_cairo_trace_table(const s252_cairo_trace* t) { return t->table.data(); }
@@ -164,6 +177,23 @@ extern "C" int s252_cairo_trace_from_table(const s252_fe* table, size_t n_rows, 
 // --------------------------------------------------------------------------------------------
 // GPU prover
 #include <cub/device/device_radix_sort.cuh>
+
+// wall-clock stage timer of the last s252_cairo_prove on this thread (diagnostics; s252_cairo_last_prove_stages)
+#include <chrono>
+static thread_local std::string g_cairo_stages, g_cairo_round1;
+struct StageTimer {
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    std::string json = "{";
+    void mark(const char* name) {
+        const auto t1 = std::chrono::steady_clock::now();
+        char b[96];
+        std::snprintf(b, sizeof b, "%s\"%s\": %.3f", json.size() > 1 ? ", " : "", name, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        json += b;
+        t0 = t1;
+    }
+};
+extern "C" const char* s252_cairo_last_prove_stages(void) { return g_cairo_stages.c_str(); }
+
 
 // inclusive multiplicative scan of data[0..n) in place (suffix products when reverse)
 static int scan_mul(s252_ctx* ctx, fe* data, size_t n, bool reverse) {
@@ -297,7 +327,10 @@ extern "C" int s252_cairo_round1(s252_ctx* ctx, const s252_cairo_trace* trace, s
     const size_t N = trace->n_rows;
     uint8_t root[32];
     s252_commit* mainc = nullptr;
+    s252_cairo_trace_pin(trace);   // first use only; a failure just leaves the table pageable
+    StageTimer R1;
     TRY(interpolate_lde_impl(ctx, trace->table.data(), N, trace->n_cols, blowup, coset_offset, S252_HOST, true, &mainc, root, true));
+    R1.mark("main_commit");
     transcript->append(root, 32);                                   // prover.rs:151
     fe rap[3];
     for (int k = 0; k < 3; ++k) { rap[k] = transcript->to_field(); H::to_lw(rap[k], rap_out[k].limbs); }   // air.rs:731-737
@@ -306,9 +339,12 @@ extern "C" int s252_cairo_round1(s252_ctx* ctx, const s252_cairo_trace* trace, s
     int rc = [&]() -> int {
         TRY(dalloc(ctx, &auxc->trace, N * s252::CAIRO_AUX_COLS));
         TRY(cairo_build_aux(ctx, mainc->trace, N, trace->pi, rap, auxc->trace));
+        R1.mark("aux_build");
         TRY(lde_from_cols(ctx, auxc->trace, N, s252::CAIRO_AUX_COLS, blowup, coset_offset, true, auxc, root));
+        R1.mark("aux_commit");
         return S252_OK;
     }();
+    g_cairo_round1 = R1.json + "}";
     if (rc != S252_OK) { commit_free(mainc); commit_free(auxc); return rc; }
     transcript->append(root, 32);
     *main_out = mainc;
@@ -389,6 +425,7 @@ extern "C" int s252_cairo_round2(s252_ctx* ctx, const s252_cairo_trace* trace, s
     E.main = mainc->lde; E.aux = auxc->lde; E.m = M; E.blowup = (unsigned)b; E.main_cols = mc; E.has_rc = has_rc;
     E.alpha = rap[0]; E.z = rap[1]; E.zrc = rap[2];
     E.g_last = H::pow_u64(g, N - 1);
+    E.two = H::from_u64(2); E.b15 = H::from_u64(1ull << 15); E.b16 = H::from_u64(1ull << 16); E.b32 = H::from_u64(1ull << 32); E.b48 = H::from_u64(1ull << 48);
     E.nb = 8;
     for (int k = 0; k < 8; ++k) { E.bcol[k] = bcs[k].col; E.bshift[k] = (b * bcs[k].step) % M; E.bval[k] = bcs[k].value; }
     TRY(get_coset_tables(ctx, M, coset_offset, &E.dom, &E.T));
@@ -464,9 +501,12 @@ extern "C" int s252_cairo_prove(s252_ctx* ctx, const s252_cairo_trace* trace, si
     s252_commit *mainc = nullptr, *auxc = nullptr, *comp = nullptr;
     s252_fri* fri = nullptr;
     s252_fe rap[3];
+    StageTimer ST;
     int rc = [&]() -> int {
         TRY(s252_cairo_round1(ctx, trace, blowup, coset_offset, &t, &mainc, &auxc, rap));
+        ST.mark("round1");
         TRY(s252_cairo_round2(ctx, trace, mainc, auxc, rap, blowup, coset_offset, &t, &comp));
+        ST.mark("round2");
         // ---- round 3 (prover.rs:650-690): z, H1(z^2), H2(z^2), t_j(z g^k)
         fe g;
         H::primitive_root(ilog2(N), &g);
@@ -487,6 +527,7 @@ extern "C" int s252_cairo_prove(s252_ctx* ctx, const s252_cairo_trace* trace, si
         uint8_t be[32];
         for (int k = 0; k < 2; ++k) { H::to_bytes_be(H::from_lw(hz[k].limbs), be); t.append(be, 32); }
         for (auto& v : ood) { H::to_bytes_be(H::from_lw(v.limbs), be); t.append(be, 32); }
+        ST.mark("round3");
         // ---- round 4 (prover.rs:327-404)
         s252_fe gamma, gamma_p;
         H::to_lw(t.to_field(), gamma.limbs); H::to_lw(t.to_field(), gamma_p.limbs);
@@ -499,6 +540,7 @@ extern "C" int s252_cairo_prove(s252_ctx* ctx, const s252_cairo_trace* trace, si
         std::vector<uint8_t> fri_roots(32 * std::max<size_t>(layers, 1));
         TRY(s252_fri_commit_phase_deep(ctx, layers, tcs, 2, comp, &zlw, offs, 2, ood.data(), &hz[0], &hz[1], &gamma, &gamma_p, tg.data(), &t,
                                        coset_offset, &fri, &last, fri_roots.data()));
+        ST.mark("deep_fri");
         uint8_t challenge[32];
         t.challenge(challenge);
         uint64_t nonce = 0;
@@ -506,6 +548,7 @@ extern "C" int s252_cairo_prove(s252_ctx* ctx, const s252_cairo_trace* trace, si
         uint8_t nb[8];
         put_u64_be(nb, nonce);
         t.append(nb, 8);
+        ST.mark("grinding");
         const size_t Q = layers ? n_queries : 0;                   // fri_query_phase returns nothing without layers (fri/mod.rs:83)
         std::vector<uint64_t> iotas(Q);
         for (auto& i : iotas) i = t.to_usize() % M;
@@ -519,6 +562,7 @@ extern "C" int s252_cairo_prove(s252_ctx* ctx, const s252_cairo_trace* trace, si
             TRY(s252_commit_open(auxc, iotas.data(), Q, aux_rows.data(), aux_paths.data()));
             TRY(s252_commit_open(comp, iotas.data(), Q, comp_rows.data(), comp_paths.data()));
         }
+        ST.mark("openings");
         // ---- StarkProof::serialize
         ByteSink S;
         uint8_t r32[32];
@@ -570,10 +614,13 @@ extern "C" int s252_cairo_prove(s252_ctx* ctx, const s252_cairo_trace* trace, si
         std::memcpy(outp, S.b.data(), S.b.size());
         *proof_out = outp;
         *proof_len = S.b.size();
+        ST.mark("serialize");
         return S252_OK;
     }();
     if (fri) s252_fri_destroy(fri);
     commit_free(mainc); commit_free(auxc); commit_free(comp);
+    ST.mark("free");
+    g_cairo_stages = ST.json + ", \"round1_detail\": " + g_cairo_round1 + "}";
     return rc;
 }
 extern "C" void s252_cairo_proof_free(uint8_t* proof) { std::free(proof); }
