@@ -265,6 +265,8 @@ def run_gpu(args):
     assert out_sync[0] == out_dev[0] and out_sync[2] == out_dev[2], "host-buffer path disagrees"
     assert out_dev[0] == out_e2e[0] and out_dev[2] == out_e2e[2], "device-resident and host-buffer paths disagree"
 
+    cairo_line = None if args.no_cairo else cairo_prove_bench(ctx, args, world, rank, barrier, dist if world > 1 else None)
+
     elems = cfg["elems_per_step"] * world
     value = elems * args.steps / (ms_dev * 1e-3)
     e2e_value = elems * args.steps / (ms_e2e * 1e-3)
@@ -326,11 +328,83 @@ def run_gpu(args):
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline_sample(args.cpu_log_n)
+        if cairo_line is not None:
+            line["cairo_prove"] = cairo_line
+            if not args.no_cpu_baseline and world == 1:
+                line["cairo_prove"]["cpu_baseline"] = cpu_cairo_prove_sample(args.cpu_fib_n)
         print(json.dumps(line))
     for p in list(dev.values()) + [q for s in staging for q in s.values()]:
         ctx.device_free(p)
     if world > 1:
         dist.destroy_process_group()
+
+
+def cairo_prove_bench(ctx, args, world, rank, barrier, dist):
+    """The second half of BASELINE.json's metric: "Cairo fib prove time".  generate_cairo_proof on the
+    regenerated fib(1,1,70000) trace (benches/criterion_prover_70k.rs: ProofOptions::new_secure(
+    Provable80Bits, 3) = blowup 4, 80 queries, grinding 20), host table in, serialized proof out;
+    wall clock around the C ABI call (host orchestration, the 570 MB upload and the read-backs included).
+    With default_test_options the proof must be byte-identical to the reference's golden file."""
+    import torch
+
+    import lambdaworks_cairo_prover_b200 as P
+    from lambdaworks_cairo_prover_b200 import _native as N, cairo
+    fib_n = args.fib_n
+    t0 = time.perf_counter()
+    regs, mem, size = cairo.run_program(cairo.fibonacci_program(fib_n))
+    trace = cairo.build_main_trace(regs, mem, size)
+    front_s = time.perf_counter() - t0
+    N.lib().s252_cairo_trace_pin(trace.handle)
+    identical = None
+    golden = os.path.join(ROOT, "tests", "golden", "reference_proofs", "fibonacci_%d.proof" % fib_n)
+    if fib_n == 70000 and os.path.exists(golden):
+        raw = open(golden, "rb").read()
+        ln = int.from_bytes(raw[:8], "big")
+        identical = cairo.generate_cairo_proof(trace, P.ProofOptions.default_test_options(), ctx) == raw[8:8 + ln]
+    opts = P.ProofOptions.new_secure("Provable80Bits", 3)
+    for _ in range(max(args.warmup, 1)):
+        proof = cairo.generate_cairo_proof(trace, opts, ctx)
+    barrier()
+    times = []
+    for _ in range(args.steps):
+        a = time.perf_counter()
+        proof = cairo.generate_cairo_proof(trace, opts, ctx)
+        ctx.synchronize()
+        times.append((time.perf_counter() - a) * 1e3)
+    stages = json.loads(N.lib().s252_cairo_last_prove_stages().decode())
+    barrier()
+    ms = float(np.median(times))
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return {"metric": "cairo_fib_prove_time", "unit": "ms", "higher_is_better": False, "value": ms,
+            "proofs_per_s": world * 1e3 / ms, "n_gpus": world, "program": "cairo0 fibonacci_%d" % fib_n, "trace_rows": trace.n_rows(),
+            "columns": [trace.n_cols, 18, 2], "options": {"blowup": opts.blowup_factor, "fri_queries": opts.fri_number_of_queries,
+                                                          "coset_offset": opts.coset_offset, "grinding": opts.grinding_factor},
+            "proof_bytes": len(proof), "ms_all": [round(x, 2) for x in times], "stages_ms": stages,
+            "h2d_bytes": int(trace.n_rows() * trace.n_cols * 32), "front_end_s": round(front_s, 2),
+            "golden_proof_byte_identical": identical,
+            "how": "wall clock around s252_cairo_prove (C ABI): pinned host trace table in, StarkProof::serialize bytes out; "
+                   "N>1: one independent proof per GPU, max over ranks"}
+
+
+def cpu_cairo_prove_sample(fib_n):
+    """The CPU restatement of prove::<CairoAIR> (oracle/, pinned byte-for-byte on the reference's golden
+    proof) on a bounded sample: a shorter fibonacci program, same options."""
+    import lambdaworks_cairo_prover_b200 as P
+    from lambdaworks_cairo_prover_b200 import cairo
+    from oracle.cairo_prover import cairo_prove
+    regs, mem, size = cairo.run_program(cairo.fibonacci_program(fib_n))
+    trace = cairo.build_main_trace(regs, mem, size)
+    table = np.array(trace.table).reshape(trace.n_rows(), trace.n_cols, 4)
+    cores = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    cairo_prove(table, trace.pub_inputs, P.ProofOptions.new_secure("Provable80Bits", 3), threads=cores)
+    dt = time.perf_counter() - t0
+    return {"value": dt * 1e3, "unit": "ms", "cores": cores, "kind": "port", "trace_rows": trace.n_rows(),
+            "sample": "fibonacci_%d (2^%d rows instead of 2^19), same options; oracle/ restatement of the reference prover "
+                      "(C kernels, python round structure; LDE and constraint evaluation threaded)" % (fib_n, trace.n_rows().bit_length() - 1)}
 
 
 def run_gpu_sharded(args):
@@ -492,6 +566,7 @@ def run_reference(args):
         "config": workload_config(LOG_N),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        **({} if args.no_cairo else {"cairo_prove": cpu_cairo_prove_sample(args.cpu_fib_n)}),
     }))
 
 
@@ -504,6 +579,9 @@ def main():
     ap.add_argument("--log-n", type=int, default=LOG_N, help="trace length exponent (default: the C2 size)")
     ap.add_argument("--cpu-log-n", type=int, default=15, help="trace length exponent of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cairo", action="store_true", help="skip the Cairo fib prove-time measurement")
+    ap.add_argument("--fib-n", type=int, default=70000, help="fibonacci program of the prove-time measurement")
+    ap.add_argument("--cpu-fib-n", type=int, default=4000, help="fibonacci program of the bounded CPU prove sample")
     ap.add_argument("--mode", default="traces", choices=["traces", "sharded"],
                     help="N>1: 'traces' = one independent trace per GPU (weak scaling, default); 'sharded' = ONE trace, "
                          "columns sharded over the GPUs with an all-to-all before leaf hashing (strong scaling)")
