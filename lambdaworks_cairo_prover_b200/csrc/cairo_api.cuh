@@ -195,33 +195,6 @@ struct StageTimer {
 extern "C" const char* s252_cairo_last_prove_stages(void) { return g_cairo_stages.c_str(); }
 
 
-// inclusive multiplicative scan of data[0..n) in place (suffix products when reverse)
-static int scan_mul(s252_ctx* ctx, fe* data, size_t n, bool reverse) {
-    const size_t tiles = (n + s252::SCAN_TILE - 1) / s252::SCAN_TILE;
-    if (tiles <= 1) {
-        prof_begin(ctx, "scan_mul_tiles");
-        s252::scan_mul_tiles<<<1, s252::SCAN_THREADS, 0, ctx->stream>>>(data, n, nullptr, reverse);
-        LAUNCH_CHECK(ctx);
-        return S252_OK;
-    }
-    Tmp<fe> totals(ctx);
-    TRY(dalloc(ctx, &totals.p, tiles));
-    prof_begin(ctx, "scan_mul_tiles");
-    prof_work(ctx, 64.0 * n, 2.0 * n, 0);
-    s252::scan_mul_tiles<<<(unsigned)tiles, s252::SCAN_THREADS, 0, ctx->stream>>>(data, n, totals.p, reverse);
-    LAUNCH_CHECK(ctx);
-    TRY(scan_mul(ctx, totals.p, tiles, false));
-    prof_begin(ctx, "scan_mul_apply");
-    prof_work(ctx, 64.0 * n, (double)n, 0);
-    s252::scan_mul_apply<<<(unsigned)((n - s252::SCAN_TILE + 255) / 256), 256, 0, ctx->stream>>>(data, n, totals.p, reverse);
-    LAUNCH_CHECK(ctx);
-    return S252_OK;
-}
-static int read_fe(s252_ctx* ctx, const fe* dev, fe* out) {
-    CU(ctx, cudaMemcpyAsync(out, dev, sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
-    return S252_OK;
-}
 // dom[i] = h w^i and T[i] = 1/(dom[i] - 1) over the LDE coset; both cached in the context
 static int get_coset_tables(s252_ctx* ctx, size_t M, uint64_t coset_offset, const fe** dom, const fe** T) {
     fe w;
@@ -231,20 +204,7 @@ static int get_coset_tables(s252_ctx* ctx, size_t M, uint64_t coset_offset, cons
     fe* t; bool fresh;
     TRY(table_alloc(ctx, "cairoT:" + std::to_string(M) + ":" + fe_key(h), M, &t, &fresh));
     if (fresh) {
-        Tmp<fe> a(ctx), b(ctx);
-        TRY(dalloc(ctx, &a.p, M));
-        TRY(dalloc(ctx, &b.p, M));
-        prof_begin(ctx, "sub_const2");
-        s252::sub_const2<<<(unsigned)((M + 255) / 256), 256, 0, ctx->stream>>>(*dom, a.p, b.p, M, H::one());
-        LAUNCH_CHECK(ctx);
-        TRY(scan_mul(ctx, a.p, M, false));
-        TRY(scan_mul(ctx, b.p, M, true));
-        fe total;
-        TRY(read_fe(ctx, a.p + (M - 1), &total));
-        if (H::is_zero(total)) FAIL(ctx, S252_ERR_INVALID, "the LDE coset contains 1 (coset offset %llu)", (unsigned long long)coset_offset);
-        prof_begin(ctx, "batch_inverse_finish");
-        s252::batch_inverse_finish<<<(unsigned)((M + 255) / 256), 256, 0, ctx->stream>>>(t, a.p, b.p, M, H::inv(total));
-        LAUNCH_CHECK(ctx);
+        TRY(invert_shifted(ctx, *dom, M, H::one(), t));
         CU(ctx, cudaStreamSynchronize(ctx->stream));
     }
     *T = t;

@@ -73,7 +73,6 @@ __global__ void __launch_bounds__(EVAL_THREADS) poly_eval_points(const fe* __res
 }
 
 constexpr int DEEP_THREADS = 128;
-constexpr int DEEP_ROWS = 4;          // rows per thread (batch size of the Montgomery inversion = ROWS*(K+1))
 constexpr int DEEP_MAX_TABLES = 4;
 constexpr int DEEP_MAX_K = 4;
 
@@ -84,10 +83,13 @@ struct DeepParams {
     unsigned ntables;                            // the last one is the composition table (H1, H2)
     unsigned K;                                  // frame rows (transition offsets)
     const fe* gammas;                            // device: [trace_cols][K] trace-term coefficients, then gamma, gamma'
-    fe zg[DEEP_MAX_K];                           // z * g^offset_k
+    // 1/(x_i - z g^k) = g^(-k) * U[i - blowup*k]  with  U[i] = 1/(x_i - z):  x_(i - blowup*k) = x_i / g^k
+    const fe* U;                                 // [m]  1/(x_i - z)
+    const fe* V;                                 // [m]  1/(x_i - z^2)
+    unsigned long long rot[DEEP_MAX_K];          // (blowup * offset_k) mod m
+    fe ginv[DEEP_MAX_K];                         // g^(-offset_k)
     fe ck[DEEP_MAX_K];                           // sum_j gamma_jk * t_j(z g^k)
-    fe z2, cz2;                                  // z^2 ; gamma*H1(z^2) + gamma'*H2(z^2)
-    fe h, w, wstep;                              // coset offset, w_M, w_M^DEEP_THREADS
+    fe cz2;                                      // gamma*H1(z^2) + gamma'*H2(z^2)
     unsigned long long m;                        // LDE rows
     fe* out;                                     // [m] evaluations of p0 (internal format)
 };
@@ -103,83 +105,41 @@ __device__ inline fe fe_inverse(const fe& a) {
     return r;
 }
 
+// One thread per LDE row: K running sums over all trace columns (lazy: a product adds < 2p, reduced every
+// 8 columns), then the K + 1 divisions as multiplications by the precomputed inverse tables.
 template <int K>
 __global__ void __launch_bounds__(DEEP_THREADS) deep_composition_kernel(DeepParams P) {
-    extern __shared__ __align__(16) unsigned char deep_smem[];
-    // per thread: ROWS*(K+1) prefix products, laid out [slot][thread] so a warp touches consecutive elements
-    fe* pre = reinterpret_cast<fe*>(deep_smem);
-    constexpr int D = K + 1;
-    const unsigned t = threadIdx.x;
-    const unsigned long long base = (unsigned long long)blockIdx.x * (DEEP_THREADS * DEEP_ROWS) + t;
-    // x of this thread's first row, then step by w^DEEP_THREADS
-    fe x0;
-    {
-        fe acc = P.h, b = P.w;
-        for (unsigned long long e = base; e; e >>= 1) {
-            if (e & 1) acc = fe_mul_full(acc, b);
-            b = fe_mul_full(b, b);
-        }
-        x0 = acc;
-    }
-    // forward pass: denominators and their running product
-    fe run = fe_one();
-    fe x = x0;
-#pragma unroll 1
-    for (int r = 0; r < DEEP_ROWS; ++r) {
+    const unsigned long long row = (unsigned long long)blockIdx.x * DEEP_THREADS + threadIdx.x;
+    if (row >= P.m) return;
+    fe s[K];
 #pragma unroll
-        for (int k = 0; k < D; ++k) {
-            const fe d = fe_sub_full(x, k < K ? P.zg[k] : P.z2);
-            st_fe(pre + ((r * D + k) * DEEP_THREADS + t), run);     // product of everything before this slot
-            run = fe_mul_full(run, d);
-        }
-        x = fe_mul_full(x, P.wstep);
-    }
-    fe inv_run = fe_inverse(run);
-    // backward pass, row by row (last row first): inverse of each denominator, then the row's value
-    // x of the last row
-    fe xr = x0;
-#pragma unroll 1
-    for (int r = 1; r < DEEP_ROWS; ++r) xr = fe_mul_full(xr, P.wstep);
-    fe wstep_inv_unused = fe_zero();
-    (void)wstep_inv_unused;
-#pragma unroll 1
-    for (int r = DEEP_ROWS - 1; r >= 0; --r) {
-        // recompute x for row r (cheap: ROWS is tiny)
-        fe xx = x0;
-#pragma unroll 1
-        for (int q = 0; q < r; ++q) xx = fe_mul_full(xx, P.wstep);
-        fe inv[D];
+    for (int k = 0; k < K; ++k) s[k] = fe_zero();
+    const fe* g = P.gammas;
+    unsigned pending = 0;
+    for (unsigned tb = 0; tb + 1 < P.ntables; ++tb) {
+        const fe* col = P.cols[tb] + row;
+        for (unsigned j = 0; j < P.ncols[tb]; ++j) {
+            const fe v = ld_fe(col + (unsigned long long)j * P.strides[tb]);
 #pragma unroll
-        for (int k = D - 1; k >= 0; --k) {
-            const fe before = ld_fe(pre + ((r * D + k) * DEEP_THREADS + t));
-            inv[k] = fe_mul_full(inv_run, before);                  // 1/d = (1/prod_through) * prod_before
-            const fe d = fe_sub_full(xx, k < K ? P.zg[k] : P.z2);
-            inv_run = fe_mul_full(inv_run, d);                      // drop this denominator
-        }
-        const unsigned long long row = base + (unsigned long long)r * DEEP_THREADS;
-        if (row < P.m) {
-            fe s[K];
+            for (int k = 0; k < K; ++k) s[k] = fe_add_lazy(s[k], fe_mul(v, ldg_fe(g + k)));        // + < 2p
+            g += K;
+            if (++pending == 8) {
 #pragma unroll
-            for (int k = 0; k < K; ++k) s[k] = fe_zero();
-            const fe* g = P.gammas;
-            for (unsigned tb = 0; tb + 1 < P.ntables; ++tb) {
-                const fe* col = P.cols[tb] + row;
-                for (unsigned j = 0; j < P.ncols[tb]; ++j) {
-                    const fe v = ld_fe(col + (unsigned long long)j * P.strides[tb]);
-#pragma unroll
-                    for (int k = 0; k < K; ++k) s[k] = fe_reduce(fe_add_lazy(s[k], fe_mul(v, ldg_fe(g + k))));
-                    g += K;
-                }
+                for (int k = 0; k < K; ++k) s[k] = fe_reduce(s[k]);                                  // < 17p before
+                pending = 0;
             }
-            const unsigned ct = P.ntables - 1;
-            const fe h1 = ld_fe(P.cols[ct] + row), h2 = ld_fe(P.cols[ct] + P.strides[ct] + row);
-            const fe sz = fe_reduce(fe_add_lazy(fe_mul(h1, ldg_fe(g)), fe_mul(h2, ldg_fe(g + 1))));
-            fe acc = fe_mul_full(fe_sub_full(sz, P.cz2), inv[K]);
-#pragma unroll
-            for (int k = 0; k < K; ++k) acc = fe_add_full(acc, fe_mul_full(fe_sub_full(s[k], P.ck[k]), inv[k]));
-            st_fe(P.out + row, acc);
         }
     }
+    const unsigned ct = P.ntables - 1;
+    const fe h1 = ld_fe(P.cols[ct] + row), h2 = ld_fe(P.cols[ct] + P.strides[ct] + row);
+    const fe sz = fe_reduce(fe_add_lazy(fe_mul(h1, ldg_fe(g)), fe_mul(h2, ldg_fe(g + 1))));
+    fe acc = fe_mul_full(fe_sub_full(sz, P.cz2), ld_fe(P.V + row));
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const fe inv = fe_mul(P.ginv[k], ld_fe(P.U + ((row + P.m - P.rot[k]) & (P.m - 1))));         // < 2p
+        acc = fe_reduce(fe_add_lazy(acc, fe_mul(fe_sub_lazy<1>(fe_reduce(s[k]), P.ck[k]), inv)));    // (2)(2)
+    }
+    st_fe(P.out + row, acc);
 }
 
 }  // namespace s252

@@ -1100,6 +1100,55 @@ extern "C" int s252_commit_evaluate_at(s252_commit* c, const s252_fe* points, si
     return S252_OK;
 }
 
+// multiplicative scans (kernels in cairo.cuh): inclusive product of data[0..n) in place (suffix products when reverse)
+static int scan_mul(s252_ctx* ctx, fe* data, size_t n, bool reverse) {
+    const size_t tiles = (n + s252::SCAN_TILE - 1) / s252::SCAN_TILE;
+    if (tiles <= 1) {
+        prof_begin(ctx, "scan_mul_tiles");
+        s252::scan_mul_tiles<<<1, s252::SCAN_THREADS, 0, ctx->stream>>>(data, n, nullptr, reverse);
+        LAUNCH_CHECK(ctx);
+        return S252_OK;
+    }
+    Tmp<fe> totals(ctx);
+    TRY(dalloc(ctx, &totals.p, tiles));
+    prof_begin(ctx, "scan_mul_tiles");
+    prof_work(ctx, 64.0 * n, 2.0 * n, 0);
+    s252::scan_mul_tiles<<<(unsigned)tiles, s252::SCAN_THREADS, 0, ctx->stream>>>(data, n, totals.p, reverse);
+    LAUNCH_CHECK(ctx);
+    TRY(scan_mul(ctx, totals.p, tiles, false));
+    prof_begin(ctx, "scan_mul_apply");
+    prof_work(ctx, 64.0 * n, (double)n, 0);
+    s252::scan_mul_apply<<<(unsigned)((n - s252::SCAN_TILE + 255) / 256), 256, 0, ctx->stream>>>(data, n, totals.p, reverse);
+    LAUNCH_CHECK(ctx);
+    return S252_OK;
+}
+static int read_fe(s252_ctx* ctx, const fe* dev, fe* out) {
+    CU(ctx, cudaMemcpyAsync(out, dev, sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return S252_OK;
+}
+// out[i] = 1 / (dom[i] - c) for a whole array with ONE field inversion (on the host): prefix and suffix
+// products are two scans, 1/x_i = prefix[i-1] * suffix[i+1] / total.
+static int invert_shifted(s252_ctx* ctx, const fe* dom, size_t n, const fe& c, fe* out) {
+    Tmp<fe> a(ctx), b(ctx);
+    TRY(dalloc(ctx, &a.p, n));
+    TRY(dalloc(ctx, &b.p, n));
+    prof_begin(ctx, "sub_const2");
+    prof_work(ctx, 96.0 * n, 0, 0);
+    s252::sub_const2<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(dom, a.p, b.p, n, c);
+    LAUNCH_CHECK(ctx);
+    TRY(scan_mul(ctx, a.p, n, false));
+    TRY(scan_mul(ctx, b.p, n, true));
+    fe total;
+    TRY(read_fe(ctx, a.p + (n - 1), &total));
+    if (H::is_zero(total)) FAIL(ctx, S252_ERR_INVALID, "division by zero: the point lies on the evaluation domain");
+    prof_begin(ctx, "batch_inverse_finish");
+    prof_work(ctx, 96.0 * n, 2.0 * n, 0);
+    s252::batch_inverse_finish<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(out, a.p, b.p, n, H::inv(total));
+    LAUNCH_CHECK(ctx);
+    return S252_OK;
+}
+
 // Round 4 from the resident commits: DEEP composition polynomial as evaluations on the LDE coset
 // (replaces compute_deep_composition_poly, prover.rs:410-482, and FRI layer 0's transform), then
 // fri_commit_phase (fri/mod.rs:20-72).
@@ -1143,39 +1192,45 @@ extern "C" int s252_fri_commit_phase_deep(s252_ctx* ctx, size_t number_layers, s
     for (size_t i = 0; i < total_cols * K; ++i) gammas[i] = H::from_lw(trace_gammas[i].limbs);
     gammas[total_cols * K] = gam;
     gammas[total_cols * K + 1] = gamp;
+    const size_t blowup = M / Ntrace;
+    const fe ginv1 = H::inv(g);
     for (unsigned k = 0; k < K; ++k) {
-        P.zg[k] = H::mul(zz, H::pow_u64(g, transition_offsets[k]));
         fe acc = H::zero();
         for (size_t j = 0; j < total_cols; ++j) acc = H::add(acc, H::mul(gammas[j * K + k], H::from_lw(trace_ood[k * total_cols + j].limbs)));
         P.ck[k] = acc;
+        P.rot[k] = (blowup * (transition_offsets[k] % Ntrace)) % M;
+        P.ginv[k] = H::pow_u64(ginv1, transition_offsets[k]);
     }
-    P.z2 = H::sqr(zz);
     P.cz2 = H::add(H::mul(gam, H::from_lw(h1_z2->limbs)), H::mul(gamp, H::from_lw(h2_z2->limbs)));
     const fe h = H::from_u64(coset_offset);
-    P.h = h;
-    H::primitive_root(ilog2(M), &P.w);
-    P.wstep = H::pow_u64(P.w, s252::DEEP_THREADS);
+    fe wM;
+    H::primitive_root(ilog2(M), &wM);
     s252_fri* f = new s252_fri();
     f->ctx = ctx; f->domain_size = M;
     int rc = [&]() -> int {
-        Tmp<fe> dg(ctx);
+        Tmp<fe> dg(ctx), dU(ctx), dV(ctx);
         TRY(dalloc(ctx, &dg.p, gammas.size()));
         CU(ctx, cudaMemcpyAsync(dg.p, gammas.data(), gammas.size() * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
         P.gammas = dg.p;
+        // inverse tables over the LDE coset x_i = h w^i
+        const fe* dom;
+        TRY(get_power_table(ctx, M, wM, h, &dom));
+        TRY(dalloc(ctx, &dU.p, M));
+        TRY(dalloc(ctx, &dV.p, M));
+        TRY(invert_shifted(ctx, dom, M, zz, dU.p));
+        TRY(invert_shifted(ctx, dom, M, H::sqr(zz), dV.p));
+        P.U = dU.p; P.V = dV.p;
         FriLayerDev cur;
         cur.size = M;
         TRY(dalloc(ctx, &cur.evals, M));
         f->layers.push_back(cur);
         P.out = f->layers[0].evals;
-        const unsigned rows_per_block = s252::DEEP_THREADS * s252::DEEP_ROWS;
-        const unsigned blocks = (unsigned)((M + rows_per_block - 1) / rows_per_block);
-        const size_t smem = (size_t)s252::DEEP_ROWS * (K + 1) * s252::DEEP_THREADS * sizeof(fe);
+        const unsigned blocks = (unsigned)((M + s252::DEEP_THREADS - 1) / s252::DEEP_THREADS);
         prof_begin(ctx, "deep_composition_kernel");
-        prof_work(ctx, 32.0 * M * (total_cols + 3), (double)M * (total_cols * K + 2 + 22.0 * (K + 1)), 0);
-#define S252_DEEP_LAUNCH(KK)                                                                                              \
-        case KK:                                                                                                          \
-            CU(ctx, cudaFuncSetAttribute(s252::deep_composition_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            s252::deep_composition_kernel<KK><<<blocks, s252::DEEP_THREADS, smem, ctx->stream>>>(P);                      \
+        prof_work(ctx, 32.0 * M * (total_cols + 3 + K + 1), (double)M * (total_cols * K + 2 + 2 * (K + 1)), 0);
+#define S252_DEEP_LAUNCH(KK)                                                                       \
+        case KK:                                                                                   \
+            s252::deep_composition_kernel<KK><<<blocks, s252::DEEP_THREADS, 0, ctx->stream>>>(P);  \
             break;
         switch (K) {
             S252_DEEP_LAUNCH(1)
