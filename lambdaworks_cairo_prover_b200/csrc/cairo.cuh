@@ -189,6 +189,17 @@ struct CairoEval {
     fe* out;                     // [m]
 };
 
+// a load the compiler treats as distinct from every other load of the same address (it is served by L1):
+// used to re-read a value instead of keeping it in registers across unrelated work
+__device__ __forceinline__ fe ld_fe_again(const fe* p) {
+    fe r;
+    asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%8];\n\t"
+                 "ld.global.v4.u32 {%4, %5, %6, %7}, [%8 + 16];"
+                 : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7])
+                 : "l"(p));
+    return r;
+}
+
 // exemption flags of CairoAIR::new (air.rs:613-625): constraints that hold everywhere but the last row
 __device__ __forceinline__ constexpr bool cairo_exempt(int k) {
     return (k >= 20 && k <= 23) || k == 34 || k == 38 || k == 42 || k == 45;
@@ -203,7 +214,11 @@ __device__ __forceinline__ constexpr bool cairo_exempt(int k) {
 #define LS1 fe_sub_lazy<1>
 #define ACC(dst, a, b) dst = fe_reduce(fe_add_lazy(dst, fe_mul(a, b)))
 
-__global__ void __launch_bounds__(CAIRO_EVAL_THREADS, 3) cairo_constraints_kernel(CairoEval P) {
+// PHASE 0: flags, instruction, operand addresses (writes out); 1: register updates and opcodes (adds);
+// 2: memory, range check, boundary constraints (adds).  Three launches keep the live set of each small
+// (no spills, 4-5 blocks per SM); the extra traffic is two read-modify-writes of `out`.
+template <int PHASE>
+__global__ void __launch_bounds__(CAIRO_EVAL_THREADS, PHASE == 1 ? 3 : 4) cairo_constraints_kernel(CairoEval P) {
     const unsigned long long i = (unsigned long long)blockIdx.x * CAIRO_EVAL_THREADS + threadIdx.x;
     if (i >= P.m) return;
     const unsigned long long i2 = (i + P.blowup) & (P.m - 1);     // Frame::read_from_trace, offsets [0, 1]
@@ -216,6 +231,7 @@ __global__ void __launch_bounds__(CAIRO_EVAL_THREADS, 3) cairo_constraints_kerne
     const fe* anx = P.aux + i2;
     const unsigned long long m = P.m;
 #define CUR(j) ld_fe(mrow + (unsigned long long)(j) * m)
+#define RCUR(j) ld_fe_again(mrow + (unsigned long long)(j) * m)
 #define NXT(j) ld_fe(mnxt + (unsigned long long)(j) * m)
 #define ACUR(j) ld_fe(arow + (unsigned long long)(j) * m)
 #define ANXT(j) ld_fe(anx + (unsigned long long)(j) * m)
@@ -225,7 +241,7 @@ __global__ void __launch_bounds__(CAIRO_EVAL_THREADS, 3) cairo_constraints_kerne
     fe sel = fe_zero(), sel_ex = fe_zero();          // constraints 16..30: times the selector (enforce_selector, air.rs:986-991)
 
     // ---- phase A: flags (air.rs:869-898), instruction decomposition, operand addresses (air.rs:900-927)
-    {
+    if constexpr (PHASE == 0) {
         fe f0 = fe_zero();
 #pragma unroll 1
         for (int j = 14; j >= 0; --j) {
@@ -258,54 +274,62 @@ __global__ void __launch_bounds__(CAIRO_EVAL_THREADS, 3) cairo_constraints_kerne
             s = LA(s, off_op1);                                                  // < 9
             ACC(sel, COEF(19), LS1(LS1(s, P.b15), CUR(22)));                     // OP1_ADDR              < 11
         }
+        ACC(acc, sel, CUR(33));
     }
-    // ---- phase B: register updates (air.rs:929-964) and opcodes (air.rs:966-984)
-    {
-        const fe ap = CUR(17), fp = CUR(18), pc = CUR(19);
-        const fe dst = CUR(24), op0 = CUR(25), op1 = CUR(26), res = CUR(16);
+    // ---- phase B: register updates (air.rs:929-964) and opcodes (air.rs:966-984).  Values are re-read where
+    // they are used (RCUR: a load the compiler may not merge with an earlier one) instead of being kept live.
+    if constexpr (PHASE == 1) {
         const fe f_jnz = CUR(9), f_call = CUR(12);
         {
-            fe s = LA(LA(ap, LM(CUR(10), res)), CUR(11));                        // < 4
+            fe s = LA(LA(RCUR(17), LM(CUR(10), RCUR(16))), CUR(11));             // < 4
             s = LA(s, LA(f_call, f_call));                                       // < 6
             ACC(sel_ex, COEF(20), LS1(s, NXT(17)));                              // NEXT_AP               < 7
         }
         {
             const fe f_ret = CUR(13);
-            fe q = LA(LM(f_ret, dst), LM(f_call, LA(ap, P.two)));                // < 4
-            q = LA(q, LM(LS1(LS1(one, f_ret), f_call), fp));                     // < 6
+            fe q = LA(LM(f_ret, RCUR(24)), LM(f_call, LA(RCUR(17), P.two)));     // < 4
+            q = LA(q, LM(LS1(LS1(one, f_ret), f_call), RCUR(18)));               // < 6
             ACC(sel_ex, COEF(21), LS1(q, NXT(18)));                              // NEXT_FP               < 7
         }
-        const fe pc_plus = LA(pc, LA(CUR(2), one));                              // pc + instruction size  < 3
-        const fe t0 = CUR(30), t1 = CUR(31);
         {
+            const fe pc = RCUR(19);
+            const fe pc_plus = LA(pc, LA(RCUR(2), one));                         // pc + instruction size  < 3
             const fe pc_next = NXT(19);
-            ACC(sel_ex, COEF(22), LM(LS1(t1, f_jnz), fe_sub_lazy<3>(pc_next, pc_plus)));              // NEXT_PC_1  (2)(4)
+            ACC(sel_ex, COEF(22), LM(LS1(RCUR(31), f_jnz), fe_sub_lazy<3>(pc_next, pc_plus)));        // NEXT_PC_1  (2)(4)
+            fe lhs = LA(LM(RCUR(30), fe_sub_lazy<2>(pc_next, LA(pc, RCUR(26)))), LM(LS1(one, f_jnz), pc_next));   // < 4
             const fe f_abs = CUR(7), f_rel = CUR(8);
-            fe lhs = LA(LM(t0, fe_sub_lazy<2>(pc_next, LA(pc, op1))), LM(LS1(one, f_jnz), pc_next));   // < 4
             const fe reg = LS1(LS1(LS1(one, f_abs), f_rel), f_jnz);              // < 4
+            const fe res = RCUR(16);
             fe rhs = LA(LM(reg, pc_plus), LM(f_abs, res));                       // (4)(3) ok, < 4
             rhs = LA(rhs, LM(f_rel, LA(pc, res)));                               // < 6
             ACC(sel_ex, COEF(23), fe_sub_lazy<6>(lhs, rhs));                     // NEXT_PC_2             < 10
         }
-        ACC(sel, COEF(24), LS1(LM(f_jnz, dst), t0));                             // T0                    < 3
-        ACC(sel, COEF(25), LS1(LM(t0, res), t1));                                // T1                    < 3
-        const fe mul = CUR(32);
-        ACC(sel, COEF(26), fe_sub_lazy<2>(mul, LM(op0, op1)));                   // MUL_1                 < 3
         {
+            const fe t0 = RCUR(30), res = RCUR(16);
+            ACC(sel, COEF(24), LS1(LM(f_jnz, RCUR(24)), t0));                    // T0                    < 3
+            ACC(sel, COEF(25), LS1(LM(t0, res), RCUR(31)));                      // T1                    < 3
+        }
+        {
+            const fe op0 = RCUR(25), op1 = RCUR(26), mul = CUR(32);
+            ACC(sel, COEF(26), fe_sub_lazy<2>(mul, LM(op0, op1)));               // MUL_1                 < 3
             const fe f_add = CUR(5), f_mul = CUR(6);
             fe u = LA(LM(f_add, LA(op0, op1)), LM(f_mul, mul));                  // < 4
             u = LA(u, LM(LS1(LS1(LS1(one, f_add), f_mul), f_jnz), op1));         // < 6
-            ACC(sel, COEF(27), fe_sub_lazy<2>(u, LM(LS1(one, f_jnz), res)));     // MUL_2                 < 8
+            ACC(sel, COEF(27), fe_sub_lazy<2>(u, LM(LS1(one, f_jnz), RCUR(16)))); // MUL_2                 < 8
         }
-        ACC(sel, COEF(28), LM(f_call, LS1(dst, fp)));                            // CALL_1
-        ACC(sel, COEF(29), LM(f_call, fe_sub_lazy<3>(op0, pc_plus)));            // CALL_2  (1)(4)
-        ACC(sel, COEF(30), LM(CUR(14), LS1(dst, res)));                          // ASSERT_EQ
+        {
+            const fe dst = RCUR(24);
+            ACC(sel, COEF(28), LM(f_call, LS1(dst, RCUR(18))));                  // CALL_1
+            ACC(sel, COEF(30), LM(CUR(14), LS1(dst, RCUR(16))));                 // ASSERT_EQ
+            const fe pc_plus = LA(RCUR(19), LA(RCUR(2), one));
+            ACC(sel, COEF(29), LM(f_call, fe_sub_lazy<3>(RCUR(25), pc_plus)));   // CALL_2  (1)(4)
+        }
         const fe selector = CUR(33);
         ACC(acc, sel, selector);
         ACC(acc_ex, sel_ex, selector);
     }
     // ---- phase C: memory -- increasing addresses, single-valued, permutation argument (air.rs:993-1096)
-    {
+    if constexpr (PHASE == 2) {
         fe a0 = ACUR(3), v0 = ACUR(7), p0 = ACUR(11);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -331,7 +355,7 @@ __global__ void __launch_bounds__(CAIRO_EVAL_THREADS, 3) cairo_constraints_kerne
         }
     }
     // ---- phase D: range check -- increasing offsets and permutation argument (air.rs:1098-1139)
-    {
+    if constexpr (PHASE == 2) {
         fe a0 = ACUR(0), p0 = ACUR(15);
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -344,16 +368,18 @@ __global__ void __launch_bounds__(CAIRO_EVAL_THREADS, 3) cairo_constraints_kerne
             a0 = a1; p0 = p1;
         }
     }
-    if (P.has_rc) {   // range_check_builtin (air.rs:1141-1160)
+    if (PHASE == 2 && P.has_rc) {   // range_check_builtin (air.rs:1141-1160)
         fe s = fe_zero();
 #pragma unroll 1
         for (int k = 7; k >= 0; --k) s = fe_reduce(LA(CUR(34 + k), LM(P.b16, s)));
         ACC(acc, COEF(49), LS1(s, CUR(42)));
     }
-    ACC(acc, acc_ex, LS1(ld_fe(P.dom + i), P.g_last));
-
+    if constexpr (PHASE != 0) {
+        ACC(acc, acc_ex, LS1(ld_fe(P.dom + i), P.g_last));
+        acc = fe_reduce(fe_add_lazy(acc, ld_fe(P.out + i)));
+    }
     // ---- boundary constraints (evaluator.rs:58-122): 1/(x - g^s) = g^(-s) * T[i - blowup*s]
-    for (unsigned k = 0; k < P.nb; ++k) {
+    for (unsigned k = 0; PHASE == 2 && k < P.nb; ++k) {
         const unsigned j = P.bcol[k];
         const fe v = j < P.main_cols ? CUR(j) : ACUR(j - P.main_cols);
         const fe zi = ld_fe(P.T + ((i + m - P.bshift[k]) & (m - 1)));
@@ -361,6 +387,7 @@ __global__ void __launch_bounds__(CAIRO_EVAL_THREADS, 3) cairo_constraints_kerne
     }
     st_fe(P.out + i, acc);
 #undef CUR
+#undef RCUR
 #undef NXT
 #undef ACUR
 #undef ANXT

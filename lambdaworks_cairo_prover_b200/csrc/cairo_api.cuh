@@ -399,10 +399,21 @@ extern "C" int s252_cairo_round2(s252_ctx* ctx, const s252_cairo_trace* trace, s
         E.bcoef = dtabs.p; E.tcoef = dtabs.p + 8 * b;
         TRY(dalloc(ctx, &evals.p, M));
         E.out = evals.p;
-        prof_begin(ctx, "cairo_constraints_kernel");
-        prof_work(ctx, 32.0 * M * (mc + 18 + 10 + 5), 160.0 * M, 0);
-        s252::cairo_constraints_kernel<<<(unsigned)((M + s252::CAIRO_EVAL_THREADS - 1) / s252::CAIRO_EVAL_THREADS), s252::CAIRO_EVAL_THREADS, 0, ctx->stream>>>(E);
-        LAUNCH_CHECK(ctx);
+        {
+            const unsigned grid = (unsigned)((M + s252::CAIRO_EVAL_THREADS - 1) / s252::CAIRO_EVAL_THREADS);
+            prof_begin(ctx, "cairo_constraints_kernel<0>");
+            prof_work(ctx, 32.0 * M * 29, 53.0 * M, 0);
+            s252::cairo_constraints_kernel<0><<<grid, s252::CAIRO_EVAL_THREADS, 0, ctx->stream>>>(E);
+            LAUNCH_CHECK(ctx);
+            prof_begin(ctx, "cairo_constraints_kernel<1>");
+            prof_work(ctx, 32.0 * M * 29, 42.0 * M, 0);
+            s252::cairo_constraints_kernel<1><<<grid, s252::CAIRO_EVAL_THREADS, 0, ctx->stream>>>(E);
+            LAUNCH_CHECK(ctx);
+            prof_begin(ctx, "cairo_constraints_kernel<2>");
+            prof_work(ctx, 32.0 * M * 44, 70.0 * M, 0);
+            s252::cairo_constraints_kernel<2><<<grid, s252::CAIRO_EVAL_THREADS, 0, ctx->stream>>>(E);
+            LAUNCH_CHECK(ctx);
+        }
         // compute_composition_poly: interpolate_offset_fft(evaluations, offset) (evaluation_table.rs:27-33)
         TRY(dalloc(ctx, &hco.p, M));
         Xform X;
