@@ -286,8 +286,14 @@ inline bool build_cairo_execution_trace(const std::vector<RegisterState>& regs, 
     const bool rc_builtin = pi.has_rc_segment;
     const size_t cols = MAIN_COLS + (rc_builtin ? RC_BUILTIN_COLS : 0);
     out->n_cols = cols;
+    {
+        size_t p2 = 1;
+        while (p2 < n + (n >> 3) + 64) p2 <<= 1;     // room for the hole / dummy / padding rows build_main_trace appends
+        out->t.reserve(p2 * cols);
+    }
     out->t.assign(n * cols, fe_zero());
     const fe one = H::one();
+    std::vector<size_t> jnz_rows;   // rows whose res is dst^-1: inverted together after the loop
     for (size_t i = 0; i < n; ++i) {
         const RegisterState& s = regs[i];
         const fe* instp = mem.get(s.pc);
@@ -323,7 +329,8 @@ inline bool build_cairo_execution_trace(const std::vector<RegisterState>& regs, 
         fe res;
         if (in.pc_update() == 4) {
             if (!(in.res_logic() == 0 && in.opcode() == 0)) { *err = "Undefined Behavior"; return false; }
-            res = H::is_zero(dst) ? dst : H::inv(dst);
+            res = dst;                                   // dst == 0 ? dst : dst.inv()  (the inversion is batched below)
+            if (!H::is_zero(dst)) jnz_rows.push_back(i);
         } else {
             res = in.res_logic() == 0 ? op1 : in.res_logic() == 1 ? H::add(op0, op1) : H::mul(op0, op1);
         }
@@ -340,6 +347,19 @@ inline bool build_cairo_execution_trace(const std::vector<RegisterState>& regs, 
         r[FRAME_T1] = H::mul(t0, res);
         r[FRAME_MUL] = H::mul(op0, op1);
         r[FRAME_SELECTOR] = (i + 1 == n) ? fe_zero() : one;
+    }
+    if (!jnz_rows.empty()) {   // one field inversion for all jnz rows (Montgomery's trick); t1 = t0 * res follows
+        std::vector<fe> pre(jnz_rows.size());
+        fe acc = one;
+        for (size_t k = 0; k < jnz_rows.size(); ++k) { pre[k] = acc; acc = H::mul(acc, out->row(jnz_rows[k])[FRAME_RES]); }
+        fe inv = H::inv(acc);
+        for (size_t k = jnz_rows.size(); k-- > 0;) {
+            fe* r = out->row(jnz_rows[k]);
+            const fe d = r[FRAME_RES];
+            r[FRAME_RES] = H::mul(inv, pre[k]);
+            inv = H::mul(inv, d);
+            r[FRAME_T1] = H::mul(r[FRAME_T0], r[FRAME_RES]);
+        }
     }
     if (rc_builtin) {   // add_rc_builtin_columns (execution_trace.rs:358-379)
         size_t k = 0;
