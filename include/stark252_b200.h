@@ -115,6 +115,10 @@ int s252_interpolate_and_lde(s252_ctx *ctx, const s252_fe *trace, size_t n_rows,
  * s252_commit_device_lde): e.g. a row block assembled from the LDE shards of several GPUs. */
 int s252_commit_device_columns(s252_ctx *ctx, const void *cols, size_t col_stride, size_t n_cols, size_t n_rows,
                                s252_commit **out, uint8_t root[32]);
+/* The same without the copy: the tree is built over the caller's columns (col_stride must equal n_rows),
+ * which must stay alive and unchanged while the handle is in use. */
+int s252_commit_device_columns_inplace(s252_ctx *ctx, const void *cols, size_t col_stride, size_t n_cols, size_t n_rows,
+                                       s252_commit **out, uint8_t root[32]);
 /* Round 2 (src/starks/prover.rs:254-276): evaluate_polynomial_on_lde_domain for each of n_polys
  * polynomials (polys: n_polys x n_coeffs, polynomial-major; n_coeffs <= domain_size) and
  * batch_commit over the zipped rows. */

@@ -41,6 +41,7 @@ SIGNATURES = {
     "s252_interpolate_and_commit": (_i, [_vp, _vp, _sz, _sz, _sz, _u64, _i, C.POINTER(_vp), _vp]),
     "s252_interpolate_and_lde": (_i, [_vp, _vp, _sz, _sz, _sz, _u64, _i, C.POINTER(_vp)]),
     "s252_commit_device_columns": (_i, [_vp, _vp, _sz, _sz, _sz, C.POINTER(_vp), _vp]),
+    "s252_commit_device_columns_inplace": (_i, [_vp, _vp, _sz, _sz, _sz, C.POINTER(_vp), _vp]),
     "s252_lde_and_commit": (_i, [_vp, _vp, _sz, _sz, _sz, _sz, _u64, _i, C.POINTER(_vp), _vp]),
     "s252_merkle_build": (_i, [_vp, _vp, _sz, _sz, _i, C.POINTER(_vp), _vp]),
     "s252_commit_destroy": (None, [_vp]),

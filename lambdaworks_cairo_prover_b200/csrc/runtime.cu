@@ -105,6 +105,7 @@ struct s252_commit {
     fe* lde = nullptr;          // [n_cols][n_rows]
     uint64_t* nodes = nullptr;  // [(2*n_rows-1)][4]
     fe* trace = nullptr;        // [n_cols][n_coeffs] trace evaluations, kept only for the Cairo prover (aux-trace build)
+    bool owns_lde = true;       // false: the columns belong to the caller (s252_commit_device_columns_inplace)
 };
 
 struct FriLayerDev {
@@ -697,7 +698,7 @@ extern "C" int s252_evaluate_polynomial_on_lde_domain(s252_ctx* ctx, const s252_
 static void commit_free(s252_commit* c) {
     if (!c) return;
     dfree(c->ctx, c->coeffs);
-    dfree(c->ctx, c->lde);
+    if (c->owns_lde) dfree(c->ctx, c->lde);
     dfree(c->ctx, c->nodes);
     dfree(c->ctx, c->trace);
     delete c;
@@ -790,6 +791,30 @@ extern "C" int s252_commit_device_columns(s252_ctx* ctx, const void* cols, size_
         TRY(dalloc(ctx, &cm->lde, n_rows * n_cols));
         CU(ctx, cudaMemcpy2DAsync(cm->lde, n_rows * sizeof(fe), cols, col_stride * sizeof(fe), n_rows * sizeof(fe), n_cols,
                                   cudaMemcpyDeviceToDevice, ctx->stream));
+        TRY(dalloc(ctx, &cm->nodes, 4 * (2 * n_rows - 1)));
+        TRY(build_tree(ctx, cm->lde, n_rows, (unsigned)n_cols, n_rows, cm->nodes));
+        TRY(fetch_root(ctx, cm->nodes, root));
+        return S252_OK;
+    }();
+    if (rc != S252_OK) { commit_free(cm); return rc; }
+    *out = cm;
+    return S252_OK;
+}
+
+// The same without the copy: the tree is built over the caller's columns, which must stay alive and
+// unchanged for as long as the handle is used (a multi-GB row block assembled by an all-to-all).
+extern "C" int s252_commit_device_columns_inplace(s252_ctx* ctx, const void* cols, size_t col_stride, size_t n_cols, size_t n_rows,
+                                                  s252_commit** out, uint8_t root[32]) {
+    if (!ctx || !cols || !out || !root) return S252_ERR_INVALID;
+    *out = nullptr;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (!is_pow2(n_rows) || n_cols == 0 || col_stride != n_rows)
+        FAIL(ctx, S252_ERR_INVALID, "in-place commit needs a power-of-two number of rows and col_stride == n_rows (got %zu, %zu)", n_rows, col_stride);
+    s252_commit* cm = new s252_commit();
+    cm->ctx = ctx; cm->n_cols = n_cols; cm->n_rows = n_rows; cm->n_coeffs = 0;
+    cm->lde = const_cast<fe*>(reinterpret_cast<const fe*>(cols));
+    cm->owns_lde = false;
+    int rc = [&]() -> int {
         TRY(dalloc(ctx, &cm->nodes, 4 * (2 * n_rows - 1)));
         TRY(build_tree(ctx, cm->lde, n_rows, (unsigned)n_cols, n_rows, cm->nodes));
         TRY(fetch_root(ctx, cm->nodes, root));

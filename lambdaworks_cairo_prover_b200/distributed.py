@@ -3,7 +3,9 @@
 One process per GPU.  Columns are independent for interpolation and LDE, so rank g transforms its
 own contiguous range of columns with no communication.  Leaves hash whole rows, so one exchange is
 needed: an all-to-all that turns "my columns, all rows" into "all columns, my row block"
-(rank g ends up with rows [g*M/G, (g+1)*M/G)).  Each rank hashes its block and builds that subtree;
+(rank g ends up with rows [g*M/G, (g+1)*M/G)).  It is issued as grouped point-to-point chunks, one
+per (column, destination), so that nothing is packed or staged, and per pipeline group of columns,
+so that the exchange of one group overlaps the upload and LDE of the next.  Each rank hashes its block and builds that subtree;
 because G is a power of two the subtree roots are exactly level log2(G) of the reference's heap,
 so an all-gather of G digests and G-1 host hashes finish the tree.  The result is the same root and
 the same authentication paths as the single-GPU (and the reference's) tree.
@@ -40,18 +42,47 @@ class _DevicePointer:
         self.__cuda_array_interface__ = {"shape": (n_words,), "typestr": "<i8", "data": (int(ptr), False), "version": 2}
 
 
+def group_ranges(n_cols, n_groups):
+    """Contiguous sub-ranges of one rank's columns: the units of the LDE -> exchange pipeline."""
+    n_groups = max(1, min(n_groups, n_cols))
+    return column_shards(n_cols, n_groups)
+
+
+class _LocalColumns:
+    """This rank's columns (coefficients + LDE, all rows), held as one handle per pipeline group."""
+
+    def __init__(self, handles, ranges):
+        self.handles, self.ranges = handles, ranges
+
+    def _find(self, j):
+        for h, (lo, hi) in zip(self.handles, self.ranges):
+            if lo <= j < hi:
+                return h, j - lo
+        raise IndexError(j)
+
+    def coefficients(self, j):
+        h, k = self._find(j)
+        return h.coefficients(k)
+
+    def lde_column(self, j, first=0, count=None):
+        h, k = self._find(j)
+        return h.lde_column(k, first, count)
+
+    def free(self):
+        for h in self.handles:
+            if h is not None and hasattr(h, "free"):
+                h.free()
+
+
 class GpuBackend:
     """The two compute steps on this rank's GPU, through the C ABI."""
 
     def __init__(self, ctx):
         self.ctx = ctx
         self.device = torch.device("cuda", ctx.device)
+        self._staging = {}
 
-    def lde(self, shard_table, n_rows, n_cols, blowup, coset_offset):
-        """-> (handle, tensor[n_cols, M, 4] int64 view of the LDE columns)"""
-        h = C.c_void_p()
-        self.ctx.check(N.lib().s252_interpolate_and_lde(self.ctx.handle, N.ptr(shard_table), n_rows, n_cols, blowup,
-                                                        coset_offset, N.HOST, C.byref(h)), N.FFTError)
+    def _wrap(self, h, n_rows, n_cols, blowup):
         commit = DeviceCommit.__new__(DeviceCommit)
         commit.ctx, commit.handle, commit.root = self.ctx, h, b""
         commit.n_cols, commit.n_rows, commit.n_coeffs = n_cols, n_rows * blowup, n_rows
@@ -60,14 +91,52 @@ class GpuBackend:
         t = torch.as_tensor(_DevicePointer(ptr, n_cols * n_rows * blowup * 4), device=self.device)
         return commit, t.view(n_cols, n_rows * blowup, 4)
 
+    def lde(self, shard_table, n_rows, n_cols, blowup, coset_offset):
+        """-> (handle, tensor[n_cols, M, 4] int64 view of the LDE columns)"""
+        h = C.c_void_p()
+        self.ctx.check(N.lib().s252_interpolate_and_lde(self.ctx.handle, N.ptr(shard_table), n_rows, n_cols, blowup,
+                                                        coset_offset, N.HOST, C.byref(h)), N.FFTError)
+        return self._wrap(h, n_rows, n_cols, blowup)
+
+    def lde_pipeline(self, group_tables, n_rows, blowup, coset_offset):
+        """Yields (handle, lde tensor) per group.  The upload of group g+1 runs on the library's copy stream
+        while group g is interpolated and extended (the tables should be pinned host memory)."""
+        sizes = [t.nbytes for t in group_tables]
+        key = tuple(sizes)
+        if key not in self._staging:                      # device staging, reused by later commits of the same shape
+            for bufs in self._staging.values():
+                for p in bufs:
+                    self.ctx.device_free(p)
+            self._staging = {key: [self.ctx.device_alloc(sz) for sz in sizes]}
+        staging = self._staging[key]
+
+        def upload(g):
+            t = group_tables[g]
+            addr = t.data_ptr() if hasattr(t, "data_ptr") else t.ctypes.data
+            self.ctx.to_device_async(staging[g], addr, sizes[g])
+
+        upload(0)
+        for g, t in enumerate(group_tables):
+            self.ctx.copy_stream_wait()
+            if g + 1 < len(group_tables):
+                upload(g + 1)
+            c = t.shape[-2] if len(t.shape) == 3 else t.shape[0] // n_rows
+            h = C.c_void_p()
+            self.ctx.check(N.lib().s252_interpolate_and_lde(self.ctx.handle, C.c_void_p(staging[g]), n_rows, c, blowup,
+                                                            coset_offset, N.DEVICE, C.byref(h)), N.FFTError)
+            yield self._wrap(h, n_rows, c, blowup)
+
     def commit_block(self, cols):
-        """cols: tensor[c_total, rows, 4] on this device -> (DeviceCommit with the subtree, subtree root bytes)"""
+        """cols: tensor[c_total, rows, 4] on this device -> (DeviceCommit with the subtree, subtree root bytes).
+        The tree is built over `cols` in place; the returned handle keeps the tensor alive."""
         c_total, rows = cols.shape[0], cols.shape[1]
         h = C.c_void_p()
         root = np.empty(32, dtype=np.uint8)
-        self.ctx.check(N.lib().s252_commit_device_columns(self.ctx.handle, C.c_void_p(cols.data_ptr()), rows, c_total, rows,
-                                                          C.byref(h), N.ptr(root)))
-        return DeviceCommit(self.ctx, h, root.tobytes()), root.tobytes()
+        self.ctx.check(N.lib().s252_commit_device_columns_inplace(self.ctx.handle, C.c_void_p(cols.data_ptr()), rows, c_total, rows,
+                                                                  C.byref(h), N.ptr(root)))
+        commit = DeviceCommit(self.ctx, h, root.tobytes())
+        commit._keepalive = cols
+        return commit, root.tobytes()
 
     def before_collective(self):
         self.ctx.synchronize()          # the library's stream -> visible to NCCL's stream
@@ -143,11 +212,18 @@ class ShardedCommit:
                 h.free()
 
 
-def interpolate_and_commit_sharded(shard_table, n_rows, n_cols_total, blowup, coset_offset, transcript, backend, group=None):
+def interpolate_and_commit_sharded(shard_table, n_rows, n_cols_total, blowup, coset_offset, transcript, backend, group=None,
+                                   pipeline_groups=1):
     """interpolate_and_commit (src/starks/prover.rs:126-159) for ONE trace whose columns are spread
     over the ranks of `group`.  shard_table: this rank's columns as a row-major table
-    (n_rows x c_rank, i.e. TraceTable::get_cols, src/starks/trace.rs:31-43).  Every rank gets the
-    root (appended to its transcript, prover.rs:151)."""
+    (n_rows x c_rank, i.e. TraceTable::get_cols, src/starks/trace.rs:31-43) -- or a LIST of such
+    tables, one per pipeline group (group_ranges(c_rank, K)), in which case the upload and LDE of
+    group g+1 overlap the exchange of group g.  Every rank gets the root (appended to its transcript,
+    prover.rs:151).
+
+    Exchange: rank r sends rows [d*M/G, (d+1)*M/G) of each of its columns to rank d -- one contiguous
+    chunk per (column, destination), straight out of the LDE buffer and straight into the receiver's
+    column-major row block (no packing, no staging copy), as grouped point-to-point operations."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     if not _is_pow2(world):
@@ -161,20 +237,51 @@ def interpolate_and_commit_sharded(shard_table, n_rows, n_cols_total, blowup, co
     counts = [b - a for a, b in shards]
     if min(counts) == 0:
         raise ValueError("fewer columns than ranks: use fewer ranks for this table")
+    tables = list(shard_table) if isinstance(shard_table, (list, tuple)) else None
+    n_groups = len(tables) if tables is not None else 1
+    # every rank runs the same number of exchange rounds; round k carries group k of every rank's columns
+    ranges = [group_ranges(c, n_groups) for c in counts]
+    if any(len(r) != n_groups for r in ranges):
+        raise ValueError("more pipeline groups than columns on some rank")
+    if tables is not None and hasattr(backend, "lde_pipeline"):
+        producer = backend.lde_pipeline(tables, n_rows, blowup, coset_offset)
+    elif tables is not None:
+        producer = (backend.lde(t, n_rows, ranges[rank][g][1] - ranges[rank][g][0], blowup, coset_offset) for g, t in enumerate(tables))
+    else:
+        producer = iter([backend.lde(shard_table, n_rows, c_mine, blowup, coset_offset)])
 
-    local, lde = backend.lde(shard_table, n_rows, c_mine, blowup, coset_offset)      # [c_mine, M, 4]
-    # pack: destination-major [G][c_mine][rows_per] so that each destination's slice is contiguous
-    send = lde.view(c_mine, world, rows_per * 4).permute(1, 0, 2).contiguous().view(world * c_mine, rows_per * 4)
-    recv = torch.empty((n_cols_total, rows_per * 4), dtype=send.dtype, device=send.device)
-    backend.before_collective()
-    dist.all_to_all_single(recv, send, output_split_sizes=counts, input_split_sizes=[c_mine] * world, group=group)
+    recv = None
+    handles, works = [], []
+    for g, (handle, lde) in enumerate(producer):                 # lde: [c_group, M, 4], complete when yielded
+        handles.append(handle)
+        if recv is None:
+            recv = torch.empty((n_cols_total, rows_per, 4), dtype=lde.dtype, device=lde.device)
+        lo, hi = ranges[rank][g]
+        ops = []
+        for d in range(world):
+            if d == rank:
+                continue
+            for c in range(hi - lo):
+                ops.append(dist.P2POp(dist.isend, lde[c, d * rows_per:(d + 1) * rows_per], d if group is None else dist.get_global_rank(group, d), group))
+        for src in range(world):
+            if src == rank:
+                continue
+            slo, shi = ranges[src][g]
+            for c in range(slo, shi):
+                ops.append(dist.P2POp(dist.irecv, recv[shards[src][0] + c], src if group is None else dist.get_global_rank(group, src), group))
+        backend.before_collective()
+        recv[shards[rank][0] + lo:shards[rank][0] + hi].copy_(lde[:, rank * rows_per:(rank + 1) * rows_per])   # my own rows
+        if ops:
+            works.extend(dist.batch_isend_irecv(ops))
+    for w in works:
+        w.wait()
     backend.after_collective()
-    block, sub_root = backend.commit_block(recv.view(n_cols_total, rows_per, 4))
-    mine = torch.frombuffer(bytearray(sub_root), dtype=torch.uint8).to(send.device)
-    gathered = torch.empty(32 * world, dtype=torch.uint8, device=send.device)
+    block, sub_root = backend.commit_block(recv)
+    mine = torch.frombuffer(bytearray(sub_root), dtype=torch.uint8).to(recv.device)
+    gathered = torch.empty(32 * world, dtype=torch.uint8, device=recv.device)
     dist.all_gather_into_tensor(gathered, mine, group=group)
     backend.after_collective()
     roots = bytes(gathered.cpu().numpy().tobytes())
     top = build_top([roots[32 * g:32 * g + 32] for g in range(world)], backend.keccak)
     transcript.append(top[0])
-    return ShardedCommit(backend, group, local, block, top, m, n_cols_total, shards)
+    return ShardedCommit(backend, group, _LocalColumns(handles, ranges[rank]), block, top, m, n_cols_total, shards)

@@ -23,7 +23,7 @@ class OracleBackend:
     """Test double: oracle arithmetic on CPU tensors."""
 
     def lde(self, shard_table, n_rows, n_cols, blowup, coset_offset):
-        r = O.interpolate_and_commit(shard_table.reshape(n_rows, n_cols, 4), blowup, coset_offset, want_nodes=False)
+        r = O.interpolate_and_commit(np.asarray(shard_table).reshape(n_rows, n_cols, 4), blowup, coset_offset, want_nodes=False)
         return None, torch.from_numpy(r["lde"].view(np.int64).copy())
 
     def commit_block(self, cols):
@@ -64,7 +64,14 @@ def main():
         ctx = P.Context(int(os.environ.get("LOCAL_RANK", rank)))
         backend = D.GpuBackend(ctx)
         transcript = P.DefaultTranscript()
-    sc = D.interpolate_and_commit_sharded(shard.reshape(-1, 4), n, n_cols, blowup, 3, transcript, backend)
+    groups = int(sys.argv[5]) if len(sys.argv) > 5 else 1
+    if groups > 1:
+        tables = [np.ascontiguousarray(shard[:, lo:hi]) for lo, hi in D.group_ranges(b - a, groups)]
+        if mode == "nccl":
+            tables = [torch.from_numpy(t.view(np.int64)).pin_memory() for t in tables]
+        sc = D.interpolate_and_commit_sharded(tables, n, n_cols, blowup, 3, transcript, backend)
+    else:
+        sc = D.interpolate_and_commit_sharded(shard.reshape(-1, 4), n, n_cols, blowup, 3, transcript, backend)
     # single-process answer
     want = O.interpolate_and_commit(trace, blowup, 3, threads=4)
     assert sc.root == want["root"], "rank %d: root differs" % rank

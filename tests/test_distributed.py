@@ -21,9 +21,10 @@ def free_port():
     return p
 
 
-def launch(mode, world, logn, n_cols, blowup, timeout=600):
+def launch(mode, world, logn, n_cols, blowup, groups=1, timeout=600):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
-           "--master-addr", "127.0.0.1", "--master-port", str(free_port()), WORKER, mode, str(logn), str(n_cols), str(blowup)]
+           "--master-addr", "127.0.0.1", "--master-port", str(free_port()), WORKER, mode, str(logn), str(n_cols), str(blowup),
+           str(groups)]
     env = dict(os.environ, OMP_NUM_THREADS="1")
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
@@ -47,9 +48,10 @@ def test_build_top_is_the_heap_rule():
     assert top[0] == O.keccak256(top[1] + top[2])
 
 
-@pytest.mark.parametrize("world,logn,n_cols,blowup", [(2, 6, 5, 4), (4, 5, 7, 2), (2, 4, 2, 8)])
-def test_sharded_commit_gloo(world, logn, n_cols, blowup):
-    launch("gloo", world, logn, n_cols, blowup)
+@pytest.mark.parametrize("world,logn,n_cols,blowup,groups", [(2, 6, 5, 4, 1), (4, 5, 7, 2, 1), (2, 4, 2, 8, 1), (2, 5, 9, 4, 3),
+                                                             (4, 4, 10, 2, 2)])
+def test_sharded_commit_gloo(world, logn, n_cols, blowup, groups):
+    launch("gloo", world, logn, n_cols, blowup, groups)
 
 
 @pytest.mark.gpu
@@ -61,3 +63,4 @@ def test_sharded_commit_nccl():
     world = 4 if g >= 4 else 2
     launch("nccl", world, 12, 33, 8)
     launch("nccl", 2, 10, 3, 4)
+    launch("nccl", world, 12, 33, 8, groups=2)
