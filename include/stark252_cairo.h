@@ -108,6 +108,13 @@ int s252_commit_read_trace(s252_commit *c, size_t col, s252_fe *out);
 int s252_cairo_round2(s252_ctx *ctx, const s252_cairo_trace *trace, s252_commit *main_commit, s252_commit *aux_commit,
                       const s252_fe rap[3], size_t blowup, uint64_t coset_offset, s252_transcript *transcript,
                       s252_commit **composition_out);
+/* ConstraintEvaluator::evaluate alone (constraints/evaluator.rs:40-262) with caller-supplied coefficients:
+ * boundary_coeffs = 8 (alpha, beta) pairs, transition_coeffs = 49 (50 with the range-check builtin)
+ * pairs; out = n_rows*blowup evaluations of the composition polynomial on the LDE coset (LW, host).
+ * Works for any table (the AIR need not be satisfied): the parity tests drive it with random traces. */
+int s252_cairo_constraint_evaluations(s252_ctx *ctx, const s252_cairo_trace *trace, s252_commit *main_commit,
+                                      s252_commit *aux_commit, const s252_fe rap[3], const s252_fe *boundary_coeffs,
+                                      const s252_fe *transition_coeffs, size_t blowup, uint64_t coset_offset, s252_fe *out);
 /* generate_cairo_proof (src/cairo/air.rs:1183-1190) = prove::<Stark252PrimeField, CairoAIR>: rounds 1-4
  * on the device and StarkProof::serialize (src/starks/proof/stark.rs:161-218).  *proof_out is malloc'ed
  * by the library; release it with s252_cairo_proof_free. */

@@ -101,6 +101,7 @@ SIGNATURES = {
     "s252_cairo_round1": (_i, [_vp, _vp, _sz, _u64, _vp, C.POINTER(_vp), C.POINTER(_vp), _vp]),
     "s252_commit_read_trace": (_i, [_vp, _sz, _vp]),
     "s252_cairo_round2": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _u64, _vp, C.POINTER(_vp)]),
+    "s252_cairo_constraint_evaluations": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _u64, _vp]),
     "s252_cairo_prove": (_i, [_vp, _vp, _sz, _sz, _u64, _u8, C.POINTER(_vp), C.POINTER(_sz)]),
     "s252_cairo_proof_free": (None, [_vp]),
     "s252_cairo_last_prove_stages": (C.c_char_p, []),

@@ -215,6 +215,19 @@ def round_2_compute_composition_polynomial(trace, main_commit, aux_commit, rap, 
     return DeviceCommit(ctx, h, _root_of(ctx, h))
 
 
+def constraint_evaluations(trace, main_commit, aux_commit, rap, boundary_coeffs, transition_coeffs, options):
+    """ConstraintEvaluator::evaluate (constraints/evaluator.rs:40-262) for CairoAIR on the GPU with
+    explicit coefficients: boundary_coeffs [8, 2, 4], transition_coeffs [49|50, 2, 4] as (alpha, beta).
+    Returns the evaluations of the composition polynomial on the LDE coset, uint64[M, 4]."""
+    ctx = main_commit.ctx
+    out = np.empty((main_commit.n_rows, 4), dtype=np.uint64)
+    ctx.check(N.lib().s252_cairo_constraint_evaluations(ctx.handle, trace.handle, main_commit.handle, aux_commit.handle,
+                                                        N.ptr(N.fe_array(rap)), N.ptr(N.fe_array(boundary_coeffs)),
+                                                        N.ptr(N.fe_array(transition_coeffs)), options.blowup_factor,
+                                                        options.coset_offset, N.ptr(out)))
+    return out
+
+
 def generate_cairo_proof(trace, proof_options, ctx=None):
     """src/cairo/air.rs:1183-1190: prove::<Stark252PrimeField, CairoAIR>(trace, pub_inputs, options) on
     the GPU.  Returns StarkProof::serialize() bytes."""

@@ -323,12 +323,11 @@ extern "C" int s252_commit_read_trace(s252_commit* c, size_t col, s252_fe* out) 
 static const uint8_t CAIRO_DEGREES[50] = {2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 1, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3,
                                           2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 1};
 
-extern "C" int s252_cairo_round2(s252_ctx* ctx, const s252_cairo_trace* trace, s252_commit* mainc, s252_commit* auxc,
-                                 const s252_fe rap_lw[3], size_t blowup, uint64_t coset_offset, s252_transcript* transcript,
-                                 s252_commit** composition_out) {
-    if (!ctx || !trace || !mainc || !auxc || !rap_lw || !transcript || !composition_out) return S252_ERR_INVALID;
-    *composition_out = nullptr;
-    CU(ctx, cudaSetDevice(ctx->device));
+// ConstraintEvaluator::evaluate for CairoAIR (evaluator.rs:40-262) into evals[M] (device, internal format);
+// ba/bb: boundary alphas/betas (8), ta/tb: transition alphas/betas (49, or 50 with the range-check builtin).
+static int cairo_eval_constraints(s252_ctx* ctx, const s252_cairo_trace* trace, const s252_commit* mainc, const s252_commit* auxc,
+                                  const fe rap[3], const fe* ba, const fe* bb, const fe* ta, const fe* tb, size_t blowup,
+                                  uint64_t coset_offset, fe* evals) {
     const CA::PublicInputs& pi = trace->pi;
     const size_t N = trace->n_rows, M = N * blowup, b = blowup;
     if (mainc->n_rows != M || auxc->n_rows != M || auxc->n_cols != s252::CAIRO_AUX_COLS || mainc->n_cols != trace->n_cols)
@@ -338,8 +337,6 @@ extern "C" int s252_cairo_round2(s252_ctx* ctx, const s252_cairo_trace* trace, s
     const bool has_rc = trace->n_cols > CA::MAIN_COLS;
     const unsigned mc = (unsigned)trace->n_cols;
     const int nt = has_rc ? 50 : 49;
-    fe rap[3];
-    for (int k = 0; k < 3; ++k) rap[k] = H::from_lw(rap_lw[k].limbs);
     fe g, w;
     H::primitive_root(ilog2(N), &g);
     H::primitive_root(ilog2(M), &w);
@@ -356,12 +353,6 @@ extern "C" int s252_cairo_round2(s252_ctx* ctx, const s252_cairo_trace* trace, s
                        {CA::FRAME_PC, pi.num_steps - 1, H::from_u64(pi.pc_final)}, {CA::FRAME_AP, pi.num_steps - 1, H::from_u64(pi.ap_final)},
                        {mc + 14, N - 1, perm_final}, {mc + 17, N - 1, H::one()},
                        {mc + 0, 0, H::from_u64(pi.range_check_min)}, {mc + 2, N - 1, H::from_u64(pi.range_check_max)}};
-    // <<<< challenges (prover.rs:598-626): boundary alphas, boundary betas, transition alphas, transition betas
-    fe ba[8], bb[8], ta[50], tb[50];
-    for (int k = 0; k < 8; ++k) ba[k] = transcript->to_field();
-    for (int k = 0; k < 8; ++k) bb[k] = transcript->to_field();
-    for (int k = 0; k < nt; ++k) ta[k] = transcript->to_field();
-    for (int k = 0; k < nt; ++k) tb[k] = transcript->to_field();
     // per-residue tables: x^N takes `blowup` values over the coset (x = h w^i, i mod blowup = r)
     std::vector<fe> tabs((8 + (size_t)nt) * b);
     {
@@ -389,31 +380,68 @@ extern "C" int s252_cairo_round2(s252_ctx* ctx, const s252_cairo_trace* trace, s
     E.nb = 8;
     for (int k = 0; k < 8; ++k) { E.bcol[k] = bcs[k].col; E.bshift[k] = (b * bcs[k].step) % M; E.bval[k] = bcs[k].value; }
     TRY(get_coset_tables(ctx, M, coset_offset, &E.dom, &E.T));
+    Tmp<fe> dtabs(ctx);
+    TRY(dalloc(ctx, &dtabs.p, tabs.size()));
+    CU(ctx, cudaMemcpyAsync(dtabs.p, tabs.data(), tabs.size() * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
+    E.bcoef = dtabs.p; E.tcoef = dtabs.p + 8 * b;
+    E.out = evals;
+    const unsigned grid = (unsigned)((M + s252::CAIRO_EVAL_THREADS - 1) / s252::CAIRO_EVAL_THREADS);
+    prof_begin(ctx, "cairo_constraints_kernel<0>");
+    prof_work(ctx, 32.0 * M * 29, 53.0 * M, 0);
+    s252::cairo_constraints_kernel<0><<<grid, s252::CAIRO_EVAL_THREADS, 0, ctx->stream>>>(E);
+    LAUNCH_CHECK(ctx);
+    prof_begin(ctx, "cairo_constraints_kernel<1>");
+    prof_work(ctx, 32.0 * M * 29, 42.0 * M, 0);
+    s252::cairo_constraints_kernel<1><<<grid, s252::CAIRO_EVAL_THREADS, 0, ctx->stream>>>(E);
+    LAUNCH_CHECK(ctx);
+    prof_begin(ctx, "cairo_constraints_kernel<2>");
+    prof_work(ctx, 32.0 * M * 44, 70.0 * M, 0);
+    s252::cairo_constraints_kernel<2><<<grid, s252::CAIRO_EVAL_THREADS, 0, ctx->stream>>>(E);
+    LAUNCH_CHECK(ctx);
+    CU(ctx, cudaStreamSynchronize(ctx->stream));   // the coefficient tables (host vector, device temporary) go out of scope
+    return S252_OK;
+}
+
+extern "C" int s252_cairo_constraint_evaluations(s252_ctx* ctx, const s252_cairo_trace* trace, s252_commit* mainc, s252_commit* auxc,
+                                                 const s252_fe rap_lw[3], const s252_fe* boundary_coeffs, const s252_fe* transition_coeffs,
+                                                 size_t blowup, uint64_t coset_offset, s252_fe* out) {
+    if (!ctx || !trace || !mainc || !auxc || !rap_lw || !boundary_coeffs || !transition_coeffs || !out) return S252_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    const int nt = trace->n_cols > CA::MAIN_COLS ? 50 : 49;
+    fe rap[3], ba[8], bb[8], ta[50], tb[50];
+    for (int k = 0; k < 3; ++k) rap[k] = H::from_lw(rap_lw[k].limbs);
+    for (int k = 0; k < 8; ++k) { ba[k] = H::from_lw(boundary_coeffs[2 * k].limbs); bb[k] = H::from_lw(boundary_coeffs[2 * k + 1].limbs); }
+    for (int k = 0; k < nt; ++k) { ta[k] = H::from_lw(transition_coeffs[2 * k].limbs); tb[k] = H::from_lw(transition_coeffs[2 * k + 1].limbs); }
+    const size_t M = trace->n_rows * blowup;
+    Tmp<fe> evals(ctx);
+    TRY(dalloc(ctx, &evals.p, M));
+    TRY(cairo_eval_constraints(ctx, trace, mainc, auxc, rap, ba, bb, ta, tb, blowup, coset_offset, evals.p));
+    return read_internal_as_lw(ctx, evals.p, M, out);
+}
+
+extern "C" int s252_cairo_round2(s252_ctx* ctx, const s252_cairo_trace* trace, s252_commit* mainc, s252_commit* auxc,
+                                 const s252_fe rap_lw[3], size_t blowup, uint64_t coset_offset, s252_transcript* transcript,
+                                 s252_commit** composition_out) {
+    if (!ctx || !trace || !mainc || !auxc || !rap_lw || !transcript || !composition_out) return S252_ERR_INVALID;
+    *composition_out = nullptr;
+    CU(ctx, cudaSetDevice(ctx->device));
+    const size_t N = trace->n_rows, M = N * blowup, b = blowup;
+    const int nt = trace->n_cols > CA::MAIN_COLS ? 50 : 49;
+    fe rap[3];
+    for (int k = 0; k < 3; ++k) rap[k] = H::from_lw(rap_lw[k].limbs);
+    // <<<< challenges (prover.rs:598-626): boundary alphas, boundary betas, transition alphas, transition betas
+    fe ba[8], bb[8], ta[50], tb[50];
+    for (int k = 0; k < 8; ++k) ba[k] = transcript->to_field();
+    for (int k = 0; k < 8; ++k) bb[k] = transcript->to_field();
+    for (int k = 0; k < nt; ++k) ta[k] = transcript->to_field();
+    for (int k = 0; k < nt; ++k) tb[k] = transcript->to_field();
     s252_commit* cm = new s252_commit();
     cm->ctx = ctx; cm->n_cols = 2; cm->n_rows = M; cm->n_coeffs = N;
     int rc = [&]() -> int {
-        Tmp<fe> dtabs(ctx), evals(ctx), hco(ctx);
+        Tmp<fe> evals(ctx), hco(ctx);
         Tmp<unsigned> flag(ctx);
-        TRY(dalloc(ctx, &dtabs.p, tabs.size()));
-        CU(ctx, cudaMemcpyAsync(dtabs.p, tabs.data(), tabs.size() * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
-        E.bcoef = dtabs.p; E.tcoef = dtabs.p + 8 * b;
         TRY(dalloc(ctx, &evals.p, M));
-        E.out = evals.p;
-        {
-            const unsigned grid = (unsigned)((M + s252::CAIRO_EVAL_THREADS - 1) / s252::CAIRO_EVAL_THREADS);
-            prof_begin(ctx, "cairo_constraints_kernel<0>");
-            prof_work(ctx, 32.0 * M * 29, 53.0 * M, 0);
-            s252::cairo_constraints_kernel<0><<<grid, s252::CAIRO_EVAL_THREADS, 0, ctx->stream>>>(E);
-            LAUNCH_CHECK(ctx);
-            prof_begin(ctx, "cairo_constraints_kernel<1>");
-            prof_work(ctx, 32.0 * M * 29, 42.0 * M, 0);
-            s252::cairo_constraints_kernel<1><<<grid, s252::CAIRO_EVAL_THREADS, 0, ctx->stream>>>(E);
-            LAUNCH_CHECK(ctx);
-            prof_begin(ctx, "cairo_constraints_kernel<2>");
-            prof_work(ctx, 32.0 * M * 44, 70.0 * M, 0);
-            s252::cairo_constraints_kernel<2><<<grid, s252::CAIRO_EVAL_THREADS, 0, ctx->stream>>>(E);
-            LAUNCH_CHECK(ctx);
-        }
+        TRY(cairo_eval_constraints(ctx, trace, mainc, auxc, rap, ba, bb, ta, tb, blowup, coset_offset, evals.p));
         // compute_composition_poly: interpolate_offset_fft(evaluations, offset) (evaluation_table.rs:27-33)
         TRY(dalloc(ctx, &hco.p, M));
         Xform X;
