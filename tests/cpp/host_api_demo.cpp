@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "stark252_b200.hpp"
+#include "stark252_cairo.hpp"
 
 using namespace stark252;
 
@@ -22,6 +23,28 @@ static void print_hex(const char* tag, const uint8_t* b, size_t n) {
 int main(int argc, char** argv) {
     if (argc > 1 && std::strcmp(argv[1], "--link-only") == 0) {
         std::printf("len %zu\n", s252_evaluate_offset_fft_len(5, 2, 0));
+        return 0;
+    }
+    if (argc > 1 && std::strcmp(argv[1], "--cairo-front-end") == 0) {
+        // host only: the reference's `mul` program (cairo_mem.rs:74-95) through the Cairo machine and build_main_trace
+        const uint64_t words[5] = {0x480680017fff8000ULL, 6, 0x400680017fff7fffULL, 6, 0x208b7fff7fff7ffeULL};
+        std::vector<uint8_t> prog(5 * 32, 0);
+        for (int i = 0; i < 5; ++i)
+            for (int k = 0; k < 8; ++k) prog[32 * i + 31 - k] = (uint8_t)(words[i] >> (8 * k));
+        auto exe = stark252::cairo::run_program(prog);
+        auto trace = stark252::cairo::build_main_trace(exe);
+        const auto pi = trace.pub_inputs();
+        std::printf("steps %zu rows %zu cols %zu ap_final %llu rc %u %u\n", exe.register_states.size() / 24, trace.n_rows(), trace.n_cols(),
+                    (unsigned long long)pi.ap_final, pi.range_check_min, pi.range_check_max);
+        if (argc > 2 && std::strcmp(argv[2], "--prove") == 0) {
+            Context ctx(0);
+            const auto proof = stark252::cairo::generate_cairo_proof(ctx, trace, ProofOptions::default_test_options());
+            uint8_t d[32];
+            s252_keccak256(proof.data(), proof.size(), d);
+            std::printf("proof %zu ", proof.size());
+            for (int i = 0; i < 32; ++i) std::printf("%02x", d[i]);
+            std::printf("\n");
+        }
         return 0;
     }
     try {

@@ -17,7 +17,8 @@ EXE = os.path.join(ROOT, "tests", "cpp", "host_api_demo")
 def build_demo():
     N.lib()
     libdir = os.path.dirname(N.library_path())
-    if not os.path.exists(EXE) or os.path.getmtime(EXE) < max(os.path.getmtime(SRC), os.path.getmtime(N.library_path())):
+    deps = [SRC, N.library_path()] + [os.path.join(ROOT, "include", h) for h in ("stark252_b200.hpp", "stark252_cairo.hpp")]
+    if not os.path.exists(EXE) or os.path.getmtime(EXE) < max(os.path.getmtime(d) for d in deps):
         subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), SRC, "-o", EXE,
                                "-L", libdir, "-lstark252_b200", "-Wl,-rpath," + libdir])
     return EXE
@@ -27,6 +28,27 @@ def test_cpp_layer_compiles_and_links():
     exe = build_demo()
     out = subprocess.run([exe, "--link-only"], capture_output=True, text=True, check=True).stdout
     assert out.strip() == "len 16"
+
+
+def test_cpp_cairo_front_end():
+    """include/stark252_cairo.hpp: run_program + build_main_trace of the reference's `mul` program (host only)."""
+    exe = build_demo()
+    out = subprocess.run([exe, "--cairo-front-end"], capture_output=True, text=True, check=True).stdout
+    assert out.strip() == "steps 3 rows 8 cols 34 ap_final 9 rc 32766 32769"
+
+
+@pytest.mark.gpu
+def test_cpp_cairo_proof_matches_oracle():
+    from lambdaworks_cairo_prover_b200 import ProofOptions, cairo
+    from oracle.cairo_prover import cairo_prove
+    exe = build_demo()
+    res = subprocess.run([exe, "--cairo-front-end", "--prove"], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    regs, mem, size = cairo.run_program([0x480680017fff8000, 6, 0x400680017fff7fff, 6, 0x208b7fff7fff7ffe])
+    t = cairo.build_main_trace(regs, mem, size)
+    table = np.array(t.table).reshape(t.n_rows(), t.n_cols, 4)
+    want = cairo_prove(table, t.pub_inputs, ProofOptions.default_test_options(), threads=1).serialize()
+    assert res.stdout.strip().splitlines()[-1] == "proof %d %s" % (len(want), O.keccak256(want).hex())
 
 
 @pytest.mark.gpu
