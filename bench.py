@@ -571,6 +571,9 @@ def run_reference(args):
 
 
 def main():
+    # stdout carries exactly one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
