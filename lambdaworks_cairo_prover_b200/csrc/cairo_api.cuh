@@ -564,6 +564,7 @@ extern "C" int s252_cairo_prove(s252_ctx* ctx, const s252_cairo_trace* trace, si
         ST.mark("openings");
         // ---- StarkProof::serialize
         ByteSink S;
+        S.b.reserve(4096 + Q * (2 * layers * (depth + 2) + 3 * (depth + 1) + cols + 8) * 32);
         uint8_t r32[32];
         S.u64(N);
         S.u64(2);

@@ -315,4 +315,36 @@ __global__ void gather_paths(const uint64_t* __restrict__ nodes, unsigned depth,
     dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
 }
 
+// fri_query_phase's reads for ALL layers in one launch (fri/mod.rs:74-127).  Layer k has size
+// domain >> k; entry e = ((sym * nq + q) * L + k): value of evaluation[(iota_q + sym*size/2) % size] and
+// its authentication path, padded to `stride` digests.
+struct FriLayerRef { const fe* evals; const uint64_t* nodes; };
+__global__ void fri_query_gather(const FriLayerRef* __restrict__ layers, unsigned L, unsigned log_domain,
+                                 const unsigned long long* __restrict__ iotas, unsigned nq, unsigned stride,
+                                 fe* __restrict__ vals_out, uint64_t* __restrict__ paths_out) {
+    const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned per = stride + 1;                       // slot 0: the value, slots 1..stride: path entries
+    const unsigned long long total = 2ull * nq * L * per;
+    if (t >= total) return;
+    const unsigned slot = (unsigned)(t % per);
+    const unsigned long long e = t / per;
+    const unsigned k = (unsigned)(e % L), q = (unsigned)((e / L) % nq), sym = (unsigned)(e / ((unsigned long long)L * nq));
+    const unsigned depth = log_domain - k;
+    const unsigned long long size = 1ull << depth;
+    const unsigned long long idx = (iotas[q] + (sym ? size / 2 : 0)) & (size - 1);
+    const FriLayerRef lay = layers[k];
+    if (slot == 0) {
+        st_lw(vals_out + e, ld_fe(lay.evals + idx));
+        return;
+    }
+    const unsigned lvl = slot - 1;
+    if (lvl >= depth) return;
+    unsigned long long node = idx + size - 1;
+    for (unsigned s = 0; s < lvl; ++s) node = (node - 1) >> 1;
+    const unsigned long long sib = (node & 1) ? node + 1 : node - 1;
+    const uint64_t* src = lay.nodes + 4 * sib;
+    uint64_t* dst = paths_out + 4 * (e * stride + lvl);
+    dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+}
+
 }  // namespace s252

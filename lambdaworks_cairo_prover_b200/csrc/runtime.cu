@@ -1298,30 +1298,44 @@ extern "C" int s252_fri_query(s252_fri* f, const uint64_t* iotas, size_t n_queri
     s252_ctx* ctx = f->ctx;
     CU(ctx, cudaSetDevice(ctx->device));
     if (!iotas && n_queries) return S252_ERR_INVALID;
-    const size_t L = f->layers.size();
-    std::vector<uint64_t> idx(n_queries), idx_sym(n_queries);
-    std::vector<s252_fe> col(n_queries);
-    std::vector<uint8_t> pth;
+    const size_t L = f->layers.size(), Q = n_queries;
+    if (L == 0 || Q == 0) return S252_OK;
+    const unsigned logd = ilog2(f->domain_size);
+    if ((paths || paths_sym) && path_stride < logd) FAIL(ctx, S252_ERR_INVALID, "path_stride %zu is smaller than the tree depth %u", path_stride, logd);
+    const size_t stride = path_stride ? path_stride : logd;
+    // one launch gathers every layer's values and authentication paths (both the index and its symmetric)
+    std::vector<s252::FriLayerRef> refs(L);
     for (size_t k = 0; k < L; ++k) {
-        const FriLayerDev& lay = f->layers[k];
-        const unsigned depth = ilog2(lay.size);
-        if (paths && path_stride < depth) FAIL(ctx, S252_ERR_INVALID, "path_stride %zu is smaller than the tree depth %u", path_stride, depth);
-        for (size_t q = 0; q < n_queries; ++q) {
-            idx[q] = iotas[q] % lay.size;                              // fri/mod.rs:101
-            idx_sym[q] = (iotas[q] + lay.size / 2) % lay.size;         // fri/mod.rs:102
-        }
-        pth.resize(n_queries * depth * 32);
-        for (int sym = 0; sym < 2; ++sym) {
-            s252_fe* ev = sym ? evals_sym : evals;
-            uint8_t* pp = sym ? paths_sym : paths;
-            TRY(open_common(ctx, lay.evals, lay.size, 1, lay.nodes, lay.size, sym ? idx_sym.data() : idx.data(), n_queries,
-                            ev ? col.data() : nullptr, pp ? pth.data() : nullptr));
-            for (size_t q = 0; q < n_queries; ++q) {
-                if (ev) ev[q * L + k] = col[q];
-                if (pp) std::memcpy(pp + (q * L + k) * path_stride * 32, pth.data() + q * depth * 32, depth * 32);
-            }
-        }
+        if (f->layers[k].size != (f->domain_size >> k)) FAIL(ctx, S252_ERR_INVALID, "internal: unexpected FRI layer size");
+        refs[k] = {f->layers[k].evals, f->layers[k].nodes};
     }
+    Tmp<s252::FriLayerRef> drefs(ctx);
+    Tmp<unsigned long long> didx(ctx);
+    Tmp<fe> dvals(ctx);
+    Tmp<uint64_t> dpaths(ctx);
+    const size_t entries = 2 * Q * L;
+    TRY(dalloc(ctx, &drefs.p, L));
+    TRY(dalloc(ctx, &didx.p, Q));
+    TRY(dalloc(ctx, &dvals.p, entries));
+    TRY(dalloc(ctx, &dpaths.p, entries * stride * 4));
+    CU(ctx, cudaMemcpyAsync(drefs.p, refs.data(), L * sizeof(s252::FriLayerRef), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(didx.p, iotas, Q * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemsetAsync(dpaths.p, 0, entries * stride * 32, ctx->stream));
+    const unsigned long long total = (unsigned long long)entries * (stride + 1);
+    prof_begin(ctx, "fri_query_gather");
+    s252::fri_query_gather<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(drefs.p, (unsigned)L, logd, didx.p, (unsigned)Q,
+                                                                                      (unsigned)stride, dvals.p, dpaths.p);
+    LAUNCH_CHECK(ctx);
+    std::vector<s252_fe> hv(entries);
+    std::vector<uint8_t> hp(entries * stride * 32);
+    CU(ctx, cudaMemcpyAsync(hv.data(), dvals.p, entries * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(hp.data(), dpaths.p, hp.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    const size_t half = Q * L;
+    if (evals) std::memcpy(evals, hv.data(), half * sizeof(s252_fe));
+    if (evals_sym) std::memcpy(evals_sym, hv.data() + half, half * sizeof(s252_fe));
+    if (paths) std::memcpy(paths, hp.data(), half * stride * 32);
+    if (paths_sym) std::memcpy(paths_sym, hp.data() + half * stride * 32, half * stride * 32);
     return S252_OK;
 }
 
