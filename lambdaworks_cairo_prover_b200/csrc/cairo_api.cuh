@@ -13,11 +13,17 @@ struct s252_cairo_run {
     CA::VmResult r;
 };
 struct s252_cairo_trace {
-    std::vector<s252_fe> table;   // row-major, LW
+    std::vector<s252_fe> table;   // row-major, LW (TraceTable.table)
+    std::vector<s252_fe> cols;    // the same table column-major: what round 1 uploads, one group of columns at a time
     size_t n_rows = 0, n_cols = 0;
     CA::PublicInputs pi;
-    mutable bool pinned = false;  // table pages registered with the CUDA driver (true DMA for the upload of round 1)
-    ~s252_cairo_trace() { if (pinned) cudaHostUnregister((void*)table.data()); }
+    mutable bool pinned = false;  // `cols` pages registered with the CUDA driver (true DMA for the upload of round 1)
+    void make_columns() {
+        cols.resize(table.size());
+        for (size_t i = 0; i < n_rows; ++i)
+            for (size_t j = 0; j < n_cols; ++j) cols[j * n_rows + i] = table[i * n_cols + j];
+    }
+    ~s252_cairo_trace() { if (pinned) cudaHostUnregister((void*)cols.data()); }
 };
 
 extern "C" const char* s252_cairo_last_error(void) { return g_cairo_err.c_str(); }
@@ -76,6 +82,7 @@ static int cairo_build_common(bool full, const uint8_t* trace_le, size_t trace_l
     t->n_rows = tab.n_rows();
     t->table.resize(tab.t.size());
     for (size_t i = 0; i < tab.t.size(); ++i) H::to_lw(tab.t[i], t->table[i].limbs);
+    t->make_columns();
     *out = t;
     return S252_OK;
 }
@@ -92,8 +99,8 @@ extern "C" int s252_cairo_build_execution_trace(const uint8_t* trace_le, size_t 
 extern "C" void s252_cairo_trace_destroy(s252_cairo_trace* t) { delete t; }
 extern "C" int s252_cairo_trace_pin(const s252_cairo_trace* t) {
     if (!t) return S252_ERR_INVALID;
-    if (!t->pinned && !t->table.empty()) {
-        if (cudaHostRegister((void*)t->table.data(), t->table.size() * sizeof(s252_fe), cudaHostRegisterDefault) != cudaSuccess) {
+    if (!t->pinned && !t->cols.empty()) {
+        if (cudaHostRegister((void*)t->cols.data(), t->cols.size() * sizeof(s252_fe), cudaHostRegisterDefault) != cudaSuccess) {
             cudaGetLastError();
             CAIRO_FAIL(S252_ERR_CUDA, "cudaHostRegister failed");
         }
@@ -170,6 +177,7 @@ extern "C" int s252_cairo_trace_from_table(const s252_fe* table, size_t n_rows, 
     p.output_segment[0] = pub->output_segment[0]; p.output_segment[1] = pub->output_segment[1];
     for (size_t i = 0; i < pub->n_public_memory; ++i) p.public_memory.push_back({pub_addrs[i], H::from_lw(pub_values[i].limbs)});
     std::sort(p.public_memory.begin(), p.public_memory.end(), [](const std::pair<uint64_t, fe>& a, const std::pair<uint64_t, fe>& b) { return a.first < b.first; });
+    t->make_columns();
     *out = t;
     return S252_OK;
 }
@@ -279,6 +287,64 @@ static int cairo_build_aux(s252_ctx* ctx, const fe* main_cols, size_t N, const C
     return S252_OK;
 }
 
+// interpolate_and_commit (prover.rs:126-159) from a column-major LW table in (pinned) host memory.  The
+// upload is pipelined with the transforms: group g+1 of columns crosses PCIe on the copy stream while
+// group g is converted, interpolated and extended, so only the first group's upload is exposed.
+static int commit_from_host_columns(s252_ctx* ctx, const s252_fe* cols_lw, size_t N, unsigned c, size_t blowup, uint64_t coset_offset,
+                                    bool keep_trace, s252_commit** out, uint8_t root[32]) {
+    if (!is_pow2(N) || c == 0) FAIL(ctx, S252_ERR_INVALID, "FFTError: trace length %zu is not a power of two", N);
+    if (!is_pow2(blowup) || blowup > MAX_COSETS) FAIL(ctx, S252_ERR_INVALID, "blowup factor %zu must be a power of two <= %u", blowup, MAX_COSETS);
+    if (coset_offset == 0) FAIL(ctx, S252_ERR_INVALID, "coset offset must be non-zero");
+    const size_t M = N * blowup;
+    const unsigned K = std::min<unsigned>(4, c);
+    s252_commit* cm = new s252_commit();
+    cm->ctx = ctx; cm->n_cols = c; cm->n_rows = M; cm->n_coeffs = N;
+    std::vector<cudaEvent_t> ev(K, nullptr);
+    cudaEvent_t start = nullptr;
+    int rc = [&]() -> int {
+        Tmp<fe> staged(ctx), cols(ctx);
+        TRY(dalloc(ctx, &staged.p, N * c));
+        TRY(dalloc(ctx, &cols.p, N * c));
+        TRY(dalloc(ctx, &cm->coeffs, N * c));
+        TRY(dalloc(ctx, &cm->lde, M * c));
+        // the staging block may be a recycled one: the copy stream must not overtake work already queued on the compute stream
+        CU(ctx, cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
+        CU(ctx, cudaEventRecord(start, ctx->stream));
+        CU(ctx, cudaStreamWaitEvent(ctx->copy_stream, start, 0));
+        std::vector<unsigned> lo(K + 1);
+        for (unsigned g = 0; g <= K; ++g) lo[g] = (unsigned)((size_t)c * g / K);
+        for (unsigned g = 0; g < K; ++g) {
+            const size_t off = (size_t)lo[g] * N, cnt = (size_t)(lo[g + 1] - lo[g]) * N;
+            CU(ctx, cudaMemcpyAsync(staged.p + off, cols_lw + off, cnt * sizeof(fe), cudaMemcpyHostToDevice, ctx->copy_stream));
+            CU(ctx, cudaEventCreateWithFlags(&ev[g], cudaEventDisableTiming));
+            CU(ctx, cudaEventRecord(ev[g], ctx->copy_stream));
+        }
+        Xform I;
+        I.logn = ilog2(N);
+        I.inverse = true;
+        for (unsigned g = 0; g < K; ++g) {
+            const unsigned cg = lo[g + 1] - lo[g];
+            const size_t off = (size_t)lo[g] * N;
+            CU(ctx, cudaStreamWaitEvent(ctx->stream, ev[g], 0));
+            TRY(convert_lw_to_internal(ctx, staged.p + off, cols.p + off, (size_t)cg * N));
+            TRY(run_ntt(ctx, I, cols.p + off, N, false, cm->coeffs + off, N, false, cg));                 // compute_trace_polys
+            TRY(evaluate_cosets(ctx, cm->coeffs + off, N, false, ilog2(N), (unsigned)blowup, H::from_u64(coset_offset),
+                                cm->lde + (size_t)lo[g] * M, M, false, cg));                              // compute_lde_trace_evaluations
+        }
+        TRY(dalloc(ctx, &cm->nodes, 4 * (2 * M - 1)));
+        TRY(build_tree(ctx, cm->lde, M, c, M, cm->nodes));                                               // batch_commit
+        TRY(fetch_root(ctx, cm->nodes, root));
+        if (keep_trace) { cm->trace = cols.p; cols.p = nullptr; }
+        return S252_OK;
+    }();
+    if (rc != S252_OK) cudaStreamSynchronize(ctx->copy_stream);
+    for (auto e : ev) if (e) cudaEventDestroy(e);
+    if (start) cudaEventDestroy(start);
+    if (rc != S252_OK) { commit_free(cm); return rc; }
+    *out = cm;
+    return S252_OK;
+}
+
 extern "C" int s252_cairo_round1(s252_ctx* ctx, const s252_cairo_trace* trace, size_t blowup, uint64_t coset_offset,
                                  s252_transcript* transcript, s252_commit** main_out, s252_commit** aux_out, s252_fe rap_out[3]) {
     if (!ctx || !trace || !transcript || !main_out || !aux_out || !rap_out) return S252_ERR_INVALID;
@@ -289,7 +355,7 @@ extern "C" int s252_cairo_round1(s252_ctx* ctx, const s252_cairo_trace* trace, s
     s252_commit* mainc = nullptr;
     s252_cairo_trace_pin(trace);   // first use only; a failure just leaves the table pageable
     StageTimer R1;
-    TRY(interpolate_lde_impl(ctx, trace->table.data(), N, trace->n_cols, blowup, coset_offset, S252_HOST, true, &mainc, root, true));
+    TRY(commit_from_host_columns(ctx, trace->cols.data(), N, (unsigned)trace->n_cols, blowup, coset_offset, true, &mainc, root));
     R1.mark("main_commit");
     transcript->append(root, 32);                                   // prover.rs:151
     fe rap[3];
