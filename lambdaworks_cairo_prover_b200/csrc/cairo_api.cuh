@@ -31,13 +31,19 @@ extern "C" const char* s252_cairo_last_error(void) { return g_cairo_err.c_str();
 extern "C" int s252_cairo_vm_run(const uint8_t* program_be, size_t n_words, uint64_t entry_offset, uint64_t max_steps,
                                  s252_cairo_run** out) {
     if (!program_be || !n_words || !out || entry_offset >= n_words) CAIRO_FAIL(S252_ERR_INVALID, "bad program");
-    std::vector<fe> prog(n_words);
-    for (size_t i = 0; i < n_words; ++i) prog[i] = H::from_bytes_be(program_be + 32 * i);
-    s252_cairo_run* run = new s252_cairo_run();
-    std::string err;
-    if (!CA::vm_run(prog, entry_offset, max_steps ? max_steps : ~0ULL, &run->r, &err)) {
+    s252_cairo_run* run = nullptr;
+    try {
+        std::vector<fe> prog(n_words);
+        for (size_t i = 0; i < n_words; ++i) prog[i] = H::from_bytes_be(program_be + 32 * i);
+        run = new s252_cairo_run();
+        std::string err;
+        if (!CA::vm_run(prog, entry_offset, max_steps ? max_steps : ~0ULL, &run->r, &err)) {
+            delete run;
+            CAIRO_FAIL(S252_ERR_INVALID, "cairo vm: " + err);
+        }
+    } catch (const std::exception& e) {           // nothing may unwind across the C boundary
         delete run;
-        CAIRO_FAIL(S252_ERR_INVALID, "cairo vm: " + err);
+        CAIRO_FAIL(S252_ERR_INVALID, std::string("cairo vm: ") + e.what());
     }
     *out = run;
     return S252_OK;
@@ -69,20 +75,26 @@ static int cairo_build_common(bool full, const uint8_t* trace_le, size_t trace_l
     CA::Memory mem;
     if (!CA::parse_trace_le(trace_le, trace_len, &regs)) CAIRO_FAIL(S252_ERR_INVALID, "IncorrectNumberOfBytes (register trace)");
     if (!CA::parse_memory_le(memory_le, memory_len, &mem)) CAIRO_FAIL(S252_ERR_INVALID, "IncorrectNumberOfBytes (memory)");
-    s252_cairo_trace* t = new s252_cairo_trace();
-    std::string err;
-    CA::Table tab;
-    bool ok = CA::public_inputs_from_regs_and_mem(regs, mem, program_size, rc_range, output_range, &t->pi, &err);
-    if (ok) ok = full ? CA::build_main_trace(regs, mem, &t->pi, &tab, &err) : CA::build_cairo_execution_trace(regs, mem, t->pi, &tab, &err);
-    if (!ok) {
+    s252_cairo_trace* t = nullptr;
+    try {
+        t = new s252_cairo_trace();
+        std::string err;
+        CA::Table tab;
+        bool ok = CA::public_inputs_from_regs_and_mem(regs, mem, program_size, rc_range, output_range, &t->pi, &err);
+        if (ok) ok = full ? CA::build_main_trace(regs, mem, &t->pi, &tab, &err) : CA::build_cairo_execution_trace(regs, mem, t->pi, &tab, &err);
+        if (!ok) {
+            delete t;
+            CAIRO_FAIL(S252_ERR_INVALID, "build_main_trace: " + err);
+        }
+        t->n_cols = tab.n_cols;
+        t->n_rows = tab.n_rows();
+        t->table.resize(tab.t.size());
+        for (size_t i = 0; i < tab.t.size(); ++i) H::to_lw(tab.t[i], t->table[i].limbs);
+        t->make_columns();
+    } catch (const std::exception& e) {
         delete t;
-        CAIRO_FAIL(S252_ERR_INVALID, "build_main_trace: " + err);
+        CAIRO_FAIL(S252_ERR_INVALID, std::string("build_main_trace: ") + e.what());
     }
-    t->n_cols = tab.n_cols;
-    t->n_rows = tab.n_rows();
-    t->table.resize(tab.t.size());
-    for (size_t i = 0; i < tab.t.size(); ++i) H::to_lw(tab.t[i], t->table[i].limbs);
-    t->make_columns();
     *out = t;
     return S252_OK;
 }
@@ -165,9 +177,15 @@ extern "C" int s252_cairo_trace_from_table(const s252_fe* table, size_t n_rows, 
                                            const uint64_t* pub_addrs, const s252_fe* pub_values, s252_cairo_trace** out) {
     if (!table || !pub || !out || (pub->n_public_memory && (!pub_addrs || !pub_values))) CAIRO_FAIL(S252_ERR_INVALID, "null argument");
     if (n_cols != CA::MAIN_COLS && n_cols != CA::MAIN_COLS + CA::RC_BUILTIN_COLS) CAIRO_FAIL(S252_ERR_INVALID, "a Cairo main trace has 34 or 43 columns");
-    s252_cairo_trace* t = new s252_cairo_trace();
+    s252_cairo_trace* t = nullptr;
+    try {
+        t = new s252_cairo_trace();
+        t->table.assign(table, table + n_rows * n_cols);
+    } catch (const std::exception& e) {
+        delete t;
+        CAIRO_FAIL(S252_ERR_INVALID, std::string("s252_cairo_trace_from_table: ") + e.what());
+    }
     t->n_rows = n_rows; t->n_cols = n_cols;
-    t->table.assign(table, table + n_rows * n_cols);
     CA::PublicInputs& p = t->pi;
     p.pc_init = pub->pc_init; p.ap_init = pub->ap_init; p.fp_init = pub->fp_init; p.pc_final = pub->pc_final; p.ap_final = pub->ap_final;
     p.num_steps = pub->num_steps;
@@ -567,7 +585,7 @@ extern "C" int s252_cairo_prove(s252_ctx* ctx, const s252_cairo_trace* trace, si
     s252_fri* fri = nullptr;
     s252_fe rap[3];
     StageTimer ST;
-    int rc = [&]() -> int {
+    auto body = [&]() -> int {
         TRY(s252_cairo_round1(ctx, trace, blowup, coset_offset, &t, &mainc, &auxc, rap));
         ST.mark("round1");
         TRY(s252_cairo_round2(ctx, trace, mainc, auxc, rap, blowup, coset_offset, &t, &comp));
@@ -682,7 +700,14 @@ extern "C" int s252_cairo_prove(s252_ctx* ctx, const s252_cairo_trace* trace, si
         *proof_len = S.b.size();
         ST.mark("serialize");
         return S252_OK;
-    }();
+    };
+    int rc;
+    try {
+        rc = body();
+    } catch (const std::exception& e) {           // host allocation failure: nothing may unwind across the C boundary
+        ctx->err = std::string("s252_cairo_prove: ") + e.what();
+        rc = S252_ERR_INVALID;
+    }
     if (fri) s252_fri_destroy(fri);
     commit_free(mainc); commit_free(auxc); commit_free(comp);
     ST.mark("free");

@@ -105,11 +105,12 @@ inline bool vm_run(const std::vector<fe>& program, uint64_t entry_offset, uint64
     const uint64_t P = program.size();
     const uint64_t exec_base = 1 + P;
     const uint64_t SENT_FP = (1ULL << 62), SENT_PC = (1ULL << 62) + 1;
+    const uint64_t MAX_ADDRESS = 1ULL << 28;      // flat memory: a stray write far away must not allocate terabytes
     std::vector<fe> mem;          // index = address
     std::vector<uint8_t> known;
     auto ensure = [&](uint64_t a) { if (a >= mem.size()) { size_t n = std::max<size_t>(a + 1, mem.size() * 2); mem.resize(n, fe_zero()); known.resize(n, 0); } };
     auto set = [&](uint64_t a, const fe& v) -> bool {
-        if (a == 0 || a >= (1ULL << 40)) return false;
+        if (a == 0 || a >= MAX_ADDRESS) return false;
         ensure(a);
         if (known[a]) return H::eq(mem[a], v);
         mem[a] = v; known[a] = 1;
@@ -174,7 +175,7 @@ inline bool vm_run(const std::vector<fe>& program, uint64_t entry_offset, uint64
             *err = "unknown operand cell";
             return false;
         }
-        for (uint64_t a : {dst_addr, op0_addr, op1_addr}) if (a >= exec_base && a < (1ULL << 40)) max_exec = std::max(max_exec, a);
+        for (uint64_t a : {dst_addr, op0_addr, op1_addr}) if (a >= exec_base && a < MAX_ADDRESS) max_exec = std::max(max_exec, a);
         // register updates
         uint64_t npc, nap, nfp;
         switch (in.pc_update()) {

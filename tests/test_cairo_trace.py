@@ -98,3 +98,22 @@ def test_main_trace_root_equals_golden_proof_root(n):
     table = np.array(t.table).reshape(t.n_rows(), t.n_cols, 4)
     r = O.interpolate_and_commit(table, 4, 3, threads=4, want_lde=False, want_nodes=False)
     assert bytes(r["root"]) == proof.lde_trace_merkle_roots[0]
+
+
+def test_machine_refuses_far_away_writes():
+    """`[ap] = 7; ap++` after `ap += 2^40`: the flat memory must refuse instead of allocating terabytes."""
+    prog = [0x040780017fff7fff, 1 << 40,      # ap += 2^40
+            0x480680017fff8000, 7,            # [ap] = 7; ap++
+            0x208b7fff7fff7ffe]               # ret
+    with pytest.raises(cairo.CairoError):
+        cairo.run_program(prog)
+
+
+def test_trace_from_table_round_trip():
+    regs, mem, size = cairo.run_program(cairo.fibonacci_program(10))
+    t = cairo.build_main_trace(regs, mem, size)
+    t2 = cairo.trace_from_table(np.array(t.table), t.n_cols, t.pub_inputs)
+    assert (np.array(t2.table) == np.array(t.table)).all() and t2.n_rows() == t.n_rows()
+    assert t2.pub_inputs.serialize() == t.pub_inputs.serialize()
+    with pytest.raises(cairo.CairoError):
+        cairo.trace_from_table(np.zeros((8 * 33, 4), dtype=np.uint64), 33, t.pub_inputs)     # not a Cairo layout
