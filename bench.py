@@ -304,7 +304,12 @@ def run_gpu(args):
                 "hbm_gbs": st["bytes"] / sec / 1e9 if sec else 0.0,
                 "imad_frac": (st["muls"] * 80 / sec / 1e9) / imad_peak if sec else 0.0,
                 "keccak_gperms": st["perms"] / sec / 1e9 if sec else 0.0,
+                # Keccak-f[1600] here is 24 x (122 LOP3 + 58 SHF) = 4320 ALU-pipe lane-operations
+                "alu_frac": (st["perms"] * 4320 / sec / 1e9) / lop_peak if sec else 0.0,
             }
+        # time-weighted fraction of the binding integer pipe over the whole step: IMAD.WIDE issue for the field
+        # kernels, LOP3/SHF issue for the Keccak kernels (whichever is larger for the kernel)
+        step_frac = sum(k["share"] * max(k["imad_frac"], k["alu_frac"]) for k in kernels.values())
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -321,7 +326,11 @@ def run_gpu(args):
             "roofline": {"bound": "hbm", "kernel": tname, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                          "note": "integer-pipe bound path: see int_roofline for the binding roof"},
-            "int_roofline": {"imad_wide_peak_gops": imad_peak, "lop3_peak_gops": lop_peak,
+            "int_roofline": {"bound": "integer issue (IMAD.WIDE for field kernels, LOP3/SHF for Keccak kernels)",
+                             "step_frac": step_frac,
+                             "step_frac_how": "sum over kernels of (share of step time) x max(imad_frac, alu_frac); peaks are the "
+                                              "isolated-instruction rates below",
+                             "imad_wide_peak_gops": imad_peak, "lop3_peak_gops": lop_peak,
                              "peak_source": "tools/microbench.py on this pool's B200 (profiles/int_peaks.json)",
                              "kernels": kernels},
             "result": {"last_root": out_dev[0].hex(), "nonce": out_dev[2]},
