@@ -90,7 +90,7 @@ int s252_cairo_trace_from_table(const s252_fe *table, size_t n_rows, size_t n_co
 /* ---- prover (GPU) ------------------------------------------------------------------------- */
 /* Round 1 of prove::<CairoAIR> (round_1_randomized_air_with_preprocessing, src/starks/prover.rs:186-224):
  * interpolate_and_commit(main) -> transcript.append(root) -> build_rap_challenges (air.rs:731-737) ->
- * build_auxiliary_trace ON THE DEVICE (air.rs:660-729: stable sort by address, permutation-argument
+ * build_auxiliary_trace ON THE DEVICE (air.rs:660-729: stable radix sort by address, permutation-argument
  * columns as multiplicative scans) -> interpolate_and_commit(aux) -> transcript.append(root).
  * rap_out[3] = alpha_memory, z_memory, z_range_check. */
 int s252_cairo_round1(s252_ctx *ctx, const s252_cairo_trace *trace, size_t blowup, uint64_t coset_offset,

@@ -1,7 +1,7 @@
 // cairo.cuh -- device kernels of the Cairo stages that sit between the LDE + commitment calls of
 // `prove::<CairoAIR>`:
 //
-//   build_auxiliary_trace          src/cairo/air.rs:660-729    sort by address, permutation columns
+//   build_auxiliary_trace          src/cairo/air.rs:660-729    stable radix sort by address, permutation columns
 //   ConstraintEvaluator::evaluate  src/starks/constraints/evaluator.rs:40-262 with
 //   CairoAIR::compute_transition   src/cairo/air.rs:743-767, 869-1160 and boundary_constraints :777-849
 //
@@ -82,6 +82,100 @@ __global__ void __launch_bounds__(256) sub_const2(const fe* __restrict__ in, fe*
 }
 
 // ------------------------------------------------------------------------------------------------
+// stable LSD radix sort, 8 bits per pass (sort_columns_by_memory_address uses Rust's stable sort_by,
+// air.rs:529-533).  A warp owns RS_ITEMS consecutive elements: pass 1 counts its digits, a scan over
+// the digit-major (digit, warp) histogram gives every warp its output base per digit, pass 2 re-reads
+// the elements in order and ranks equal digits inside each 32-element chunk with __match_any_sync, so
+// equal keys keep their input order.
+constexpr unsigned RS_ITEMS = 2048;
+constexpr unsigned RS_WARPS = 4;
+
+template <typename K>
+__global__ void __launch_bounds__(RS_WARPS * 32) rs_histogram(const K* __restrict__ keys, unsigned n, unsigned shift,
+                                                              unsigned* __restrict__ hist, unsigned units) {
+    __shared__ unsigned cnt[RS_WARPS][256];
+    const unsigned w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned unit = blockIdx.x * RS_WARPS + w;
+    if (unit >= units) return;                       // whole warps leave together
+    for (unsigned d = lane; d < 256; d += 32) cnt[w][d] = 0;
+    __syncwarp();
+    const unsigned lo = unit * RS_ITEMS;
+    for (unsigned c = 0; c < RS_ITEMS && lo + c < n; c += 32) {
+        const unsigned i = lo + c + lane;
+        const bool valid = i < n;
+        const unsigned d = valid ? ((unsigned)(keys[i] >> shift) & 255u) : 256u + lane;
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        if (valid && lane == (unsigned)__ffs(peers) - 1) cnt[w][d] += __popc(peers);      // one update per distinct digit
+        __syncwarp();
+    }
+    for (unsigned d = lane; d < 256; d += 32) hist[d * units + unit] = cnt[w][d];
+}
+// block d: exclusive scan of row d of the digit-major histogram (in place) and the row total
+__global__ void __launch_bounds__(1024) rs_scan_rows(unsigned* __restrict__ hist, unsigned units, unsigned* __restrict__ digit_totals) {
+    __shared__ unsigned wsum[32];
+    const unsigned t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    unsigned* row = hist + blockIdx.x * units;
+    unsigned carry = 0;
+    for (unsigned base = 0; base < units; base += 1024) {
+        const unsigned x = base + t < units ? row[base + t] : 0;
+        unsigned incl = x;
+        for (unsigned o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+        if (lane == 31) wsum[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            unsigned v = wsum[lane];
+            for (unsigned o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += y; }
+            wsum[lane] = v;
+        }
+        __syncthreads();
+        const unsigned prefix = wid ? wsum[wid - 1] : 0;
+        if (base + t < units) row[base + t] = carry + prefix + incl - x;
+        carry += wsum[31];
+        __syncthreads();
+    }
+    if (t == 0) digit_totals[blockIdx.x] = carry;
+}
+template <typename K, bool HAS_VALS>
+__global__ void __launch_bounds__(RS_WARPS * 32) rs_scatter(const K* __restrict__ keys, const unsigned* __restrict__ vals, unsigned n,
+                                                            unsigned shift, const unsigned* __restrict__ hist, unsigned units,
+                                                            const unsigned* __restrict__ digit_totals, K* __restrict__ keys_out,
+                                                            unsigned* __restrict__ vals_out) {
+    __shared__ unsigned base[RS_WARPS][256];
+    __shared__ unsigned dbase[256];
+    const unsigned w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned unit = blockIdx.x * RS_WARPS + w;
+    if (w == 0) {                                    // exclusive scan of the 256 digit totals: 8 digits per lane
+        unsigned v[8], s = 0;
+        for (int k = 0; k < 8; ++k) { v[k] = digit_totals[lane * 8 + k]; s += v[k]; }
+        unsigned incl = s;
+        for (unsigned o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+        unsigned run = incl - s;
+        for (int k = 0; k < 8; ++k) { dbase[lane * 8 + k] = run; run += v[k]; }
+    }
+    __syncthreads();
+    if (unit >= units) return;
+    for (unsigned d = lane; d < 256; d += 32) base[w][d] = dbase[d] + hist[d * units + unit];
+    __syncwarp();
+    const unsigned lo = unit * RS_ITEMS;
+    for (unsigned c = 0; c < RS_ITEMS && lo + c < n; c += 32) {
+        const unsigned i = lo + c + lane;
+        const bool valid = i < n;
+        const K key = valid ? keys[i] : (K)0;
+        const unsigned d = (unsigned)(key >> shift) & 255u;
+        const unsigned peers = __match_any_sync(0xffffffffu, valid ? d : 256u + lane);
+        const unsigned rank = __popc(peers & ((1u << lane) - 1u));
+        const unsigned pos = valid ? base[w][d] + rank : 0;
+        __syncwarp();
+        if (valid && rank + 1 == (unsigned)__popc(peers)) base[w][d] += rank + 1;     // the last peer advances the digit's cursor
+        __syncwarp();
+        if (valid) {
+            keys_out[pos] = key;
+            if (HAS_VALS) vals_out[pos] = vals[i];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // auxiliary trace
 constexpr unsigned CAIRO_PC = 19, CAIRO_INST = 23, CAIRO_OFF_DST = 27, CAIRO_AUX_COLS = 18;
 
@@ -102,14 +196,19 @@ __device__ __forceinline__ unsigned long long fe_low64(const fe& mont) {
 // long-format sort keys: entry L = 4*row + k is (addr column k, value column k) of that row; the last
 // n_pub entries are replaced by the public memory (add_pub_memory_in_public_input_section, air.rs:488-506)
 __global__ void __launch_bounds__(256) cairo_aux_keys(CairoAux P, unsigned long long* __restrict__ keys, unsigned* __restrict__ idx,
-                                                      unsigned short* __restrict__ okeys) {
+                                                      unsigned short* __restrict__ okeys, unsigned long long* __restrict__ key_or) {
     const unsigned long long L = (unsigned long long)blockIdx.x * 256 + threadIdx.x;
     const unsigned long long total = 4 * P.n;
+    unsigned long long k = 0;
     if (L < total) {
         const unsigned long long first_pub = total - P.n_pub;
-        keys[L] = L >= first_pub ? P.pub_addr[L - first_pub] : fe_low64(ld_fe(P.main + (CAIRO_PC + (L & 3)) * P.n + (L >> 2)));
+        k = L >= first_pub ? P.pub_addr[L - first_pub] : fe_low64(ld_fe(P.main + (CAIRO_PC + (L & 3)) * P.n + (L >> 2)));
+        keys[L] = k;
         idx[L] = (unsigned)L;
     }
+    // OR of all keys: its bit length bounds the number of radix passes
+    for (int o = 16; o > 0; o >>= 1) k |= __shfl_xor_sync(0xffffffffu, k, o);
+    if ((threadIdx.x & 31) == 0 && k) atomicOr(key_or, k);
     if (L < 3 * P.n) okeys[L] = (unsigned short)fe_low64(ld_fe(P.main + (CAIRO_OFF_DST + L % 3) * P.n + L / 3));
 }
 // numerators / denominators of the memory permutation argument (air.rs:535-563) and the sorted

@@ -202,7 +202,6 @@ extern "C" int s252_cairo_trace_from_table(const s252_fe* table, size_t n_rows, 
 
 // --------------------------------------------------------------------------------------------
 // GPU prover
-#include <cub/device/device_radix_sort.cuh>
 
 // wall-clock stage timer of the last s252_cairo_prove on this thread (diagnostics; s252_cairo_last_prove_stages)
 #include <chrono>
@@ -237,6 +236,31 @@ static int get_coset_tables(s252_ctx* ctx, size_t M, uint64_t coset_offset, cons
     return S252_OK;
 }
 
+// Stable LSD radix sort over the low `bits` bits (kernels in cairo.cuh).  Ping-pongs between the two buffers;
+// returns through *result which one holds the sorted keys (vals likewise).
+template <typename K>
+static int radix_sort(s252_ctx* ctx, K* keys, K* keys2, unsigned* vals, unsigned* vals2, size_t n, unsigned bits, unsigned* hist,
+                      int* result) {
+    const unsigned units = (unsigned)((n + s252::RS_ITEMS - 1) / s252::RS_ITEMS);
+    const unsigned blocks = (units + s252::RS_WARPS - 1) / s252::RS_WARPS;
+    int cur = 0;
+    for (unsigned shift = 0; shift < bits; shift += 8) {
+        K* kin = cur ? keys2 : keys; K* kout = cur ? keys : keys2;
+        unsigned* vin = cur ? vals2 : vals; unsigned* vout = cur ? vals : vals2;
+        prof_begin(ctx, "radix_sort_pass");
+        prof_work(ctx, (double)n * (2 * sizeof(K) + (vals ? 8 : 0) + sizeof(K)), 0, 0);
+        s252::rs_histogram<K><<<blocks, s252::RS_WARPS * 32, 0, ctx->stream>>>(kin, (unsigned)n, shift, hist, units);
+        s252::rs_scan_rows<<<256, 1024, 0, ctx->stream>>>(hist, units, hist + 256 * units);
+        if (vals) s252::rs_scatter<K, true><<<blocks, s252::RS_WARPS * 32, 0, ctx->stream>>>(kin, vin, (unsigned)n, shift, hist, units, hist + 256 * units, kout, vout);
+        else s252::rs_scatter<K, false><<<blocks, s252::RS_WARPS * 32, 0, ctx->stream>>>(kin, nullptr, (unsigned)n, shift, hist, units, hist + 256 * units, kout, nullptr);
+        ctx->launches += 2;
+        LAUNCH_CHECK(ctx);
+        cur ^= 1;
+    }
+    *result = cur;
+    return S252_OK;
+}
+
 // build_auxiliary_trace (air.rs:660-729) into aux[18][N] (column-major, internal format)
 static int cairo_build_aux(s252_ctx* ctx, const fe* main_cols, size_t N, const CA::PublicInputs& pi, const fe rap[3], fe* aux) {
     const size_t L = 4 * N, R = 3 * N, np = pi.public_memory.size();
@@ -249,7 +273,8 @@ static int cairo_build_aux(s252_ctx* ctx, const fe* main_cols, size_t N, const C
     Tmp<fe> d_paddr_fe(ctx), d_pval(ctx), num(ctx), den(ctx), rnum(ctx), rden(ctx);
     Tmp<unsigned> idx(ctx), idx2(ctx);
     Tmp<unsigned short> okeys(ctx), okeys2(ctx);
-    Tmp<unsigned char> tmp(ctx);
+    Tmp<unsigned> hist(ctx);
+    Tmp<unsigned long long> key_or(ctx);
     TRY(dalloc(ctx, &d_paddr.p, np + 1)); TRY(dalloc(ctx, &d_paddr_fe.p, np + 1)); TRY(dalloc(ctx, &d_pval.p, np + 1));
     if (np) {
         CU(ctx, cudaMemcpyAsync(d_paddr.p, paddr.data(), np * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -259,30 +284,35 @@ static int cairo_build_aux(s252_ctx* ctx, const fe* main_cols, size_t N, const C
     TRY(dalloc(ctx, &keys.p, L)); TRY(dalloc(ctx, &keys2.p, L)); TRY(dalloc(ctx, &idx.p, L)); TRY(dalloc(ctx, &idx2.p, L));
     TRY(dalloc(ctx, &okeys.p, R)); TRY(dalloc(ctx, &okeys2.p, R));
     TRY(dalloc(ctx, &num.p, L)); TRY(dalloc(ctx, &den.p, L)); TRY(dalloc(ctx, &rnum.p, R)); TRY(dalloc(ctx, &rden.p, R));
+    TRY(dalloc(ctx, &hist.p, 256 * ((L + s252::RS_ITEMS - 1) / s252::RS_ITEMS) + 256));   // (digit, warp) counts + 256 digit totals
+    TRY(dalloc(ctx, &key_or.p, 1));
+    CU(ctx, cudaMemsetAsync(key_or.p, 0, 8, ctx->stream));
     s252::CairoAux P{};
     P.main = main_cols; P.n = N; P.pub_addr = d_paddr.p; P.pub_addr_fe = d_paddr_fe.p; P.pub_val = d_pval.p; P.n_pub = (unsigned)np;
     P.alpha = rap[0]; P.z = rap[1]; P.zrc = rap[2]; P.aux = aux;
     const unsigned gl = (unsigned)((L + 255) / 256), gr = (unsigned)((R + 255) / 256);
     prof_begin(ctx, "cairo_aux_keys");
     prof_work(ctx, 32.0 * 7 * N, 7.0 * N * 0.2, 0);
-    s252::cairo_aux_keys<<<gl, 256, 0, ctx->stream>>>(P, keys.p, idx.p, okeys.p);
+    s252::cairo_aux_keys<<<gl, 256, 0, ctx->stream>>>(P, keys.p, idx.p, okeys.p, key_or.p);
     LAUNCH_CHECK(ctx);
     // sort_columns_by_memory_address (air.rs:529-533): stable sort by address; offsets_sorted.sort() (air.rs:684-689)
-    size_t b1 = 0, b2 = 0;
-    CU(ctx, cub::DeviceRadixSort::SortPairs(nullptr, b1, keys.p, keys2.p, idx.p, idx2.p, (int)L, 0, 64, ctx->stream));
-    CU(ctx, cub::DeviceRadixSort::SortKeys(nullptr, b2, okeys.p, okeys2.p, (int)R, 0, 16, ctx->stream));
-    TRY(dalloc(ctx, &tmp.p, std::max(b1, b2) + 256));
-    prof_begin(ctx, "cub_radix_sort");
-    CU(ctx, cub::DeviceRadixSort::SortPairs(tmp.p, b1, keys.p, keys2.p, idx.p, idx2.p, (int)L, 0, 64, ctx->stream));
-    CU(ctx, cub::DeviceRadixSort::SortKeys(tmp.p, b2, okeys.p, okeys2.p, (int)R, 0, 16, ctx->stream));
-    LAUNCH_CHECK(ctx);
+    unsigned long long kor = 0;
+    CU(ctx, cudaMemcpyAsync(&kor, key_or.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    unsigned key_bits = 0;
+    while (key_bits < 64 && (kor >> key_bits)) ++key_bits;
+    int which = 0, owhich = 0;
+    TRY(radix_sort<unsigned long long>(ctx, keys.p, keys2.p, idx.p, idx2.p, L, key_bits, hist.p, &which));
+    TRY(radix_sort<unsigned short>(ctx, okeys.p, okeys2.p, nullptr, nullptr, R, 16, hist.p, &owhich));
+    const unsigned* sorted_idx = which ? idx2.p : idx.p;
+    const unsigned short* sorted_off = owhich ? okeys2.p : okeys.p;
     prof_begin(ctx, "cairo_aux_terms");
     prof_work(ctx, 32.0 * 8 * L, 2.0 * L, 0);
-    s252::cairo_aux_terms<<<gl, 256, 0, ctx->stream>>>(P, idx2.p, num.p, den.p);
+    s252::cairo_aux_terms<<<gl, 256, 0, ctx->stream>>>(P, sorted_idx, num.p, den.p);
     LAUNCH_CHECK(ctx);
     prof_begin(ctx, "cairo_aux_rc_terms");
     prof_work(ctx, 32.0 * 4 * R, 1.0 * R, 0);
-    s252::cairo_aux_rc_terms<<<gr, 256, 0, ctx->stream>>>(P, okeys2.p, rnum.p, rden.p);
+    s252::cairo_aux_rc_terms<<<gr, 256, 0, ctx->stream>>>(P, sorted_off, rnum.p, rden.p);
     LAUNCH_CHECK(ctx);
     TRY(scan_mul(ctx, num.p, L, false));
     TRY(scan_mul(ctx, den.p, L, true));
