@@ -179,6 +179,12 @@ int s252_fri_commit_phase_deep(s252_ctx *ctx, size_t number_layers, s252_commit 
                                const s252_fe *h1_z2, const s252_fe *h2_z2, const s252_fe *gamma, const s252_fe *gamma_p,
                                const s252_fe *trace_gammas, s252_transcript *transcript, uint64_t coset_offset,
                                s252_fri **out, s252_fe *last_value, uint8_t *roots_out);
+/* fri_commit_phase from layer 0 given as evaluations on the LDE coset (device, internal element format):
+ * what s252_fri_commit_phase_deep runs after building the DEEP polynomial; a sharded prover gathers the
+ * row blocks of that polynomial and calls this on one rank. */
+int s252_fri_commit_phase_evals(s252_ctx *ctx, size_t number_layers, const void *p0_evals, size_t domain_size,
+                                s252_transcript *transcript, uint64_t coset_offset, s252_fri **out, s252_fe *last_value,
+                                uint8_t *roots_out);
 void s252_fri_destroy(s252_fri *f);
 size_t s252_fri_n_layers(const s252_fri *f);
 /* FriLayer.evaluation[first..first+count) of layer k */

@@ -121,6 +121,41 @@ int s252_cairo_constraint_evaluations(s252_ctx *ctx, const s252_cairo_trace *tra
 int s252_cairo_prove(s252_ctx *ctx, const s252_cairo_trace *trace, size_t blowup, size_t fri_number_of_queries,
                      uint64_t coset_offset, uint8_t grinding_factor, uint8_t **proof_out, size_t *proof_len);
 void s252_cairo_proof_free(uint8_t *proof);
+/* ---- building blocks of a proof sharded over several GPUs ------------------------------------
+ * The same kernels as s252_cairo_prove, applied to this rank's columns (LDE) or to this rank's block of
+ * LDE rows; lambdaworks_cairo_prover_b200/cairo_distributed.py strings them together with NCCL.
+ * "device columns" / "blocks" are column-major buffers in the library's internal element format
+ * (s252_commit_device_lde). */
+/* The handle's table column-major (n_cols x n_rows, LW; pinned after s252_cairo_trace_pin). */
+const s252_fe *s252_cairo_trace_columns(const s252_cairo_trace *t);
+/* compute_trace_polys + compute_lde_trace_evaluations (prover.rs:161-185) for n_cols columns given
+ * column-major in (pinned) host memory / on the device; no tree. */
+int s252_lde_host_columns(s252_ctx *ctx, const s252_fe *cols_lw, size_t n_rows, size_t n_cols, size_t blowup,
+                          uint64_t coset_offset, s252_commit **out);
+int s252_lde_device_columns(s252_ctx *ctx, const void *cols, size_t n_rows, size_t n_cols, size_t blowup,
+                            uint64_t coset_offset, s252_commit **out);
+/* build_auxiliary_trace (air.rs:660-729) on this device: *aux_out = device columns [18][n_rows]
+ * (release with s252_device_free). */
+int s252_cairo_aux_trace_device(s252_ctx *ctx, const s252_cairo_trace *trace, const s252_fe rap[3], void **aux_out);
+/* ConstraintEvaluator::evaluate (evaluator.rs:40-262) on LDE rows [row0, row0+rows): main_block / aux_block
+ * hold those rows of every column (stride elements apart); *_halo hold the `blowup` rows that follow
+ * the block (mod the domain; the frame's next row).  evals_out: device, [rows]. */
+int s252_cairo_constraints_rows(s252_ctx *ctx, const s252_cairo_trace *trace, const void *main_block, const void *aux_block,
+                                size_t stride, size_t row0, size_t rows, const void *main_halo, const void *aux_halo,
+                                size_t halo_stride, const s252_fe rap[3], const s252_fe *boundary_coeffs,
+                                const s252_fe *transition_coeffs, size_t blowup, uint64_t coset_offset, void *evals_out);
+/* The rest of round 2 (prover.rs:246-283) from the n_rows*blowup constraint evaluations (device):
+ * interpolate_offset_fft, even/odd split, LDE of H1/H2, batch_commit. */
+int s252_cairo_composition_commit(s252_ctx *ctx, const void *evals, size_t n_rows, size_t blowup, uint64_t coset_offset,
+                                  s252_commit **out, uint8_t root[32]);
+/* The DEEP composition polynomial (prover.rs:410-482 as the verifier's formula, verifier.rs:526-557) on
+ * LDE rows [row0, row0+rows): tables[t] = block of table t (trace tables first, (H1, H2) last).
+ * Argument meaning as in s252_fri_commit_phase_deep.  out: device, [rows]. */
+int s252_deep_rows(s252_ctx *ctx, const void *const *tables, const size_t *strides, const size_t *n_cols, size_t n_tables,
+                   size_t row0, size_t rows, size_t lde_rows, size_t trace_rows, const s252_fe *z,
+                   const uint64_t *transition_offsets, size_t n_offsets, const s252_fe *trace_ood, const s252_fe *h1_z2,
+                   const s252_fe *h2_z2, const s252_fe *gamma, const s252_fe *gamma_p, const s252_fe *trace_gammas,
+                   uint64_t coset_offset, void *out);
 /* Diagnostics: host wall-clock milliseconds per stage of the last s252_cairo_prove on this thread, as JSON. */
 const char *s252_cairo_last_prove_stages(void);
 

@@ -60,6 +60,7 @@ SIGNATURES = {
     "s252_commit_evaluate_at": (_i, [_vp, _vp, _sz, _vp, _sz, _sz]),
     "s252_fri_commit_phase_deep": (_i, [_vp, _sz, _vp, _sz, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u64,
                                         C.POINTER(_vp), _vp, _vp]),
+    "s252_fri_commit_phase_evals": (_i, [_vp, _sz, _vp, _sz, _vp, _u64, C.POINTER(_vp), _vp, _vp]),
     "s252_fri_destroy": (None, [_vp]),
     "s252_fri_n_layers": (_sz, [_vp]),
     "s252_fri_read_layer": (_i, [_vp, _sz, _sz, _sz, _vp]),
@@ -102,6 +103,13 @@ SIGNATURES = {
     "s252_commit_read_trace": (_i, [_vp, _sz, _vp]),
     "s252_cairo_round2": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _u64, _vp, C.POINTER(_vp)]),
     "s252_cairo_constraint_evaluations": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _u64, _vp]),
+    "s252_cairo_trace_columns": (_vp, [_vp]),
+    "s252_lde_host_columns": (_i, [_vp, _vp, _sz, _sz, _sz, _u64, C.POINTER(_vp)]),
+    "s252_lde_device_columns": (_i, [_vp, _vp, _sz, _sz, _sz, _u64, C.POINTER(_vp)]),
+    "s252_cairo_aux_trace_device": (_i, [_vp, _vp, _vp, C.POINTER(_vp)]),
+    "s252_cairo_constraints_rows": (_i, [_vp, _vp, _vp, _vp, _sz, _sz, _sz, _vp, _vp, _sz, _vp, _vp, _vp, _sz, _u64, _vp]),
+    "s252_cairo_composition_commit": (_i, [_vp, _vp, _sz, _sz, _u64, C.POINTER(_vp), _vp]),
+    "s252_deep_rows": (_i, [_vp, _vp, _vp, _vp, _sz, _sz, _sz, _sz, _sz, _vp, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _vp]),
     "s252_cairo_prove": (_i, [_vp, _vp, _sz, _sz, _u64, _u8, C.POINTER(_vp), C.POINTER(_sz)]),
     "s252_cairo_proof_free": (None, [_vp]),
     "s252_cairo_last_prove_stages": (C.c_char_p, []),

@@ -1,0 +1,271 @@
+"""generate_cairo_proof (src/cairo/air.rs:1183-1190) for ONE trace on the GPUs of one box.
+
+One process per GPU (torch.distributed / NCCL as plumbing; the kernels are the library's own, through the
+building blocks of include/stark252_cairo.h).  What is sharded and how:
+
+  round 1   columns of the main trace are split over the ranks: every rank uploads, interpolates and
+            extends only its columns, the exchange of distributed.py turns them into row blocks, every
+            rank hashes its rows and builds that subtree, the roots are gathered.  The auxiliary trace is
+            built REDUNDANTLY on every rank (1 ms; it needs 11 main columns, which every rank uploads
+            itself) and its 18 columns are then sharded the same way.
+  round 2   every rank evaluates the constraints on its row block (the frame's next row for the last
+            `blowup` rows comes from the next rank: a 7 KB halo); the evaluations are all-gathered and
+            rank 0 interpolates H, extends H1/H2 and commits them; root and LDE are broadcast.
+  round 3   every rank evaluates ITS polynomials at z and z*g; the values are all-gathered.
+  round 4   every rank builds the DEEP composition polynomial on its row block; the blocks are gathered
+            and rank 0 runs FRI, grinding and the query sampling; the trace openings come from the ranks
+            that own the rows.
+Every rank runs the same Fiat-Shamir transcript up to the FRI phase, so no challenge is ever sent.
+The proof bytes are identical to the single-GPU prover's (tests/test_distributed.py).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _native as N
+from . import distributed as D
+from . import felt
+from .merkle import DeviceCommit
+from .transcript import DefaultTranscript, transcript_to_field, transcript_to_usize
+
+P = felt.MODULUS
+_TWO_ADIC_ROOT = 0x5282db87529cfa3f0464519c8b0fa5ad187148e11a61616070024f42f8ef94   # order 2^192
+
+
+def _dev_tensor(ptr, n_words, device):
+    return torch.as_tensor(D._DevicePointer(ptr, n_words), device=device)
+
+
+def _wrap_lde(ctx, h, device):
+    L = N.lib()
+    commit = DeviceCommit.__new__(DeviceCommit)
+    commit.ctx, commit.handle, commit.root = ctx, h, b""
+    commit.n_cols, commit.n_rows, commit.n_coeffs = L.s252_commit_n_cols(h), L.s252_commit_n_rows(h), L.s252_commit_n_coeffs(h)
+    ctx.adopt(commit)
+    t = _dev_tensor(L.s252_commit_device_lde(h), commit.n_cols * commit.n_rows * 4, device)
+    return commit, t.view(commit.n_cols, commit.n_rows, 4)
+
+
+def _u64be(v):
+    return int(v).to_bytes(8, "big")
+
+
+def _path(p):
+    return _u64be(len(p)) + b"".join(bytes(x) for x in p)
+
+
+def _blob(b):
+    return _u64be(len(b)) + b
+
+
+def _bcast_bytes(data, n, device, group):
+    t = torch.frombuffer(bytearray(data if data is not None else bytes(n)), dtype=torch.uint8).to(device)
+    dist.broadcast(t, src=0 if group is None else dist.get_global_rank(group, 0), group=group)
+    return bytes(t.cpu().numpy().tobytes())
+
+
+def generate_cairo_proof_sharded(trace, options, ctx, group=None, timings=None):
+    """trace: the same MainTrace on every rank (lambdaworks_cairo_prover_b200.cairo).  Returns
+    StarkProof::serialize() bytes on rank 0 and None on the other ranks."""
+    L = N.lib()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    device = torch.device("cuda", ctx.device)
+    backend = D.GpuBackend(ctx)
+    n, c_main = trace.n_rows(), trace.n_cols
+    b, h = options.blowup_factor, options.coset_offset
+    m = n * b
+    rows_per = m // world
+    if rows_per < b or m % world:
+        raise ValueError("too many ranks for this trace")
+    order = n.bit_length() - 1
+    g = pow(_TWO_ADIC_ROOT, 1 << (192 - order), P)
+    nt = 50 if c_main > 34 else 49
+    t = DefaultTranscript()
+    L.s252_cairo_trace_pin(trace.handle)
+    cols_ptr = L.s252_cairo_trace_columns(trace.handle)
+
+    def sharded_commit(n_cols_total, lde_of_my_columns):
+        shards = D.column_shards(n_cols_total, world)
+        if min(hi - lo for lo, hi in shards) == 0:
+            raise ValueError("fewer columns than ranks")
+        ranges = [D.group_ranges(hi - lo, 1) for lo, hi in shards]
+        lo, hi = shards[rank]
+        return D.exchange_and_commit(iter([lde_of_my_columns(lo, hi)]), ranges, shards, m, n_cols_total, t, backend, group)
+
+    # ---- round 1 (prover.rs:186-224)
+    def main_lde(lo, hi):
+        hnd = C.c_void_p()
+        ctx.check(L.s252_lde_host_columns(ctx.handle, C.c_void_p(cols_ptr + lo * n * 32), n, hi - lo, b, h, C.byref(hnd)), N.FFTError)
+        return _wrap_lde(ctx, hnd, device)
+    sc_main = sharded_commit(c_main, main_lde)
+    rap = np.stack([transcript_to_field(t) for _ in range(3)])
+    aux_ptr = C.c_void_p()
+    ctx.check(L.s252_cairo_aux_trace_device(ctx.handle, trace.handle, N.ptr(rap), C.byref(aux_ptr)))
+
+    def aux_lde(lo, hi):
+        hnd = C.c_void_p()
+        ctx.check(L.s252_lde_device_columns(ctx.handle, C.c_void_p(aux_ptr.value + lo * n * 32), n, hi - lo, b, h, C.byref(hnd)), N.FFTError)
+        return _wrap_lde(ctx, hnd, device)
+    sc_aux = sharded_commit(18, aux_lde)
+    ctx.device_free(aux_ptr.value)
+    # ---- round 2 (prover.rs:598-640, 226-283)
+    bco = np.zeros((8, 2, 4), dtype=np.uint64)
+    tco = np.zeros((nt, 2, 4), dtype=np.uint64)
+    for j in range(2):
+        for k in range(8):
+            bco[k, j] = transcript_to_field(t)
+    for j in range(2):
+        for k in range(nt):
+            tco[k, j] = transcript_to_field(t)
+    mblock, ablock = sc_main.block_tensor, sc_aux.block_tensor                  # [cols, rows_per, 4]
+    mhalo = torch.empty((c_main, b, 4), dtype=mblock.dtype, device=device)
+    ahalo = torch.empty((18, b, 4), dtype=mblock.dtype, device=device)
+    if world == 1:
+        mhalo.copy_(mblock[:, :b])
+        ahalo.copy_(ablock[:, :b])
+    else:
+        gr = (lambda r: r) if group is None else (lambda r: dist.get_global_rank(group, r))
+        nxt, prv = gr((rank + 1) % world), gr((rank - 1) % world)
+        msend, asend = mblock[:, :b].contiguous(), ablock[:, :b].contiguous()
+        for w_ in dist.batch_isend_irecv([dist.P2POp(dist.isend, msend, prv, group), dist.P2POp(dist.isend, asend, prv, group),
+                                          dist.P2POp(dist.irecv, mhalo, nxt, group), dist.P2POp(dist.irecv, ahalo, nxt, group)]):
+            w_.wait()
+    torch.cuda.synchronize(device)
+    evals = torch.empty((m, 4), dtype=mblock.dtype, device=device)
+    mine = evals[rank * rows_per:(rank + 1) * rows_per]
+    ctx.check(L.s252_cairo_constraints_rows(ctx.handle, trace.handle, C.c_void_p(mblock.data_ptr()), C.c_void_p(ablock.data_ptr()),
+                                            rows_per, rank * rows_per, rows_per, C.c_void_p(mhalo.data_ptr()), C.c_void_p(ahalo.data_ptr()),
+                                            b, N.ptr(rap), N.ptr(bco), N.ptr(tco), b, h, C.c_void_p(mine.data_ptr())))
+    if world > 1:
+        dist.all_gather_into_tensor(evals.view(-1), mine.reshape(-1).clone(), group=group)
+        torch.cuda.synchronize(device)
+    comp = None
+    comp_lde = torch.empty((2, m, 4), dtype=mblock.dtype, device=device)
+    comp_root = None
+    if rank == 0:
+        hnd = C.c_void_p()
+        root = np.empty(32, dtype=np.uint8)
+        ctx.check(L.s252_cairo_composition_commit(ctx.handle, C.c_void_p(evals.data_ptr()), n, b, h, C.byref(hnd), N.ptr(root)))
+        comp = DeviceCommit(ctx, hnd, root.tobytes())
+        comp_root = root.tobytes()
+        comp_lde.copy_(_dev_tensor(L.s252_commit_device_lde(hnd), 2 * m * 4, device).view(2, m, 4))
+        torch.cuda.synchronize(device)
+    del evals
+    if world > 1:
+        comp_root = _bcast_bytes(comp_root, 32, device, group)
+        dist.broadcast(comp_lde, src=0 if group is None else dist.get_global_rank(group, 0), group=group)
+        torch.cuda.synchronize(device)
+    t.append(comp_root)
+    # ---- round 3 (prover.rs:650-690)
+    hinv = pow(h, -1, P)
+    while True:                                                                  # sample_z_ood, transcript.rs:53-70
+        z = felt.to_int(transcript_to_field(t))
+        if pow(z * hinv % P, m, P) != 1 and pow(z, n, P) != 1:
+            break
+    pts = felt.from_ints([z, z * g % P])
+
+    def local_ood(local):
+        outs = []
+        for hnd in local.handles:
+            o = np.empty((2, hnd.n_cols, 4), dtype=np.uint64)
+            ctx.check(L.s252_commit_evaluate_at(hnd.handle, N.ptr(pts), 2, N.ptr(o), hnd.n_cols, 0))
+            outs.append(o)
+        return np.concatenate(outs, axis=1)
+    mine_ood = (local_ood(sc_main.local), local_ood(sc_aux.local))
+    hz = np.zeros((2, 4), dtype=np.uint64)
+    if rank == 0:
+        z2 = felt.from_ints([z * z % P])
+        ctx.check(L.s252_commit_evaluate_at(comp.handle, N.ptr(z2), 1, N.ptr(hz), 2, 0))
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, (mine_ood, hz if rank == 0 else None), group=group)
+        ood = np.concatenate([p_[0][0] for p_ in parts] + [p_[0][1] for p_ in parts], axis=1)        # [2, 52, 4]
+        hz = parts[0][1]
+    else:
+        ood = np.concatenate(mine_ood, axis=1)
+    ncols = ood.shape[1]
+    t.append(felt.to_bytes_be(hz[0]))
+    t.append(felt.to_bytes_be(hz[1]))
+    for row in ood:
+        for v in row:
+            t.append(felt.to_bytes_be(v))
+    # ---- round 4 (prover.rs:327-404)
+    gamma, gamma_p = transcript_to_field(t), transcript_to_field(t)
+    tg = np.stack([transcript_to_field(t) for _ in range(2 * ncols)])
+    p0 = torch.empty((m, 4), dtype=mblock.dtype, device=device)
+    mine = p0[rank * rows_per:(rank + 1) * rows_per]
+    cblock = comp_lde[:, rank * rows_per:(rank + 1) * rows_per]                  # stride m
+    tables = (C.c_void_p * 3)(mblock.data_ptr(), ablock.data_ptr(), cblock.data_ptr())
+    strides = (C.c_size_t * 3)(rows_per, rows_per, m)
+    ncs = (C.c_size_t * 3)(c_main, 18, 2)
+    offs = np.array([0, 1], dtype=np.uint64)
+    zlw = felt.from_int(z)
+    ood_flat = np.ascontiguousarray(ood.reshape(-1, 4))
+    ctx.check(L.s252_deep_rows(ctx.handle, tables, strides, ncs, 3, rank * rows_per, rows_per, m, n, N.ptr(zlw), N.ptr(offs), 2,
+                               N.ptr(ood_flat), N.ptr(np.ascontiguousarray(hz[0])), N.ptr(np.ascontiguousarray(hz[1])),
+                               N.ptr(gamma), N.ptr(gamma_p), N.ptr(tg), h, C.c_void_p(mine.data_ptr())))
+    if world > 1:
+        dist.all_gather_into_tensor(p0.view(-1), mine.reshape(-1).clone(), group=group)
+        torch.cuda.synchronize(device)
+    layers = order
+    q_count = options.fri_number_of_queries if layers else 0
+    iotas = np.zeros(max(q_count, 1), dtype=np.uint64)
+    fri = C.c_void_p()
+    if rank == 0:
+        last = np.empty(4, dtype=np.uint64)
+        fri_roots = np.empty((max(layers, 1), 32), dtype=np.uint8)
+        ctx.check(L.s252_fri_commit_phase_evals(ctx.handle, layers, C.c_void_p(p0.data_ptr()), m, t.handle, h, C.byref(fri), N.ptr(last),
+                                                N.ptr(fri_roots)))
+        nonce = C.c_uint64()
+        ch = np.frombuffer(t.challenge(), dtype=np.uint8).copy()
+        ctx.check(L.s252_generate_nonce_with_grinding(ctx.handle, N.ptr(ch), options.grinding_factor, 0, C.byref(nonce)))
+        t.append(_u64be(nonce.value))
+        for q in range(q_count):
+            iotas[q] = transcript_to_usize(t) % m
+    del p0
+    if world > 1:
+        it = torch.from_numpy(iotas.view(np.int64)).to(device)
+        dist.broadcast(it, src=0 if group is None else dist.get_global_rank(group, 0), group=group)
+        iotas = it.cpu().numpy().view(np.uint64)
+    idx = [int(i) for i in iotas[:q_count]]
+    main_rows, main_paths = sc_main.open(idx) if q_count else ([], [])
+    aux_rows, aux_paths = sc_aux.open(idx) if q_count else ([], [])
+    proof = None
+    if rank == 0:
+        depth = m.bit_length() - 1
+        ev = np.empty((q_count, layers, 4), dtype=np.uint64)
+        evs = np.empty_like(ev)
+        pa = np.empty((q_count, layers, depth, 32), dtype=np.uint8)
+        pas = np.empty_like(pa)
+        crow = np.empty((q_count, 2, 4), dtype=np.uint64)
+        cpath = np.empty((q_count, depth, 32), dtype=np.uint8)
+        if q_count:
+            ia = np.array(idx, dtype=np.uint64)
+            ctx.check(L.s252_fri_query(fri, N.ptr(ia), q_count, N.ptr(ev), N.ptr(evs), N.ptr(pa), N.ptr(pas), depth))
+            ctx.check(L.s252_commit_open(comp.handle, N.ptr(ia), q_count, N.ptr(crow), N.ptr(cpath)))
+        fb = felt.to_bytes_be
+        out = _u64be(n) + _u64be(2) + sc_main.root + sc_aux.root                 # StarkProof::serialize, proof/stark.rs:161-218
+        frame = _u64be(2 * ncols) + _u64be(32) + b"".join(fb(v) for row in ood for v in row) + _u64be(ncols)
+        out += _blob(frame) + comp_root + _u64be(32) + fb(hz[0]) + fb(hz[1])
+        out += _u64be(layers) + fri_roots[:layers].tobytes() + fb(last) + _u64be(q_count)
+        for q in range(q_count):
+            d = _u64be(layers) + b"".join(_path(pas[q, k, :depth - k]) for k in range(layers)) + _u64be(32)
+            d += _u64be(layers) + b"".join(fb(evs[q, k]) for k in range(layers))
+            d += _u64be(layers) + b"".join(fb(ev[q, k]) for k in range(layers))
+            d += _u64be(layers) + b"".join(_path(pa[q, k, :depth - k]) for k in range(layers))
+            out += _blob(d)
+        out += _u64be(q_count)
+        for q in range(q_count):
+            o = _path(cpath[q]) + _u64be(32) + fb(crow[q, 0]) + fb(crow[q, 1]) + _u64be(2) + _path(main_paths[q]) + _path(aux_paths[q])
+            o += _u64be(ncols) + b"".join(fb(v) for v in np.asarray(main_rows[q]).view(np.uint64).reshape(-1, 4))
+            o += b"".join(fb(v) for v in np.asarray(aux_rows[q]).view(np.uint64).reshape(-1, 4))
+            out += _blob(o)
+        out += _u64be(nonce.value)
+        proof = out
+        L.s252_fri_destroy(fri)
+        comp.free()
+    sc_main.free()
+    sc_aux.free()
+    return proof

@@ -180,7 +180,8 @@ __global__ void __launch_bounds__(RS_WARPS * 32) rs_scatter(const K* __restrict_
 constexpr unsigned CAIRO_PC = 19, CAIRO_INST = 23, CAIRO_OFF_DST = 27, CAIRO_AUX_COLS = 18;
 
 struct CairoAux {
-    const fe* main;                   // column-major main trace [cols][n] (internal format)
+    const fe* main;                   // column-major main trace (internal format), starting at trace column `col0`
+    unsigned col0;                    // 0: the whole table; 19: only the 11 columns pc .. off_op1 the builder reads
     unsigned long long n;             // rows
     const unsigned long long* pub_addr;   // public memory addresses (address order)
     const fe* pub_addr_fe;            // the same as field elements
@@ -202,14 +203,14 @@ __global__ void __launch_bounds__(256) cairo_aux_keys(CairoAux P, unsigned long 
     unsigned long long k = 0;
     if (L < total) {
         const unsigned long long first_pub = total - P.n_pub;
-        k = L >= first_pub ? P.pub_addr[L - first_pub] : fe_low64(ld_fe(P.main + (CAIRO_PC + (L & 3)) * P.n + (L >> 2)));
+        k = L >= first_pub ? P.pub_addr[L - first_pub] : fe_low64(ld_fe(P.main + (CAIRO_PC - P.col0 + (L & 3)) * P.n + (L >> 2)));
         keys[L] = k;
         idx[L] = (unsigned)L;
     }
     // OR of all keys: its bit length bounds the number of radix passes
     for (int o = 16; o > 0; o >>= 1) k |= __shfl_xor_sync(0xffffffffu, k, o);
     if ((threadIdx.x & 31) == 0 && k) atomicOr(key_or, k);
-    if (L < 3 * P.n) okeys[L] = (unsigned short)fe_low64(ld_fe(P.main + (CAIRO_OFF_DST + L % 3) * P.n + L / 3));
+    if (L < 3 * P.n) okeys[L] = (unsigned short)fe_low64(ld_fe(P.main + (CAIRO_OFF_DST - P.col0 + L % 3) * P.n + L / 3));
 }
 // numerators / denominators of the memory permutation argument (air.rs:535-563) and the sorted
 // address / value columns
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(256) cairo_aux_terms(CairoAux P, const unsigne
     const unsigned long long total = 4 * P.n, first_pub = total - P.n_pub;
     if (L >= total) return;
     const unsigned long long i = L >> 2, k = L & 3;
-    const fe a = ld_fe(P.main + (CAIRO_PC + k) * P.n + i), v = ld_fe(P.main + (CAIRO_INST + k) * P.n + i);
+    const fe a = ld_fe(P.main + (CAIRO_PC - P.col0 + k) * P.n + i), v = ld_fe(P.main + (CAIRO_INST - P.col0 + k) * P.n + i);
     st_fe(num + L, fe_sub_full(P.z, fe_add_full(a, fe_mul_full(P.alpha, v))));
     const unsigned long long s = sorted_idx[L];
     fe as, vs;
@@ -227,8 +228,8 @@ __global__ void __launch_bounds__(256) cairo_aux_terms(CairoAux P, const unsigne
         as = ld_fe(P.pub_addr_fe + (s - first_pub));
         vs = ld_fe(P.pub_val + (s - first_pub));
     } else {
-        as = ld_fe(P.main + (CAIRO_PC + (s & 3)) * P.n + (s >> 2));
-        vs = ld_fe(P.main + (CAIRO_INST + (s & 3)) * P.n + (s >> 2));
+        as = ld_fe(P.main + (CAIRO_PC - P.col0 + (s & 3)) * P.n + (s >> 2));
+        vs = ld_fe(P.main + (CAIRO_INST - P.col0 + (s & 3)) * P.n + (s >> 2));
     }
     st_fe(den + L, fe_sub_full(P.z, fe_add_full(as, fe_mul_full(P.alpha, vs))));
     st_fe(P.aux + (3 + k) * P.n + i, as);
@@ -240,7 +241,7 @@ __global__ void __launch_bounds__(256) cairo_aux_rc_terms(CairoAux P, const unsi
     const unsigned long long R = (unsigned long long)blockIdx.x * 256 + threadIdx.x;
     if (R >= 3 * P.n) return;
     const unsigned long long i = R / 3, k = R % 3;
-    st_fe(num + R, fe_sub_full(P.zrc, ld_fe(P.main + (CAIRO_OFF_DST + k) * P.n + i)));
+    st_fe(num + R, fe_sub_full(P.zrc, ld_fe(P.main + (CAIRO_OFF_DST - P.col0 + k) * P.n + i)));
     fe so = fe_zero();
     so.l[0] = sorted_off[R];
     so = fe_to_mont(so);
@@ -265,9 +266,16 @@ constexpr int CAIRO_MAX_TRANSITION = 50;
 constexpr int CAIRO_EVAL_THREADS = 128;
 
 struct CairoEval {
-    const fe* main;              // column-major LDE of the main trace [main_cols][m]
-    const fe* aux;               // column-major LDE of the auxiliary trace [18][m]
-    unsigned long long m;        // LDE rows
+    // The kernel works on a block of `rows` consecutive LDE rows starting at global row `row0` (the whole
+    // coset on one GPU; this rank's row block in a sharded proof).  The "next" frame row i + blowup of the
+    // last `blowup` rows lives in the halo (on one GPU: the first rows of the same table, stride m).
+    const fe* main;              // column-major LDE of the main trace [main_cols][stride]
+    const fe* aux;               // column-major LDE of the auxiliary trace [18][stride]
+    const fe* hmain;             // halo: rows row0+rows .. row0+rows+blowup-1 (mod m) of the main columns [main_cols][hstride]
+    const fe* haux;
+    unsigned long long stride, hstride;
+    unsigned long long row0, rows;
+    unsigned long long m;        // LDE rows (global)
     unsigned blowup;
     unsigned main_cols;          // 34, or 43 with the range-check builtin
     unsigned has_rc;
@@ -285,7 +293,7 @@ struct CairoEval {
     const fe* bcoef;
     const fe* tcoef;
     fe two, b15, b16, b32, b48;  // 2, 2^15, 2^16, 2^32, 2^48
-    fe* out;                     // [m]
+    fe* out;                     // [rows]
 };
 
 // a load the compiler treats as distinct from every other load of the same address (it is served by L1):
@@ -318,22 +326,24 @@ __device__ __forceinline__ constexpr bool cairo_exempt(int k) {
 // (no spills, 4-5 blocks per SM); the extra traffic is two read-modify-writes of `out`.
 template <int PHASE>
 __global__ void __launch_bounds__(CAIRO_EVAL_THREADS, PHASE == 1 ? 3 : 4) cairo_constraints_kernel(CairoEval P) {
-    const unsigned long long i = (unsigned long long)blockIdx.x * CAIRO_EVAL_THREADS + threadIdx.x;
-    if (i >= P.m) return;
-    const unsigned long long i2 = (i + P.blowup) & (P.m - 1);     // Frame::read_from_trace, offsets [0, 1]
+    const unsigned long long il = (unsigned long long)blockIdx.x * CAIRO_EVAL_THREADS + threadIdx.x;   // row inside the block
+    if (il >= P.rows) return;
+    const unsigned long long i = P.row0 + il;                      // global LDE row
+    const unsigned long long n2 = il + P.blowup;                   // Frame::read_from_trace, offsets [0, 1]
+    const bool in_block = n2 < P.rows;
     const unsigned r = (unsigned)(i & (P.blowup - 1));
     const fe* tc = P.tcoef + r;
     const unsigned bs = P.blowup;
-    const fe* mrow = P.main + i;
-    const fe* mnxt = P.main + i2;
-    const fe* arow = P.aux + i;
-    const fe* anx = P.aux + i2;
-    const unsigned long long m = P.m;
-#define CUR(j) ld_fe(mrow + (unsigned long long)(j) * m)
-#define RCUR(j) ld_fe_again(mrow + (unsigned long long)(j) * m)
-#define NXT(j) ld_fe(mnxt + (unsigned long long)(j) * m)
-#define ACUR(j) ld_fe(arow + (unsigned long long)(j) * m)
-#define ANXT(j) ld_fe(anx + (unsigned long long)(j) * m)
+    const fe* mrow = P.main + il;
+    const fe* mnxt = in_block ? P.main + n2 : P.hmain + (n2 - P.rows);
+    const fe* arow = P.aux + il;
+    const fe* anx = in_block ? P.aux + n2 : P.haux + (n2 - P.rows);
+    const unsigned long long m = P.m, cs = P.stride, ns = in_block ? P.stride : P.hstride;
+#define CUR(j) ld_fe(mrow + (unsigned long long)(j) * cs)
+#define RCUR(j) ld_fe_again(mrow + (unsigned long long)(j) * cs)
+#define NXT(j) ld_fe(mnxt + (unsigned long long)(j) * ns)
+#define ACUR(j) ld_fe(arow + (unsigned long long)(j) * cs)
+#define ANXT(j) ld_fe(anx + (unsigned long long)(j) * ns)
 #define COEF(k) ldg_fe(tc + (unsigned)(k) * bs)
     const fe one = fe_one();
     fe acc = fe_zero(), acc_ex = fe_zero();          // plain and exempted (times x - g^(n-1)) constraints
@@ -475,7 +485,7 @@ __global__ void __launch_bounds__(CAIRO_EVAL_THREADS, PHASE == 1 ? 3 : 4) cairo_
     }
     if constexpr (PHASE != 0) {
         ACC(acc, acc_ex, LS1(ld_fe(P.dom + i), P.g_last));
-        acc = fe_reduce(fe_add_lazy(acc, ld_fe(P.out + i)));
+        acc = fe_reduce(fe_add_lazy(acc, ld_fe(P.out + il)));
     }
     // ---- boundary constraints (evaluator.rs:58-122): 1/(x - g^s) = g^(-s) * T[i - blowup*s]
     for (unsigned k = 0; PHASE == 2 && k < P.nb; ++k) {
@@ -484,7 +494,7 @@ __global__ void __launch_bounds__(CAIRO_EVAL_THREADS, PHASE == 1 ? 3 : 4) cairo_
         const fe zi = ld_fe(P.T + ((i + m - P.bshift[k]) & (m - 1)));
         ACC(acc, LM(zi, ldg_fe(P.bcoef + k * bs + r)), LS1(v, P.bval[k]));        // (2)(2)
     }
-    st_fe(P.out + i, acc);
+    st_fe(P.out + il, acc);
 #undef CUR
 #undef RCUR
 #undef NXT

@@ -262,7 +262,7 @@ static int radix_sort(s252_ctx* ctx, K* keys, K* keys2, unsigned* vals, unsigned
 }
 
 // build_auxiliary_trace (air.rs:660-729) into aux[18][N] (column-major, internal format)
-static int cairo_build_aux(s252_ctx* ctx, const fe* main_cols, size_t N, const CA::PublicInputs& pi, const fe rap[3], fe* aux) {
+static int cairo_build_aux(s252_ctx* ctx, const fe* main_cols, unsigned col0, size_t N, const CA::PublicInputs& pi, const fe rap[3], fe* aux) {
     const size_t L = 4 * N, R = 3 * N, np = pi.public_memory.size();
     if (np > L) FAIL(ctx, S252_ERR_INVALID, "public memory (%zu words) does not fit the trace", np);
     if (L >= (1ull << 31)) FAIL(ctx, S252_ERR_INVALID, "trace too long for the auxiliary-trace sort");
@@ -288,7 +288,7 @@ static int cairo_build_aux(s252_ctx* ctx, const fe* main_cols, size_t N, const C
     TRY(dalloc(ctx, &key_or.p, 1));
     CU(ctx, cudaMemsetAsync(key_or.p, 0, 8, ctx->stream));
     s252::CairoAux P{};
-    P.main = main_cols; P.n = N; P.pub_addr = d_paddr.p; P.pub_addr_fe = d_paddr_fe.p; P.pub_val = d_pval.p; P.n_pub = (unsigned)np;
+    P.main = main_cols; P.col0 = col0; P.n = N; P.pub_addr = d_paddr.p; P.pub_addr_fe = d_paddr_fe.p; P.pub_val = d_pval.p; P.n_pub = (unsigned)np;
     P.alpha = rap[0]; P.z = rap[1]; P.zrc = rap[2]; P.aux = aux;
     const unsigned gl = (unsigned)((L + 255) / 256), gr = (unsigned)((R + 255) / 256);
     prof_begin(ctx, "cairo_aux_keys");
@@ -339,7 +339,7 @@ static int cairo_build_aux(s252_ctx* ctx, const fe* main_cols, size_t N, const C
 // upload is pipelined with the transforms: group g+1 of columns crosses PCIe on the copy stream while
 // group g is converted, interpolated and extended, so only the first group's upload is exposed.
 static int commit_from_host_columns(s252_ctx* ctx, const s252_fe* cols_lw, size_t N, unsigned c, size_t blowup, uint64_t coset_offset,
-                                    bool keep_trace, s252_commit** out, uint8_t root[32]) {
+                                    bool keep_trace, s252_commit** out, uint8_t root[32], bool with_tree = true) {
     if (!is_pow2(N) || c == 0) FAIL(ctx, S252_ERR_INVALID, "FFTError: trace length %zu is not a power of two", N);
     if (!is_pow2(blowup) || blowup > MAX_COSETS) FAIL(ctx, S252_ERR_INVALID, "blowup factor %zu must be a power of two <= %u", blowup, MAX_COSETS);
     if (coset_offset == 0) FAIL(ctx, S252_ERR_INVALID, "coset offset must be non-zero");
@@ -379,9 +379,13 @@ static int commit_from_host_columns(s252_ctx* ctx, const s252_fe* cols_lw, size_
             TRY(evaluate_cosets(ctx, cm->coeffs + off, N, false, ilog2(N), (unsigned)blowup, H::from_u64(coset_offset),
                                 cm->lde + (size_t)lo[g] * M, M, false, cg));                              // compute_lde_trace_evaluations
         }
-        TRY(dalloc(ctx, &cm->nodes, 4 * (2 * M - 1)));
-        TRY(build_tree(ctx, cm->lde, M, c, M, cm->nodes));                                               // batch_commit
-        TRY(fetch_root(ctx, cm->nodes, root));
+        if (with_tree) {
+            TRY(dalloc(ctx, &cm->nodes, 4 * (2 * M - 1)));
+            TRY(build_tree(ctx, cm->lde, M, c, M, cm->nodes));                                           // batch_commit
+            TRY(fetch_root(ctx, cm->nodes, root));
+        } else {
+            CU(ctx, cudaStreamSynchronize(ctx->stream));
+        }
         if (keep_trace) { cm->trace = cols.p; cols.p = nullptr; }
         return S252_OK;
     }();
@@ -412,7 +416,7 @@ extern "C" int s252_cairo_round1(s252_ctx* ctx, const s252_cairo_trace* trace, s
     auxc->ctx = ctx; auxc->n_cols = s252::CAIRO_AUX_COLS; auxc->n_rows = N * blowup; auxc->n_coeffs = N;
     int rc = [&]() -> int {
         TRY(dalloc(ctx, &auxc->trace, N * s252::CAIRO_AUX_COLS));
-        TRY(cairo_build_aux(ctx, mainc->trace, N, trace->pi, rap, auxc->trace));
+        TRY(cairo_build_aux(ctx, mainc->trace, 0, N, trace->pi, rap, auxc->trace));
         R1.mark("aux_build");
         TRY(lde_from_cols(ctx, auxc->trace, N, s252::CAIRO_AUX_COLS, blowup, coset_offset, true, auxc, root));
         R1.mark("aux_commit");
@@ -439,13 +443,29 @@ static const uint8_t CAIRO_DEGREES[50] = {2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2,
 
 // ConstraintEvaluator::evaluate for CairoAIR (evaluator.rs:40-262) into evals[M] (device, internal format);
 // ba/bb: boundary alphas/betas (8), ta/tb: transition alphas/betas (49, or 50 with the range-check builtin).
+// a block of consecutive LDE rows of the two round-1 tables (the whole coset on one GPU)
+struct CairoRowBlock {
+    const fe *main, *aux, *hmain, *haux;      // column-major blocks and their `blowup`-row halos (see CairoEval)
+    size_t stride, hstride, row0, rows;
+};
+static int cairo_eval_constraints_rows(s252_ctx* ctx, const s252_cairo_trace* trace, const CairoRowBlock& B, const fe rap[3],
+                                       const fe* ba, const fe* bb, const fe* ta, const fe* tb, size_t blowup, uint64_t coset_offset,
+                                       fe* evals);
 static int cairo_eval_constraints(s252_ctx* ctx, const s252_cairo_trace* trace, const s252_commit* mainc, const s252_commit* auxc,
                                   const fe rap[3], const fe* ba, const fe* bb, const fe* ta, const fe* tb, size_t blowup,
                                   uint64_t coset_offset, fe* evals) {
-    const CA::PublicInputs& pi = trace->pi;
-    const size_t N = trace->n_rows, M = N * blowup, b = blowup;
+    const size_t M = trace->n_rows * blowup;
     if (mainc->n_rows != M || auxc->n_rows != M || auxc->n_cols != s252::CAIRO_AUX_COLS || mainc->n_cols != trace->n_cols)
         FAIL(ctx, S252_ERR_INVALID, "round-1 handles do not match the trace");
+    const CairoRowBlock B{mainc->lde, auxc->lde, mainc->lde, auxc->lde, M, M, 0, M};
+    return cairo_eval_constraints_rows(ctx, trace, B, rap, ba, bb, ta, tb, blowup, coset_offset, evals);
+}
+static int cairo_eval_constraints_rows(s252_ctx* ctx, const s252_cairo_trace* trace, const CairoRowBlock& B, const fe rap[3],
+                                       const fe* ba, const fe* bb, const fe* ta, const fe* tb, size_t blowup, uint64_t coset_offset,
+                                       fe* evals) {
+    const CA::PublicInputs& pi = trace->pi;
+    const size_t N = trace->n_rows, M = N * blowup, b = blowup;
+    if (B.rows == 0 || B.row0 + B.rows > M || B.stride < B.rows || B.hstride < b) FAIL(ctx, S252_ERR_INVALID, "bad row block");
     if (!pi.has_rc) FAIL(ctx, S252_ERR_INVALID, "public inputs carry no range-check bounds (build_main_trace sets them)");
     if (pi.num_steps == 0 || pi.num_steps > N) FAIL(ctx, S252_ERR_INVALID, "num_steps out of range");
     const bool has_rc = trace->n_cols > CA::MAIN_COLS;
@@ -487,7 +507,8 @@ static int cairo_eval_constraints(s252_ctx* ctx, const s252_cairo_trace* trace, 
         }
     }
     s252::CairoEval E{};
-    E.main = mainc->lde; E.aux = auxc->lde; E.m = M; E.blowup = (unsigned)b; E.main_cols = mc; E.has_rc = has_rc;
+    E.main = B.main; E.aux = B.aux; E.m = M; E.blowup = (unsigned)b; E.main_cols = mc; E.has_rc = has_rc;
+    E.hmain = B.hmain; E.haux = B.haux; E.stride = B.stride; E.hstride = B.hstride; E.row0 = B.row0; E.rows = B.rows;
     E.alpha = rap[0]; E.z = rap[1]; E.zrc = rap[2];
     E.g_last = H::pow_u64(g, N - 1);
     E.two = H::from_u64(2); E.b15 = H::from_u64(1ull << 15); E.b16 = H::from_u64(1ull << 16); E.b32 = H::from_u64(1ull << 32); E.b48 = H::from_u64(1ull << 48);
@@ -499,17 +520,17 @@ static int cairo_eval_constraints(s252_ctx* ctx, const s252_cairo_trace* trace, 
     CU(ctx, cudaMemcpyAsync(dtabs.p, tabs.data(), tabs.size() * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
     E.bcoef = dtabs.p; E.tcoef = dtabs.p + 8 * b;
     E.out = evals;
-    const unsigned grid = (unsigned)((M + s252::CAIRO_EVAL_THREADS - 1) / s252::CAIRO_EVAL_THREADS);
+    const unsigned grid = (unsigned)((B.rows + s252::CAIRO_EVAL_THREADS - 1) / s252::CAIRO_EVAL_THREADS);
     prof_begin(ctx, "cairo_constraints_kernel<0>");
-    prof_work(ctx, 32.0 * M * 29, 53.0 * M, 0);
+    prof_work(ctx, 32.0 * B.rows * 29, 53.0 * B.rows, 0);
     s252::cairo_constraints_kernel<0><<<grid, s252::CAIRO_EVAL_THREADS, 0, ctx->stream>>>(E);
     LAUNCH_CHECK(ctx);
     prof_begin(ctx, "cairo_constraints_kernel<1>");
-    prof_work(ctx, 32.0 * M * 29, 42.0 * M, 0);
+    prof_work(ctx, 32.0 * B.rows * 29, 42.0 * B.rows, 0);
     s252::cairo_constraints_kernel<1><<<grid, s252::CAIRO_EVAL_THREADS, 0, ctx->stream>>>(E);
     LAUNCH_CHECK(ctx);
     prof_begin(ctx, "cairo_constraints_kernel<2>");
-    prof_work(ctx, 32.0 * M * 44, 70.0 * M, 0);
+    prof_work(ctx, 32.0 * B.rows * 44, 70.0 * B.rows, 0);
     s252::cairo_constraints_kernel<2><<<grid, s252::CAIRO_EVAL_THREADS, 0, ctx->stream>>>(E);
     LAUNCH_CHECK(ctx);
     CU(ctx, cudaStreamSynchronize(ctx->stream));   // the coefficient tables (host vector, device temporary) go out of scope
@@ -533,37 +554,24 @@ extern "C" int s252_cairo_constraint_evaluations(s252_ctx* ctx, const s252_cairo
     return read_internal_as_lw(ctx, evals.p, M, out);
 }
 
-extern "C" int s252_cairo_round2(s252_ctx* ctx, const s252_cairo_trace* trace, s252_commit* mainc, s252_commit* auxc,
-                                 const s252_fe rap_lw[3], size_t blowup, uint64_t coset_offset, s252_transcript* transcript,
-                                 s252_commit** composition_out) {
-    if (!ctx || !trace || !mainc || !auxc || !rap_lw || !transcript || !composition_out) return S252_ERR_INVALID;
-    *composition_out = nullptr;
-    CU(ctx, cudaSetDevice(ctx->device));
-    const size_t N = trace->n_rows, M = N * blowup, b = blowup;
-    const int nt = trace->n_cols > CA::MAIN_COLS ? 50 : 49;
-    fe rap[3];
-    for (int k = 0; k < 3; ++k) rap[k] = H::from_lw(rap_lw[k].limbs);
-    // <<<< challenges (prover.rs:598-626): boundary alphas, boundary betas, transition alphas, transition betas
-    fe ba[8], bb[8], ta[50], tb[50];
-    for (int k = 0; k < 8; ++k) ba[k] = transcript->to_field();
-    for (int k = 0; k < 8; ++k) bb[k] = transcript->to_field();
-    for (int k = 0; k < nt; ++k) ta[k] = transcript->to_field();
-    for (int k = 0; k < nt; ++k) tb[k] = transcript->to_field();
+// round_2_compute_composition_polynomial after the constraint evaluation (prover.rs:246-283): H from its M
+// evaluations on the coset (interpolate_offset_fft, evaluation_table.rs:27-33), even/odd split, LDE of H1 and
+// H2, batch_commit.  The handle keeps the H1, H2 coefficients.
+static int cairo_composition_commit(s252_ctx* ctx, const fe* evals, size_t N, size_t blowup, uint64_t coset_offset,
+                                    s252_commit** out, uint8_t root[32]) {
+    const size_t M = N * blowup;
     s252_commit* cm = new s252_commit();
     cm->ctx = ctx; cm->n_cols = 2; cm->n_rows = M; cm->n_coeffs = N;
     int rc = [&]() -> int {
-        Tmp<fe> evals(ctx), hco(ctx);
+        Tmp<fe> hco(ctx);
         Tmp<unsigned> flag(ctx);
-        TRY(dalloc(ctx, &evals.p, M));
-        TRY(cairo_eval_constraints(ctx, trace, mainc, auxc, rap, ba, bb, ta, tb, blowup, coset_offset, evals.p));
-        // compute_composition_poly: interpolate_offset_fft(evaluations, offset) (evaluation_table.rs:27-33)
         TRY(dalloc(ctx, &hco.p, M));
         Xform X;
         X.logn = ilog2(M);
         X.inverse = true;
         X.has_offset_scale = true;
         X.oscale_base = H::inv(H::from_u64(coset_offset));
-        TRY(run_ntt(ctx, X, evals.p, M, false, hco.p, M, false, 1));
+        TRY(run_ntt(ctx, X, evals, M, false, hco.p, M, false, 1));
         // even_odd_decomposition (prover.rs:252)
         TRY(dalloc(ctx, &cm->coeffs, 2 * N));
         TRY(dalloc(ctx, &flag.p, 1));
@@ -578,17 +586,128 @@ extern "C" int s252_cairo_round2(s252_ctx* ctx, const s252_cairo_trace* trace, s
         if (over) FAIL(ctx, S252_ERR_INVALID, "the composition polynomial exceeds its degree bound: the trace does not satisfy the Cairo AIR");
         // evaluate_polynomial_on_lde_domain(H1), (H2) + batch_commit (prover.rs:254-276)
         TRY(dalloc(ctx, &cm->lde, 2 * M));
-        TRY(evaluate_cosets(ctx, cm->coeffs, N, false, ilog2(N), (unsigned)b, H::from_u64(coset_offset), cm->lde, M, false, 2));
+        TRY(evaluate_cosets(ctx, cm->coeffs, N, false, ilog2(N), (unsigned)blowup, H::from_u64(coset_offset), cm->lde, M, false, 2));
         TRY(dalloc(ctx, &cm->nodes, 4 * (2 * M - 1)));
         TRY(build_tree(ctx, cm->lde, M, 2, M, cm->nodes));
-        uint8_t root[32];
         TRY(fetch_root(ctx, cm->nodes, root));
-        transcript->append(root, 32);                               // prover.rs:635
         return S252_OK;
     }();
     if (rc != S252_OK) { commit_free(cm); return rc; }
-    *composition_out = cm;
+    *out = cm;
     return S252_OK;
+}
+
+extern "C" int s252_cairo_round2(s252_ctx* ctx, const s252_cairo_trace* trace, s252_commit* mainc, s252_commit* auxc,
+                                 const s252_fe rap_lw[3], size_t blowup, uint64_t coset_offset, s252_transcript* transcript,
+                                 s252_commit** composition_out) {
+    if (!ctx || !trace || !mainc || !auxc || !rap_lw || !transcript || !composition_out) return S252_ERR_INVALID;
+    *composition_out = nullptr;
+    CU(ctx, cudaSetDevice(ctx->device));
+    const size_t N = trace->n_rows, M = N * blowup;
+    const int nt = trace->n_cols > CA::MAIN_COLS ? 50 : 49;
+    fe rap[3];
+    for (int k = 0; k < 3; ++k) rap[k] = H::from_lw(rap_lw[k].limbs);
+    // <<<< challenges (prover.rs:598-626): boundary alphas, boundary betas, transition alphas, transition betas
+    fe ba[8], bb[8], ta[50], tb[50];
+    for (int k = 0; k < 8; ++k) ba[k] = transcript->to_field();
+    for (int k = 0; k < 8; ++k) bb[k] = transcript->to_field();
+    for (int k = 0; k < nt; ++k) ta[k] = transcript->to_field();
+    for (int k = 0; k < nt; ++k) tb[k] = transcript->to_field();
+    Tmp<fe> evals(ctx);
+    TRY(dalloc(ctx, &evals.p, M));
+    TRY(cairo_eval_constraints(ctx, trace, mainc, auxc, rap, ba, bb, ta, tb, blowup, coset_offset, evals.p));
+    uint8_t root[32];
+    TRY(cairo_composition_commit(ctx, evals.p, N, blowup, coset_offset, composition_out, root));
+    transcript->append(root, 32);                                   // prover.rs:635
+    return S252_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// Building blocks of a proof sharded over several GPUs (lambdaworks_cairo_prover_b200/cairo_distributed.py):
+// the same kernels as s252_cairo_prove, on this rank's columns (LDE) or on this rank's block of LDE rows.
+extern "C" const s252_fe* s252_cairo_trace_columns(const s252_cairo_trace* t) { return t->cols.data(); }
+
+extern "C" int s252_lde_host_columns(s252_ctx* ctx, const s252_fe* cols_lw, size_t n_rows, size_t n_cols, size_t blowup,
+                                     uint64_t coset_offset, s252_commit** out) {
+    if (!ctx || !cols_lw || !out) return S252_ERR_INVALID;
+    *out = nullptr;
+    CU(ctx, cudaSetDevice(ctx->device));
+    return commit_from_host_columns(ctx, cols_lw, n_rows, (unsigned)n_cols, blowup, coset_offset, false, out, nullptr, false);
+}
+extern "C" int s252_lde_device_columns(s252_ctx* ctx, const void* cols, size_t n_rows, size_t n_cols, size_t blowup,
+                                       uint64_t coset_offset, s252_commit** out) {
+    if (!ctx || !cols || !out) return S252_ERR_INVALID;
+    *out = nullptr;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (!is_pow2(n_rows) || n_cols == 0 || !is_pow2(blowup) || blowup > MAX_COSETS || coset_offset == 0) FAIL(ctx, S252_ERR_INVALID, "bad LDE shape");
+    s252_commit* cm = new s252_commit();
+    cm->ctx = ctx; cm->n_cols = n_cols; cm->n_rows = n_rows * blowup; cm->n_coeffs = n_rows;
+    const int rc = lde_from_cols(ctx, reinterpret_cast<const fe*>(cols), n_rows, (unsigned)n_cols, blowup, coset_offset, false, cm, nullptr);
+    if (rc != S252_OK) { commit_free(cm); return rc; }
+    *out = cm;
+    return S252_OK;
+}
+// build_auxiliary_trace on this device from the 11 main-trace columns it reads (pc .. off_op1, uploaded from
+// the handle's pinned column-major table): *aux_out = device buffer [18][n_rows] (internal format; free it
+// with s252_device_free).
+extern "C" int s252_cairo_aux_trace_device(s252_ctx* ctx, const s252_cairo_trace* trace, const s252_fe rap_lw[3], void** aux_out) {
+    if (!ctx || !trace || !rap_lw || !aux_out) return S252_ERR_INVALID;
+    *aux_out = nullptr;
+    CU(ctx, cudaSetDevice(ctx->device));
+    const size_t N = trace->n_rows;
+    fe rap[3];
+    for (int k = 0; k < 3; ++k) rap[k] = H::from_lw(rap_lw[k].limbs);
+    s252_cairo_trace_pin(trace);
+    Tmp<fe> staged(ctx), cols(ctx);
+    fe* aux = nullptr;
+    TRY(dalloc(ctx, &staged.p, 11 * N));
+    TRY(dalloc(ctx, &cols.p, 11 * N));
+    CU(ctx, cudaMemcpyAsync(staged.p, trace->cols.data() + (size_t)s252::CAIRO_PC * N, 11 * N * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
+    TRY(convert_lw_to_internal(ctx, staged.p, cols.p, 11 * N));
+    TRY(dalloc(ctx, &aux, (size_t)s252::CAIRO_AUX_COLS * N));
+    const int rc = cairo_build_aux(ctx, cols.p, s252::CAIRO_PC, N, trace->pi, rap, aux);
+    if (rc != S252_OK) { dfree(ctx, aux); return rc; }
+    *aux_out = aux;
+    return S252_OK;
+}
+extern "C" int s252_cairo_constraints_rows(s252_ctx* ctx, const s252_cairo_trace* trace, const void* main_block, const void* aux_block,
+                                           size_t stride, size_t row0, size_t rows, const void* main_halo, const void* aux_halo,
+                                           size_t halo_stride, const s252_fe rap_lw[3], const s252_fe* boundary_coeffs,
+                                           const s252_fe* transition_coeffs, size_t blowup, uint64_t coset_offset, void* evals_out) {
+    if (!ctx || !trace || !main_block || !aux_block || !main_halo || !aux_halo || !rap_lw || !boundary_coeffs || !transition_coeffs || !evals_out)
+        return S252_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    const int nt = trace->n_cols > CA::MAIN_COLS ? 50 : 49;
+    fe rap[3], ba[8], bb[8], ta[50], tb[50];
+    for (int k = 0; k < 3; ++k) rap[k] = H::from_lw(rap_lw[k].limbs);
+    for (int k = 0; k < 8; ++k) { ba[k] = H::from_lw(boundary_coeffs[2 * k].limbs); bb[k] = H::from_lw(boundary_coeffs[2 * k + 1].limbs); }
+    for (int k = 0; k < nt; ++k) { ta[k] = H::from_lw(transition_coeffs[2 * k].limbs); tb[k] = H::from_lw(transition_coeffs[2 * k + 1].limbs); }
+    const CairoRowBlock B{reinterpret_cast<const fe*>(main_block), reinterpret_cast<const fe*>(aux_block), reinterpret_cast<const fe*>(main_halo),
+                          reinterpret_cast<const fe*>(aux_halo), stride, halo_stride, row0, rows};
+    return cairo_eval_constraints_rows(ctx, trace, B, rap, ba, bb, ta, tb, blowup, coset_offset, reinterpret_cast<fe*>(evals_out));
+}
+extern "C" int s252_cairo_composition_commit(s252_ctx* ctx, const void* evals, size_t n_rows, size_t blowup, uint64_t coset_offset,
+                                             s252_commit** out, uint8_t root[32]) {
+    if (!ctx || !evals || !out || !root) return S252_ERR_INVALID;
+    *out = nullptr;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (!is_pow2(n_rows) || !is_pow2(blowup) || coset_offset == 0) FAIL(ctx, S252_ERR_INVALID, "bad composition shape");
+    return cairo_composition_commit(ctx, reinterpret_cast<const fe*>(evals), n_rows, blowup, coset_offset, out, root);
+}
+extern "C" int s252_deep_rows(s252_ctx* ctx, const void* const* tables, const size_t* strides, const size_t* n_cols, size_t n_tables,
+                              size_t row0, size_t rows, size_t lde_rows, size_t trace_rows, const s252_fe* z,
+                              const uint64_t* transition_offsets, size_t n_offsets, const s252_fe* trace_ood, const s252_fe* h1_z2,
+                              const s252_fe* h2_z2, const s252_fe* gamma, const s252_fe* gamma_p, const s252_fe* trace_gammas,
+                              uint64_t coset_offset, void* out) {
+    if (!ctx || !tables || !strides || !n_cols || !z || !transition_offsets || !trace_ood || !h1_z2 || !h2_z2 || !gamma || !gamma_p ||
+        !trace_gammas || !out || n_tables < 2 || n_tables > (size_t)s252::DEEP_MAX_TABLES)
+        return S252_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    DeepTables T{};
+    for (size_t i = 0; i < n_tables; ++i) { T.cols[i] = reinterpret_cast<const fe*>(tables[i]); T.strides[i] = strides[i]; T.ncols[i] = (unsigned)n_cols[i]; }
+    T.ntables = (unsigned)n_tables;
+    return deep_evaluate_rows(ctx, T, row0, rows, lde_rows, trace_rows, z, transition_offsets, n_offsets, trace_ood, h1_z2, h2_z2, gamma,
+                              gamma_p, trace_gammas, coset_offset, reinterpret_cast<fe*>(out));
 }
 
 // StarkProof::serialize helpers (proof/stark.rs:161-218; frame.rs:86-105; fri_decommit.rs:19-45; utils.rs:6-13)

@@ -90,8 +90,9 @@ struct DeepParams {
     fe ginv[DEEP_MAX_K];                         // g^(-offset_k)
     fe ck[DEEP_MAX_K];                           // sum_j gamma_jk * t_j(z g^k)
     fe cz2;                                      // gamma*H1(z^2) + gamma'*H2(z^2)
-    unsigned long long m;                        // LDE rows
-    fe* out;                                     // [m] evaluations of p0 (internal format)
+    unsigned long long m;                        // LDE rows (global)
+    unsigned long long row0, rows;               // the block of rows this launch covers (0, m on one GPU); cols/out are block-local
+    fe* out;                                     // [rows] evaluations of p0 (internal format)
 };
 
 // a^(p-2)
@@ -109,8 +110,9 @@ __device__ inline fe fe_inverse(const fe& a) {
 // 8 columns), then the K + 1 divisions as multiplications by the precomputed inverse tables.
 template <int K>
 __global__ void __launch_bounds__(DEEP_THREADS) deep_composition_kernel(DeepParams P) {
-    const unsigned long long row = (unsigned long long)blockIdx.x * DEEP_THREADS + threadIdx.x;
-    if (row >= P.m) return;
+    const unsigned long long row = (unsigned long long)blockIdx.x * DEEP_THREADS + threadIdx.x;    // row inside the block
+    if (row >= P.rows) return;
+    const unsigned long long gi = P.row0 + row;                                                     // global LDE row
     fe s[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) s[k] = fe_zero();
@@ -133,10 +135,10 @@ __global__ void __launch_bounds__(DEEP_THREADS) deep_composition_kernel(DeepPara
     const unsigned ct = P.ntables - 1;
     const fe h1 = ld_fe(P.cols[ct] + row), h2 = ld_fe(P.cols[ct] + P.strides[ct] + row);
     const fe sz = fe_reduce(fe_add_lazy(fe_mul(h1, ldg_fe(g)), fe_mul(h2, ldg_fe(g + 1))));
-    fe acc = fe_mul_full(fe_sub_full(sz, P.cz2), ld_fe(P.V + row));
+    fe acc = fe_mul_full(fe_sub_full(sz, P.cz2), ld_fe(P.V + gi));
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        const fe inv = fe_mul(P.ginv[k], ld_fe(P.U + ((row + P.m - P.rot[k]) & (P.m - 1))));         // < 2p
+        const fe inv = fe_mul(P.ginv[k], ld_fe(P.U + ((gi + P.m - P.rot[k]) & (P.m - 1))));         // < 2p
         acc = fe_reduce(fe_add_lazy(acc, fe_mul(fe_sub_lazy<1>(fe_reduce(s[k]), P.ck[k]), inv)));    // (2)(2)
     }
     st_fe(P.out + row, acc);

@@ -1174,38 +1174,30 @@ static int invert_shifted(s252_ctx* ctx, const fe* dom, size_t n, const fe& c, f
     return S252_OK;
 }
 
-// Round 4 from the resident commits: DEEP composition polynomial as evaluations on the LDE coset
-// (replaces compute_deep_composition_poly, prover.rs:410-482, and FRI layer 0's transform), then
-// fri_commit_phase (fri/mod.rs:20-72).
-extern "C" int s252_fri_commit_phase_deep(s252_ctx* ctx, size_t number_layers, s252_commit* const* trace_commits,
-                                          size_t n_trace_commits, s252_commit* composition_commit, const s252_fe* z,
-                                          const uint64_t* transition_offsets, size_t n_offsets, const s252_fe* trace_ood,
-                                          const s252_fe* h1_z2, const s252_fe* h2_z2, const s252_fe* gamma,
-                                          const s252_fe* gamma_p, const s252_fe* trace_gammas, s252_transcript* transcript,
-                                          uint64_t coset_offset, s252_fri** out, s252_fe* last_value, uint8_t* roots_out) {
-    if (!ctx || !trace_commits || !composition_commit || !z || !transition_offsets || !trace_ood || !h1_z2 || !h2_z2 || !gamma ||
-        !gamma_p || !trace_gammas || !transcript || !out || !last_value)
-        return S252_ERR_INVALID;
-    *out = nullptr;
-    CU(ctx, cudaSetDevice(ctx->device));
-    if (n_trace_commits == 0 || n_trace_commits + 1 > s252::DEEP_MAX_TABLES) FAIL(ctx, S252_ERR_INVALID, "between 1 and %d trace tables are supported", s252::DEEP_MAX_TABLES - 1);
+// The DEEP composition polynomial on a block of LDE rows [row0, row0 + rows): tables[t] holds the block's
+// rows of table t column-major with stride strides[t]; the last table is (H1, H2).  out: [rows].
+struct DeepTables {
+    const fe* cols[s252::DEEP_MAX_TABLES];
+    size_t strides[s252::DEEP_MAX_TABLES];
+    unsigned ncols[s252::DEEP_MAX_TABLES];
+    unsigned ntables;
+};
+static int deep_evaluate_rows(s252_ctx* ctx, const DeepTables& T, size_t row0, size_t rows, size_t M, size_t Ntrace, const s252_fe* z,
+                              const uint64_t* transition_offsets, size_t n_offsets, const s252_fe* trace_ood, const s252_fe* h1_z2,
+                              const s252_fe* h2_z2, const s252_fe* gamma, const s252_fe* gamma_p, const s252_fe* trace_gammas,
+                              uint64_t coset_offset, fe* out) {
+    if (T.ntables < 2 || T.ntables > (unsigned)s252::DEEP_MAX_TABLES) FAIL(ctx, S252_ERR_INVALID, "between 1 and %d trace tables are supported", s252::DEEP_MAX_TABLES - 1);
     if (n_offsets == 0 || n_offsets > (size_t)s252::DEEP_MAX_K) FAIL(ctx, S252_ERR_INVALID, "between 1 and %d frame rows are supported", s252::DEEP_MAX_K);
-    if (composition_commit->n_cols != 2) FAIL(ctx, S252_ERR_INVALID, "the composition commit must hold H1 and H2");
     if (coset_offset == 0) FAIL(ctx, S252_ERR_INVALID, "coset offset must be non-zero");
-    const size_t M = composition_commit->n_rows, Ntrace = trace_commits[0]->n_coeffs;
-    if (!is_pow2(M) || Ntrace == 0 || number_layers > ilog2(M)) FAIL(ctx, S252_ERR_INVALID, "bad domain sizes for FRI");
+    if (!is_pow2(M) || Ntrace == 0 || rows == 0 || row0 + rows > M) FAIL(ctx, S252_ERR_INVALID, "bad domain sizes for the DEEP polynomial");
     s252::DeepParams P{};
     size_t total_cols = 0;
-    for (size_t i = 0; i < n_trace_commits; ++i) {
-        const s252_commit* tc = trace_commits[i];
-        if (tc->n_rows != M || tc->ctx != ctx) FAIL(ctx, S252_ERR_INVALID, "trace commit %zu does not share the LDE domain / context", i);
-        P.cols[i] = tc->lde; P.strides[i] = tc->n_rows; P.ncols[i] = (unsigned)tc->n_cols;
-        total_cols += tc->n_cols;
+    for (unsigned i = 0; i < T.ntables; ++i) {
+        P.cols[i] = T.cols[i]; P.strides[i] = T.strides[i]; P.ncols[i] = T.ncols[i];
+        if (i + 1 < T.ntables) total_cols += T.ncols[i];
     }
-    P.cols[n_trace_commits] = composition_commit->lde;
-    P.strides[n_trace_commits] = M;
-    P.ncols[n_trace_commits] = 2;
-    P.ntables = (unsigned)n_trace_commits + 1;
+    if (T.ncols[T.ntables - 1] != 2) FAIL(ctx, S252_ERR_INVALID, "the composition table must hold H1 and H2");
+    P.ntables = T.ntables;
     P.K = (unsigned)n_offsets;
     P.m = M;
     const unsigned K = (unsigned)n_offsets;
@@ -1230,43 +1222,100 @@ extern "C" int s252_fri_commit_phase_deep(s252_ctx* ctx, size_t number_layers, s
     const fe h = H::from_u64(coset_offset);
     fe wM;
     H::primitive_root(ilog2(M), &wM);
+    Tmp<fe> dg(ctx), dU(ctx), dV(ctx);
+    TRY(dalloc(ctx, &dg.p, gammas.size()));
+    CU(ctx, cudaMemcpyAsync(dg.p, gammas.data(), gammas.size() * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
+    P.gammas = dg.p;
+    // inverse tables over the LDE coset x_i = h w^i (whole coset: the frame offsets index it by rotation)
+    const fe* dom;
+    TRY(get_power_table(ctx, M, wM, h, &dom));
+    TRY(dalloc(ctx, &dU.p, M));
+    TRY(dalloc(ctx, &dV.p, M));
+    TRY(invert_shifted(ctx, dom, M, zz, dU.p));
+    TRY(invert_shifted(ctx, dom, M, H::sqr(zz), dV.p));
+    P.U = dU.p; P.V = dV.p;
+    P.out = out;
+    P.row0 = row0; P.rows = rows;
+    const unsigned blocks = (unsigned)((rows + s252::DEEP_THREADS - 1) / s252::DEEP_THREADS);
+    prof_begin(ctx, "deep_composition_kernel");
+    prof_work(ctx, 32.0 * rows * (total_cols + 3 + K + 1), (double)rows * (total_cols * K + 2 + 2 * (K + 1)), 0);
+#define S252_DEEP_LAUNCH(KK)                                                                   \
+    case KK:                                                                                   \
+        s252::deep_composition_kernel<KK><<<blocks, s252::DEEP_THREADS, 0, ctx->stream>>>(P);  \
+        break;
+    switch (K) {
+        S252_DEEP_LAUNCH(1)
+        S252_DEEP_LAUNCH(2)
+        S252_DEEP_LAUNCH(3)
+        S252_DEEP_LAUNCH(4)
+    }
+#undef S252_DEEP_LAUNCH
+    LAUNCH_CHECK(ctx);
+    CU(ctx, cudaStreamSynchronize(ctx->stream));   // the host vector / device temporaries stay alive until the kernel is done
+    return S252_OK;
+}
+
+// Round 4 from the resident commits: DEEP composition polynomial as evaluations on the LDE coset
+// (replaces compute_deep_composition_poly, prover.rs:410-482, and FRI layer 0's transform), then
+// fri_commit_phase (fri/mod.rs:20-72).
+extern "C" int s252_fri_commit_phase_deep(s252_ctx* ctx, size_t number_layers, s252_commit* const* trace_commits,
+                                          size_t n_trace_commits, s252_commit* composition_commit, const s252_fe* z,
+                                          const uint64_t* transition_offsets, size_t n_offsets, const s252_fe* trace_ood,
+                                          const s252_fe* h1_z2, const s252_fe* h2_z2, const s252_fe* gamma,
+                                          const s252_fe* gamma_p, const s252_fe* trace_gammas, s252_transcript* transcript,
+                                          uint64_t coset_offset, s252_fri** out, s252_fe* last_value, uint8_t* roots_out) {
+    if (!ctx || !trace_commits || !composition_commit || !z || !transition_offsets || !trace_ood || !h1_z2 || !h2_z2 || !gamma ||
+        !gamma_p || !trace_gammas || !transcript || !out || !last_value)
+        return S252_ERR_INVALID;
+    *out = nullptr;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (n_trace_commits == 0 || n_trace_commits + 1 > s252::DEEP_MAX_TABLES) FAIL(ctx, S252_ERR_INVALID, "between 1 and %d trace tables are supported", s252::DEEP_MAX_TABLES - 1);
+    if (composition_commit->n_cols != 2) FAIL(ctx, S252_ERR_INVALID, "the composition commit must hold H1 and H2");
+    const size_t M = composition_commit->n_rows, Ntrace = trace_commits[0]->n_coeffs;
+    if (!is_pow2(M) || Ntrace == 0 || number_layers > ilog2(M)) FAIL(ctx, S252_ERR_INVALID, "bad domain sizes for FRI");
+    DeepTables T{};
+    for (size_t i = 0; i < n_trace_commits; ++i) {
+        const s252_commit* tc = trace_commits[i];
+        if (tc->n_rows != M || tc->ctx != ctx) FAIL(ctx, S252_ERR_INVALID, "trace commit %zu does not share the LDE domain / context", i);
+        T.cols[i] = tc->lde; T.strides[i] = tc->n_rows; T.ncols[i] = (unsigned)tc->n_cols;
+    }
+    T.cols[n_trace_commits] = composition_commit->lde;
+    T.strides[n_trace_commits] = M;
+    T.ncols[n_trace_commits] = 2;
+    T.ntables = (unsigned)n_trace_commits + 1;
     s252_fri* f = new s252_fri();
     f->ctx = ctx; f->domain_size = M;
     int rc = [&]() -> int {
-        Tmp<fe> dg(ctx), dU(ctx), dV(ctx);
-        TRY(dalloc(ctx, &dg.p, gammas.size()));
-        CU(ctx, cudaMemcpyAsync(dg.p, gammas.data(), gammas.size() * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
-        P.gammas = dg.p;
-        // inverse tables over the LDE coset x_i = h w^i
-        const fe* dom;
-        TRY(get_power_table(ctx, M, wM, h, &dom));
-        TRY(dalloc(ctx, &dU.p, M));
-        TRY(dalloc(ctx, &dV.p, M));
-        TRY(invert_shifted(ctx, dom, M, zz, dU.p));
-        TRY(invert_shifted(ctx, dom, M, H::sqr(zz), dV.p));
-        P.U = dU.p; P.V = dV.p;
         FriLayerDev cur;
         cur.size = M;
         TRY(dalloc(ctx, &cur.evals, M));
         f->layers.push_back(cur);
-        P.out = f->layers[0].evals;
-        const unsigned blocks = (unsigned)((M + s252::DEEP_THREADS - 1) / s252::DEEP_THREADS);
-        prof_begin(ctx, "deep_composition_kernel");
-        prof_work(ctx, 32.0 * M * (total_cols + 3 + K + 1), (double)M * (total_cols * K + 2 + 2 * (K + 1)), 0);
-#define S252_DEEP_LAUNCH(KK)                                                                       \
-        case KK:                                                                                   \
-            s252::deep_composition_kernel<KK><<<blocks, s252::DEEP_THREADS, 0, ctx->stream>>>(P);  \
-            break;
-        switch (K) {
-            S252_DEEP_LAUNCH(1)
-            S252_DEEP_LAUNCH(2)
-            S252_DEEP_LAUNCH(3)
-            S252_DEEP_LAUNCH(4)
-        }
-#undef S252_DEEP_LAUNCH
-        LAUNCH_CHECK(ctx);
-        CU(ctx, cudaStreamSynchronize(ctx->stream));   // gammas.data() / dg stay alive until the kernel is done
-        return fri_from_layer0(ctx, f, number_layers, transcript, h, M, last_value, roots_out);
+        TRY(deep_evaluate_rows(ctx, T, 0, M, M, Ntrace, z, transition_offsets, n_offsets, trace_ood, h1_z2, h2_z2, gamma, gamma_p,
+                               trace_gammas, coset_offset, f->layers[0].evals));
+        return fri_from_layer0(ctx, f, number_layers, transcript, H::from_u64(coset_offset), M, last_value, roots_out);
+    }();
+    if (rc != S252_OK) { fri_free(f); return rc; }
+    *out = f;
+    return S252_OK;
+}
+// fri_commit_phase (fri/mod.rs:20-72) from layer 0 given as EVALUATIONS on the LDE coset, resident on this
+// device in the library's internal element format (e.g. the DEEP polynomial gathered from row blocks).
+extern "C" int s252_fri_commit_phase_evals(s252_ctx* ctx, size_t number_layers, const void* p0_evals, size_t domain_size,
+                                           s252_transcript* transcript, uint64_t coset_offset, s252_fri** out, s252_fe* last_value,
+                                           uint8_t* roots_out) {
+    if (!ctx || !p0_evals || !transcript || !out || !last_value) return S252_ERR_INVALID;
+    *out = nullptr;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (!is_pow2(domain_size) || number_layers > ilog2(domain_size) || coset_offset == 0) FAIL(ctx, S252_ERR_INVALID, "bad domain sizes for FRI");
+    s252_fri* f = new s252_fri();
+    f->ctx = ctx; f->domain_size = domain_size;
+    int rc = [&]() -> int {
+        FriLayerDev cur;
+        cur.size = domain_size;
+        TRY(dalloc(ctx, &cur.evals, domain_size));
+        f->layers.push_back(cur);
+        CU(ctx, cudaMemcpyAsync(f->layers[0].evals, p0_evals, domain_size * sizeof(fe), cudaMemcpyDeviceToDevice, ctx->stream));
+        return fri_from_layer0(ctx, f, number_layers, transcript, H::from_u64(coset_offset), domain_size, last_value, roots_out);
     }();
     if (rc != S252_OK) { fri_free(f); return rc; }
     *out = f;

@@ -250,6 +250,16 @@ def interpolate_and_commit_sharded(shard_table, n_rows, n_cols_total, blowup, co
     else:
         producer = iter([backend.lde(shard_table, n_rows, c_mine, blowup, coset_offset)])
 
+    return exchange_and_commit(producer, ranges, shards, m, n_cols_total, transcript, backend, group)
+
+
+def exchange_and_commit(producer, ranges, shards, m, n_cols_total, transcript, backend, group=None):
+    """The exchange + per-rank subtree + top of the tree for LDE columns produced group by group:
+    `producer` yields (handle, lde[c_group, M, 4]) for this rank's pipeline groups in order; ranges[r][g] is
+    the column range (within rank r's shard) of rank r's group g."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    rows_per = m // world
     recv = None
     handles, works = [], []
     for g, (handle, lde) in enumerate(producer):                 # lde: [c_group, M, 4], complete when yielded
@@ -284,4 +294,6 @@ def interpolate_and_commit_sharded(shard_table, n_rows, n_cols_total, blowup, co
     roots = bytes(gathered.cpu().numpy().tobytes())
     top = build_top([roots[32 * g:32 * g + 32] for g in range(world)], backend.keccak)
     transcript.append(top[0])
-    return ShardedCommit(backend, group, _LocalColumns(handles, ranges[rank]), block, top, m, n_cols_total, shards)
+    sc = ShardedCommit(backend, group, _LocalColumns(handles, ranges[rank]), block, top, m, n_cols_total, shards)
+    sc.block_tensor = recv          # [n_cols_total, rows_per, 4]: all columns, this rank's rows
+    return sc

@@ -1,0 +1,40 @@
+"""Worker for the sharded Cairo prover (launched under torch.distributed.run, one GPU per rank):
+generate_cairo_proof_sharded must return the single-GPU prover's bytes."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import lambdaworks_cairo_prover_b200 as P                                    # noqa: E402
+from lambdaworks_cairo_prover_b200 import cairo                                # noqa: E402
+from lambdaworks_cairo_prover_b200.cairo_distributed import generate_cairo_proof_sharded   # noqa: E402
+
+
+def main():
+    fib_n = int(sys.argv[1])
+    opts = P.ProofOptions(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank = dist.get_rank()
+    ctx = P.Context(local)
+    regs, mem, size = cairo.run_program(cairo.fibonacci_program(fib_n))
+    trace = cairo.build_main_trace(regs, mem, size)
+    proof = generate_cairo_proof_sharded(trace, opts, ctx)
+    if rank == 0:
+        want = cairo.generate_cairo_proof(trace, opts, ctx)
+        assert proof == want, "sharded proof differs from the single-GPU proof (%d vs %d bytes)" % (len(proof), len(want))
+    else:
+        assert proof is None
+    dist.barrier()
+    if rank == 0:
+        print("DIST_CAIRO_OK", dist.get_world_size(), trace.n_rows(), len(proof))
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -64,3 +64,19 @@ def test_sharded_commit_nccl():
     launch("nccl", world, 12, 33, 8)
     launch("nccl", 2, 10, 3, 4)
     launch("nccl", world, 12, 33, 8, groups=2)
+
+
+@pytest.mark.gpu
+def test_sharded_cairo_proof_nccl():
+    """ONE Cairo proof over 2 (and 4) GPUs == the single-GPU proof, byte for byte."""
+    import torch
+    g = torch.cuda.device_count()
+    if g < 2:
+        pytest.skip("needs at least two GPUs")
+    worker = os.path.join(ROOT, "tests", "dist_cairo_worker.py")
+    for world, args in ((2, ("100", "4", "3", "3", "1")), (4 if g >= 4 else 2, ("1000", "8", "5", "7", "6"))):
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+               "--master-addr", "127.0.0.1", "--master-port", str(free_port()), worker] + list(args)
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, OMP_NUM_THREADS="1"))
+        assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+        assert "DIST_CAIRO_OK" in res.stdout
