@@ -203,6 +203,8 @@ int s252_fri_query(s252_fri *f, const uint64_t *iotas, size_t n_queries, s252_fe
 int s252_generate_nonce_with_grinding(s252_ctx *ctx, const uint8_t challenge[32], uint8_t grinding_factor,
                                       uint64_t limit, uint64_t *nonce);
 
+/* ByteConversion::to_bytes_be for n elements on the host (the proof's wire format): out = n x 32 bytes. */
+void s252_fe_to_bytes_be(const s252_fe *in, size_t n, uint8_t *out);
 /* Keccak256 on the host (node rule of the Merkle back-ends: Keccak256(left || right)). */
 void s252_keccak256(const uint8_t *data, size_t len, uint8_t out[32]);
 

@@ -67,6 +67,7 @@ SIGNATURES = {
     "s252_fri_read_nodes": (_i, [_vp, _sz, _sz, _sz, _vp]),
     "s252_fri_query": (_i, [_vp, _vp, _sz, _vp, _vp, _vp, _vp, _sz]),
     "s252_generate_nonce_with_grinding": (_i, [_vp, _vp, _u8, _u64, C.POINTER(_u64)]),
+    "s252_fe_to_bytes_be": (None, [_vp, _sz, _vp]),
     "s252_keccak256": (None, [_vp, _sz, _vp]),
     "s252_transcript_new": (_vp, []),
     "s252_transcript_free": (None, [_vp]),
@@ -106,7 +107,7 @@ SIGNATURES = {
     "s252_cairo_trace_columns": (_vp, [_vp]),
     "s252_lde_host_columns": (_i, [_vp, _vp, _sz, _sz, _sz, _u64, C.POINTER(_vp)]),
     "s252_lde_device_columns": (_i, [_vp, _vp, _sz, _sz, _sz, _u64, C.POINTER(_vp)]),
-    "s252_cairo_aux_trace_device": (_i, [_vp, _vp, _vp, C.POINTER(_vp)]),
+    "s252_cairo_aux_trace_device": (_i, [_vp, _vp, _vp, _vp, C.POINTER(_vp)]),
     "s252_cairo_constraints_rows": (_i, [_vp, _vp, _vp, _vp, _sz, _sz, _sz, _vp, _vp, _sz, _vp, _vp, _vp, _sz, _u64, _vp]),
     "s252_cairo_composition_commit": (_i, [_vp, _vp, _sz, _sz, _u64, C.POINTER(_vp), _vp]),
     "s252_deep_rows": (_i, [_vp, _vp, _vp, _vp, _sz, _sz, _sz, _sz, _sz, _vp, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _vp]),

@@ -66,12 +66,21 @@ def _bcast_bytes(data, n, device, group):
     return bytes(t.cpu().numpy().tobytes())
 
 
-def generate_cairo_proof_sharded(trace, options, ctx, group=None, timings=None):
+def generate_cairo_proof_sharded(trace, options, ctx, group=None, timings=None, exchange="a2a"):
     """trace: the same MainTrace on every rank (lambdaworks_cairo_prover_b200.cairo).  Returns
     StarkProof::serialize() bytes on rank 0 and None on the other ranks."""
+    import time
     L = N.lib()
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     device = torch.device("cuda", ctx.device)
+    _t = [time.perf_counter()]
+
+    def mark(name):
+        if timings is not None:
+            torch.cuda.synchronize(device)
+            now = time.perf_counter()
+            timings[name] = timings.get(name, 0.0) + (now - _t[0]) * 1e3
+            _t[0] = now
     backend = D.GpuBackend(ctx)
     n, c_main = trace.n_rows(), trace.n_cols
     b, h = options.blowup_factor, options.coset_offset
@@ -92,17 +101,24 @@ def generate_cairo_proof_sharded(trace, options, ctx, group=None, timings=None):
             raise ValueError("fewer columns than ranks")
         ranges = [D.group_ranges(hi - lo, 1) for lo, hi in shards]
         lo, hi = shards[rank]
-        return D.exchange_and_commit(iter([lde_of_my_columns(lo, hi)]), ranges, shards, m, n_cols_total, t, backend, group)
+        sub = None if timings is None else timings.setdefault("commit_detail", {})
+        return D.exchange_and_commit((lde_of_my_columns(lo, hi) for _ in range(1)), ranges, shards, m, n_cols_total, t, backend, group,
+                                     exchange=exchange, timings=sub)
 
     # ---- round 1 (prover.rs:186-224)
+    aux_in = ctx.device_alloc(11 * n * 32)      # trace columns 19..29, uploaded while the main columns are exchanged and hashed
+
     def main_lde(lo, hi):
         hnd = C.c_void_p()
         ctx.check(L.s252_lde_host_columns(ctx.handle, C.c_void_p(cols_ptr + lo * n * 32), n, hi - lo, b, h, C.byref(hnd)), N.FFTError)
+        ctx.to_device_async(aux_in, cols_ptr + 19 * n * 32, 11 * n * 32)
         return _wrap_lde(ctx, hnd, device)
     sc_main = sharded_commit(c_main, main_lde)
+    mark("main_commit")
     rap = np.stack([transcript_to_field(t) for _ in range(3)])
     aux_ptr = C.c_void_p()
-    ctx.check(L.s252_cairo_aux_trace_device(ctx.handle, trace.handle, N.ptr(rap), C.byref(aux_ptr)))
+    ctx.copy_stream_wait()
+    ctx.check(L.s252_cairo_aux_trace_device(ctx.handle, trace.handle, N.ptr(rap), C.c_void_p(aux_in), C.byref(aux_ptr)))
 
     def aux_lde(lo, hi):
         hnd = C.c_void_p()
@@ -110,6 +126,8 @@ def generate_cairo_proof_sharded(trace, options, ctx, group=None, timings=None):
         return _wrap_lde(ctx, hnd, device)
     sc_aux = sharded_commit(18, aux_lde)
     ctx.device_free(aux_ptr.value)
+    ctx.device_free(aux_in)
+    mark("aux_commit")
     # ---- round 2 (prover.rs:598-640, 226-283)
     bco = np.zeros((8, 2, 4), dtype=np.uint64)
     tco = np.zeros((nt, 2, 4), dtype=np.uint64)
@@ -138,6 +156,7 @@ def generate_cairo_proof_sharded(trace, options, ctx, group=None, timings=None):
     ctx.check(L.s252_cairo_constraints_rows(ctx.handle, trace.handle, C.c_void_p(mblock.data_ptr()), C.c_void_p(ablock.data_ptr()),
                                             rows_per, rank * rows_per, rows_per, C.c_void_p(mhalo.data_ptr()), C.c_void_p(ahalo.data_ptr()),
                                             b, N.ptr(rap), N.ptr(bco), N.ptr(tco), b, h, C.c_void_p(mine.data_ptr())))
+    mark("constraints")
     if world > 1:
         dist.all_gather_into_tensor(evals.view(-1), mine.reshape(-1).clone(), group=group)
         torch.cuda.synchronize(device)
@@ -158,6 +177,7 @@ def generate_cairo_proof_sharded(trace, options, ctx, group=None, timings=None):
         dist.broadcast(comp_lde, src=0 if group is None else dist.get_global_rank(group, 0), group=group)
         torch.cuda.synchronize(device)
     t.append(comp_root)
+    mark("composition")
     # ---- round 3 (prover.rs:650-690)
     hinv = pow(h, -1, P)
     while True:                                                                  # sample_z_ood, transcript.rs:53-70
@@ -191,6 +211,7 @@ def generate_cairo_proof_sharded(trace, options, ctx, group=None, timings=None):
     for row in ood:
         for v in row:
             t.append(felt.to_bytes_be(v))
+    mark("ood")
     # ---- round 4 (prover.rs:327-404)
     gamma, gamma_p = transcript_to_field(t), transcript_to_field(t)
     tg = np.stack([transcript_to_field(t) for _ in range(2 * ncols)])
@@ -209,6 +230,7 @@ def generate_cairo_proof_sharded(trace, options, ctx, group=None, timings=None):
     if world > 1:
         dist.all_gather_into_tensor(p0.view(-1), mine.reshape(-1).clone(), group=group)
         torch.cuda.synchronize(device)
+    mark("deep")
     layers = order
     q_count = options.fri_number_of_queries if layers else 0
     iotas = np.zeros(max(q_count, 1), dtype=np.uint64)
@@ -225,13 +247,14 @@ def generate_cairo_proof_sharded(trace, options, ctx, group=None, timings=None):
         for q in range(q_count):
             iotas[q] = transcript_to_usize(t) % m
     del p0
+    mark("fri_grind")
     if world > 1:
         it = torch.from_numpy(iotas.view(np.int64)).to(device)
         dist.broadcast(it, src=0 if group is None else dist.get_global_rank(group, 0), group=group)
         iotas = it.cpu().numpy().view(np.uint64)
     idx = [int(i) for i in iotas[:q_count]]
-    main_rows, main_paths = sc_main.open(idx) if q_count else ([], [])
-    aux_rows, aux_paths = sc_aux.open(idx) if q_count else ([], [])
+    (main_rows, main_paths), (aux_rows, aux_paths) = D.open_many([sc_main, sc_aux], idx) if q_count else (([], []), ([], []))
+    mark("trace_openings")
     proof = None
     if rank == 0:
         depth = m.bit_length() - 1
@@ -245,27 +268,40 @@ def generate_cairo_proof_sharded(trace, options, ctx, group=None, timings=None):
             ia = np.array(idx, dtype=np.uint64)
             ctx.check(L.s252_fri_query(fri, N.ptr(ia), q_count, N.ptr(ev), N.ptr(evs), N.ptr(pa), N.ptr(pas), depth))
             ctx.check(L.s252_commit_open(comp.handle, N.ptr(ia), q_count, N.ptr(crow), N.ptr(cpath)))
-        fb = felt.to_bytes_be
+        bb = lambda a: felt.to_bytes_be_many(np.asarray(a).view(np.uint64).reshape(-1, 4))               # elements -> wire bytes
+        u8 = lambda v: np.frombuffer(_u64be(v), dtype=np.uint8)
+        const = lambda v: np.tile(u8(v), (q_count, 1))
         out = _u64be(n) + _u64be(2) + sc_main.root + sc_aux.root                 # StarkProof::serialize, proof/stark.rs:161-218
-        frame = _u64be(2 * ncols) + _u64be(32) + b"".join(fb(v) for row in ood for v in row) + _u64be(ncols)
-        out += _blob(frame) + comp_root + _u64be(32) + fb(hz[0]) + fb(hz[1])
-        out += _u64be(layers) + fri_roots[:layers].tobytes() + fb(last) + _u64be(q_count)
-        for q in range(q_count):
-            d = _u64be(layers) + b"".join(_path(pas[q, k, :depth - k]) for k in range(layers)) + _u64be(32)
-            d += _u64be(layers) + b"".join(fb(evs[q, k]) for k in range(layers))
-            d += _u64be(layers) + b"".join(fb(ev[q, k]) for k in range(layers))
-            d += _u64be(layers) + b"".join(_path(pa[q, k, :depth - k]) for k in range(layers))
-            out += _blob(d)
+        frame = _u64be(2 * ncols) + _u64be(32) + bb(ood).tobytes() + _u64be(ncols)
+        out += _blob(frame) + comp_root + _u64be(32) + bb(hz).tobytes()
+        out += _u64be(layers) + fri_roots[:layers].tobytes() + bb(last).tobytes() + _u64be(q_count)
+        if q_count:
+            # every query's blob has the same layout, so all of them are assembled as rows of one byte matrix
+            def path_section(paths):                                             # [Q, layers, depth, 32] -> u64(len_k) || path_k for every layer
+                offs = np.cumsum([0] + [8 + 32 * (depth - k) for k in range(layers)])
+                sec = np.empty((q_count, offs[-1]), dtype=np.uint8)
+                for k in range(layers):
+                    sec[:, offs[k]:offs[k] + 8] = u8(depth - k)
+                    sec[:, offs[k] + 8:offs[k + 1]] = paths[:, k, :depth - k].reshape(q_count, -1)
+                return sec
+            dec = np.concatenate([const(layers), path_section(pas), const(32), const(layers), bb(evs).reshape(q_count, -1),
+                                  const(layers), bb(ev).reshape(q_count, -1), const(layers), path_section(pa)], axis=1)
+            out += np.concatenate([const(dec.shape[1]), dec], axis=1).tobytes()
         out += _u64be(q_count)
-        for q in range(q_count):
-            o = _path(cpath[q]) + _u64be(32) + fb(crow[q, 0]) + fb(crow[q, 1]) + _u64be(2) + _path(main_paths[q]) + _path(aux_paths[q])
-            o += _u64be(ncols) + b"".join(fb(v) for v in np.asarray(main_rows[q]).view(np.uint64).reshape(-1, 4))
-            o += b"".join(fb(v) for v in np.asarray(aux_rows[q]).view(np.uint64).reshape(-1, 4))
-            out += _blob(o)
+        if q_count:
+            as_u8 = lambda paths: np.frombuffer(b"".join(b"".join(bytes(x) for x in p_) for p_ in paths), dtype=np.uint8).reshape(q_count, -1)
+            rows52 = np.concatenate([np.stack([np.asarray(r_).view(np.uint64).reshape(-1, 4) for r_ in main_rows]),
+                                     np.stack([np.asarray(r_).view(np.uint64).reshape(-1, 4) for r_ in aux_rows])], axis=1)
+            opn = np.concatenate([const(depth), cpath.reshape(q_count, -1), const(32), bb(crow).reshape(q_count, -1), const(2),
+                                  const(depth), as_u8(main_paths), const(depth), as_u8(aux_paths), const(ncols),
+                                  bb(rows52).reshape(q_count, -1)], axis=1)
+            out += np.concatenate([const(opn.shape[1]), opn], axis=1).tobytes()
         out += _u64be(nonce.value)
         proof = out
         L.s252_fri_destroy(fri)
         comp.free()
+    mark("serialize")
     sc_main.free()
     sc_aux.free()
+    mark("free")
     return proof

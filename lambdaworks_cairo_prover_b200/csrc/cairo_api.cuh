@@ -650,7 +650,8 @@ extern "C" int s252_lde_device_columns(s252_ctx* ctx, const void* cols, size_t n
 // build_auxiliary_trace on this device from the 11 main-trace columns it reads (pc .. off_op1, uploaded from
 // the handle's pinned column-major table): *aux_out = device buffer [18][n_rows] (internal format; free it
 // with s252_device_free).
-extern "C" int s252_cairo_aux_trace_device(s252_ctx* ctx, const s252_cairo_trace* trace, const s252_fe rap_lw[3], void** aux_out) {
+extern "C" int s252_cairo_aux_trace_device(s252_ctx* ctx, const s252_cairo_trace* trace, const s252_fe rap_lw[3], const void* prefetched,
+                                           void** aux_out) {
     if (!ctx || !trace || !rap_lw || !aux_out) return S252_ERR_INVALID;
     *aux_out = nullptr;
     CU(ctx, cudaSetDevice(ctx->device));
@@ -660,10 +661,14 @@ extern "C" int s252_cairo_aux_trace_device(s252_ctx* ctx, const s252_cairo_trace
     s252_cairo_trace_pin(trace);
     Tmp<fe> staged(ctx), cols(ctx);
     fe* aux = nullptr;
-    TRY(dalloc(ctx, &staged.p, 11 * N));
     TRY(dalloc(ctx, &cols.p, 11 * N));
-    CU(ctx, cudaMemcpyAsync(staged.p, trace->cols.data() + (size_t)s252::CAIRO_PC * N, 11 * N * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
-    TRY(convert_lw_to_internal(ctx, staged.p, cols.p, 11 * N));
+    const fe* src = reinterpret_cast<const fe*>(prefetched);
+    if (!src) {
+        TRY(dalloc(ctx, &staged.p, 11 * N));
+        CU(ctx, cudaMemcpyAsync(staged.p, trace->cols.data() + (size_t)s252::CAIRO_PC * N, 11 * N * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
+        src = staged.p;
+    }
+    TRY(convert_lw_to_internal(ctx, src, cols.p, 11 * N));
     TRY(dalloc(ctx, &aux, (size_t)s252::CAIRO_AUX_COLS * N));
     const int rc = cairo_build_aux(ctx, cols.p, s252::CAIRO_PC, N, trace->pi, rap, aux);
     if (rc != S252_OK) { dfree(ctx, aux); return rc; }

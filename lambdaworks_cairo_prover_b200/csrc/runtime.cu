@@ -1422,6 +1422,10 @@ extern "C" int s252_generate_nonce_with_grinding(s252_ctx* ctx, const uint8_t ch
 
 // --------------------------------------------------------------------------------------------
 // host Keccak-256 (a few digests: the top levels above per-GPU subtree roots)
+// ByteConversion::to_bytes_be for n elements (host): LW Montgomery -> 32-byte big-endian canonical values
+extern "C" void s252_fe_to_bytes_be(const s252_fe* in, size_t n, uint8_t* out) {
+    for (size_t i = 0; i < n; ++i) H::to_bytes_be(H::from_lw(in[i].limbs), out + 32 * i);
+}
 extern "C" void s252_keccak256(const uint8_t* data, size_t len, uint8_t out[32]) {
     H::Keccak256 k;
     k.update(data, len);

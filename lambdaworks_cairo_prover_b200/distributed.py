@@ -212,6 +212,44 @@ class ShardedCommit:
                 h.free()
 
 
+def open_many(commits, indices):
+    """ShardedCommit.open for several commits over the same row partition with ONE exchange: returns
+    [(rows, paths), ...] in the order of `commits`."""
+    first = commits[0]
+    world = dist.get_world_size(first.group)
+    rank = dist.get_rank(first.group)
+    rows_per = first.n_rows // world
+    mine = [(q, i % rows_per) for q, i in enumerate(indices) if i // rows_per == rank]
+    part = {}
+    if mine:
+        for ci, sc in enumerate(commits):
+            rows, paths = sc.backend.open_block(sc.block, [i for _, i in mine])
+            for k, (q, _) in enumerate(mine):
+                part[(ci, q)] = (np.asarray(rows[k]).copy(), [bytes(np.asarray(p).tobytes()) for p in paths[k]])
+    gathered = [None] * world
+    if world > 1:
+        dist.all_gather_object(gathered, part, group=first.group)
+    else:
+        gathered = [part]
+    merged = {}
+    for p in gathered:
+        merged.update(p)
+    out = []
+    for ci, sc in enumerate(commits):
+        out_rows, out_paths = [], []
+        for q, i in enumerate(indices):
+            rows, path = merged[(ci, q)]
+            node = (world - 1) + i // rows_per
+            while node != 0:
+                sib = node + 1 if node & 1 else node - 1
+                path = path + [sc.top[sib]]
+                node = (node - 1) >> 1
+            out_rows.append(rows)
+            out_paths.append(path)
+        out.append((out_rows, out_paths))
+    return out
+
+
 def interpolate_and_commit_sharded(shard_table, n_rows, n_cols_total, blowup, coset_offset, transcript, backend, group=None,
                                    pipeline_groups=1):
     """interpolate_and_commit (src/starks/prover.rs:126-159) for ONE trace whose columns are spread
@@ -253,20 +291,43 @@ def interpolate_and_commit_sharded(shard_table, n_rows, n_cols_total, blowup, co
     return exchange_and_commit(producer, ranges, shards, m, n_cols_total, transcript, backend, group)
 
 
-def exchange_and_commit(producer, ranges, shards, m, n_cols_total, transcript, backend, group=None):
+def exchange_and_commit(producer, ranges, shards, m, n_cols_total, transcript, backend, group=None, exchange="p2p", timings=None):
     """The exchange + per-rank subtree + top of the tree for LDE columns produced group by group:
     `producer` yields (handle, lde[c_group, M, 4]) for this rank's pipeline groups in order; ranges[r][g] is
-    the column range (within rank r's shard) of rank r's group g."""
+    the column range (within rank r's shard) of rank r's group g.
+    exchange: "p2p" = one point-to-point chunk per (column, destination), nothing packed (large tables,
+    pipelined groups); "a2a" = one packed all_to_all_single (one NCCL call instead of dozens: better when
+    the table is small and the launch latency of the chunks would dominate; single group only)."""
+    import time
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     rows_per = m // world
     recv = None
     handles, works = [], []
+    clock = [time.perf_counter()]
+
+    def mark(name):
+        if timings is not None:
+            backend.after_collective()
+            now = time.perf_counter()
+            timings[name] = timings.get(name, 0.0) + (now - clock[0]) * 1e3
+            clock[0] = now
     for g, (handle, lde) in enumerate(producer):                 # lde: [c_group, M, 4], complete when yielded
+        mark("lde")
         handles.append(handle)
         if recv is None:
             recv = torch.empty((n_cols_total, rows_per, 4), dtype=lde.dtype, device=lde.device)
         lo, hi = ranges[rank][g]
+        if exchange == "a2a":
+            if len(ranges[rank]) != 1:
+                raise ValueError("the packed all-to-all exchange takes a single pipeline group")
+            c_mine = hi - lo
+            counts = [b - a for a, b in shards]
+            send = lde.view(c_mine, world, rows_per * 4).permute(1, 0, 2).contiguous().view(world * c_mine, rows_per * 4)
+            backend.before_collective()
+            dist.all_to_all_single(recv.view(n_cols_total, rows_per * 4), send, output_split_sizes=counts,
+                                   input_split_sizes=[c_mine] * world, group=group)
+            continue
         ops = []
         for d in range(world):
             if d == rank:
@@ -286,7 +347,9 @@ def exchange_and_commit(producer, ranges, shards, m, n_cols_total, transcript, b
     for w in works:
         w.wait()
     backend.after_collective()
+    mark("exchange")
     block, sub_root = backend.commit_block(recv)
+    mark("hash")
     mine = torch.frombuffer(bytearray(sub_root), dtype=torch.uint8).to(recv.device)
     gathered = torch.empty(32 * world, dtype=torch.uint8, device=recv.device)
     dist.all_gather_into_tensor(gathered, mine, group=group)
@@ -294,6 +357,7 @@ def exchange_and_commit(producer, ranges, shards, m, n_cols_total, transcript, b
     roots = bytes(gathered.cpu().numpy().tobytes())
     top = build_top([roots[32 * g:32 * g + 32] for g in range(world)], backend.keccak)
     transcript.append(top[0])
+    mark("roots")
     sc = ShardedCommit(backend, group, _LocalColumns(handles, ranges[rank]), block, top, m, n_cols_total, shards)
     sc.block_tensor = recv          # [n_cols_total, rows_per, 4]: all columns, this rank's rows
     return sc

@@ -51,3 +51,12 @@ def zero():
 
 def one():
     return from_int(1)
+
+
+def to_bytes_be_many(a):
+    """to_bytes_be for an array of LW elements at once (native): uint64[..., 4] -> uint8[..., 32]."""
+    from . import _native as N
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    out = np.empty(a.shape[:-1] + (32,), dtype=np.uint8)
+    N.lib().s252_fe_to_bytes_be(N.ptr(a), a.size // 4, N.ptr(out))
+    return out
