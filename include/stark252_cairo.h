@@ -131,15 +131,18 @@ const s252_fe *s252_cairo_trace_columns(const s252_cairo_trace *t);
 /* compute_trace_polys + compute_lde_trace_evaluations (prover.rs:161-185) for n_cols columns given
  * column-major in (pinned) host memory / on the device; no tree. */
 int s252_lde_host_columns(s252_ctx *ctx, const s252_fe *cols_lw, size_t n_rows, size_t n_cols, size_t blowup,
-                          uint64_t coset_offset, s252_commit **out);
+                          uint64_t coset_offset, int keep_trace, s252_commit **out);
+/* The trace evaluations a handle kept (keep_trace / s252_cairo_round1): device columns [n_cols][n_coeffs], or NULL. */
+const void *s252_commit_device_trace(const s252_commit *c);
 int s252_lde_device_columns(s252_ctx *ctx, const void *cols, size_t n_rows, size_t n_cols, size_t blowup,
                             uint64_t coset_offset, s252_commit **out);
 /* build_auxiliary_trace (air.rs:660-729) on this device: *aux_out = device columns [18][n_rows]
  * (release with s252_device_free).  It reads trace columns 19..29 (pc .. off_op1): `prefetched`, if not
- * NULL, is a device copy of s252_cairo_trace_columns(t) + 19*n_rows (11*n_rows LW elements) that the
- * caller uploaded earlier (s252_copy_to_device_async + s252_copy_stream_wait); NULL uploads them here. */
+ * NULL, holds those 11 columns on the device -- either a copy of s252_cairo_trace_columns(t) + 19*n_rows
+ * (LW elements, prefetched_internal = 0) or device columns in the internal format, e.g. collected from
+ * the ranks that own them (s252_commit_device_trace, prefetched_internal = 1); NULL uploads them here. */
 int s252_cairo_aux_trace_device(s252_ctx *ctx, const s252_cairo_trace *trace, const s252_fe rap[3], const void *prefetched,
-                                void **aux_out);
+                                int prefetched_internal, void **aux_out);
 /* ConstraintEvaluator::evaluate (evaluator.rs:40-262) on LDE rows [row0, row0+rows): main_block / aux_block
  * hold those rows of every column (stride elements apart); *_halo hold the `blowup` rows that follow
  * the block (mod the domain; the frame's next row).  evals_out: device, [rows]. */

@@ -105,9 +105,10 @@ SIGNATURES = {
     "s252_cairo_round2": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _u64, _vp, C.POINTER(_vp)]),
     "s252_cairo_constraint_evaluations": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _u64, _vp]),
     "s252_cairo_trace_columns": (_vp, [_vp]),
-    "s252_lde_host_columns": (_i, [_vp, _vp, _sz, _sz, _sz, _u64, C.POINTER(_vp)]),
+    "s252_lde_host_columns": (_i, [_vp, _vp, _sz, _sz, _sz, _u64, _i, C.POINTER(_vp)]),
+    "s252_commit_device_trace": (_vp, [_vp]),
     "s252_lde_device_columns": (_i, [_vp, _vp, _sz, _sz, _sz, _u64, C.POINTER(_vp)]),
-    "s252_cairo_aux_trace_device": (_i, [_vp, _vp, _vp, _vp, C.POINTER(_vp)]),
+    "s252_cairo_aux_trace_device": (_i, [_vp, _vp, _vp, _vp, _i, C.POINTER(_vp)]),
     "s252_cairo_constraints_rows": (_i, [_vp, _vp, _vp, _vp, _sz, _sz, _sz, _vp, _vp, _sz, _vp, _vp, _vp, _sz, _u64, _vp]),
     "s252_cairo_composition_commit": (_i, [_vp, _vp, _sz, _sz, _u64, C.POINTER(_vp), _vp]),
     "s252_deep_rows": (_i, [_vp, _vp, _vp, _vp, _sz, _sz, _sz, _sz, _sz, _vp, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _vp]),

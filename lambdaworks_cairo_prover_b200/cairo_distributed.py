@@ -6,8 +6,8 @@ building blocks of include/stark252_cairo.h).  What is sharded and how:
   round 1   columns of the main trace are split over the ranks: every rank uploads, interpolates and
             extends only its columns, the exchange of distributed.py turns them into row blocks, every
             rank hashes its rows and builds that subtree, the roots are gathered.  The auxiliary trace is
-            built REDUNDANTLY on every rank (1 ms; it needs 11 main columns, which every rank uploads
-            itself) and its 18 columns are then sharded the same way.
+            built REDUNDANTLY on every rank (1 ms; the 11 main columns it needs are broadcast over NVLink
+            by the ranks that hold them) and its 18 columns are then sharded the same way.
   round 2   every rank evaluates the constraints on its row block (the frame's next row for the last
             `blowup` rows comes from the next rank: a 7 KB halo); the evaluations are all-gathered and
             rank 0 interpolates H, extends H1/H2 and commits them; root and LDE are broadcast.
@@ -106,19 +106,33 @@ def generate_cairo_proof_sharded(trace, options, ctx, group=None, timings=None, 
                                      exchange=exchange, timings=sub)
 
     # ---- round 1 (prover.rs:186-224)
-    aux_in = ctx.device_alloc(11 * n * 32)      # trace columns 19..29, uploaded while the main columns are exchanged and hashed
+    main_handle = []
 
     def main_lde(lo, hi):
         hnd = C.c_void_p()
-        ctx.check(L.s252_lde_host_columns(ctx.handle, C.c_void_p(cols_ptr + lo * n * 32), n, hi - lo, b, h, C.byref(hnd)), N.FFTError)
-        ctx.to_device_async(aux_in, cols_ptr + 19 * n * 32, 11 * n * 32)
+        ctx.check(L.s252_lde_host_columns(ctx.handle, C.c_void_p(cols_ptr + lo * n * 32), n, hi - lo, b, h, 1, C.byref(hnd)), N.FFTError)
+        main_handle.append(hnd)
         return _wrap_lde(ctx, hnd, device)
     sc_main = sharded_commit(c_main, main_lde)
     mark("main_commit")
     rap = np.stack([transcript_to_field(t) for _ in range(3)])
     aux_ptr = C.c_void_p()
-    ctx.copy_stream_wait()
-    ctx.check(L.s252_cairo_aux_trace_device(ctx.handle, trace.handle, N.ptr(rap), C.c_void_p(aux_in), C.byref(aux_ptr)))
+    # build_auxiliary_trace reads main columns 19..29: each is broadcast over NVLink by the rank that holds it on its
+    # device (uploading them from the host on every rank would multiply the PCIe traffic by the number of ranks)
+    aux_in = torch.empty((11, n, 4), dtype=torch.int64, device=device)
+    shards_main = D.column_shards(c_main, world)
+    my_lo, my_hi = shards_main[rank]
+    my_trace = _dev_tensor(L.s252_commit_device_trace(main_handle[0]), (my_hi - my_lo) * n * 4, device).view(my_hi - my_lo, n, 4)
+    if world == 1:
+        aux_in.copy_(my_trace[19:30])
+    else:
+        for col in range(19, 30):
+            owner = next(r for r, (lo, hi) in enumerate(shards_main) if lo <= col < hi)
+            if owner == rank:
+                aux_in[col - 19].copy_(my_trace[col - my_lo])
+            dist.broadcast(aux_in[col - 19], src=owner if group is None else dist.get_global_rank(group, owner), group=group)
+    torch.cuda.synchronize(device)
+    ctx.check(L.s252_cairo_aux_trace_device(ctx.handle, trace.handle, N.ptr(rap), C.c_void_p(aux_in.data_ptr()), 1, C.byref(aux_ptr)))
 
     def aux_lde(lo, hi):
         hnd = C.c_void_p()
@@ -126,7 +140,7 @@ def generate_cairo_proof_sharded(trace, options, ctx, group=None, timings=None, 
         return _wrap_lde(ctx, hnd, device)
     sc_aux = sharded_commit(18, aux_lde)
     ctx.device_free(aux_ptr.value)
-    ctx.device_free(aux_in)
+    del aux_in
     mark("aux_commit")
     # ---- round 2 (prover.rs:598-640, 226-283)
     bco = np.zeros((8, 2, 4), dtype=np.uint64)

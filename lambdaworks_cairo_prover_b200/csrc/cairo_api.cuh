@@ -628,12 +628,13 @@ extern "C" int s252_cairo_round2(s252_ctx* ctx, const s252_cairo_trace* trace, s
 extern "C" const s252_fe* s252_cairo_trace_columns(const s252_cairo_trace* t) { return t->cols.data(); }
 
 extern "C" int s252_lde_host_columns(s252_ctx* ctx, const s252_fe* cols_lw, size_t n_rows, size_t n_cols, size_t blowup,
-                                     uint64_t coset_offset, s252_commit** out) {
+                                     uint64_t coset_offset, int keep_trace, s252_commit** out) {
     if (!ctx || !cols_lw || !out) return S252_ERR_INVALID;
     *out = nullptr;
     CU(ctx, cudaSetDevice(ctx->device));
-    return commit_from_host_columns(ctx, cols_lw, n_rows, (unsigned)n_cols, blowup, coset_offset, false, out, nullptr, false);
+    return commit_from_host_columns(ctx, cols_lw, n_rows, (unsigned)n_cols, blowup, coset_offset, keep_trace != 0, out, nullptr, false);
 }
+extern "C" const void* s252_commit_device_trace(const s252_commit* c) { return c->trace; }
 extern "C" int s252_lde_device_columns(s252_ctx* ctx, const void* cols, size_t n_rows, size_t n_cols, size_t blowup,
                                        uint64_t coset_offset, s252_commit** out) {
     if (!ctx || !cols || !out) return S252_ERR_INVALID;
@@ -651,7 +652,7 @@ extern "C" int s252_lde_device_columns(s252_ctx* ctx, const void* cols, size_t n
 // the handle's pinned column-major table): *aux_out = device buffer [18][n_rows] (internal format; free it
 // with s252_device_free).
 extern "C" int s252_cairo_aux_trace_device(s252_ctx* ctx, const s252_cairo_trace* trace, const s252_fe rap_lw[3], const void* prefetched,
-                                           void** aux_out) {
+                                           int prefetched_internal, void** aux_out) {
     if (!ctx || !trace || !rap_lw || !aux_out) return S252_ERR_INVALID;
     *aux_out = nullptr;
     CU(ctx, cudaSetDevice(ctx->device));
@@ -661,16 +662,20 @@ extern "C" int s252_cairo_aux_trace_device(s252_ctx* ctx, const s252_cairo_trace
     s252_cairo_trace_pin(trace);
     Tmp<fe> staged(ctx), cols(ctx);
     fe* aux = nullptr;
-    TRY(dalloc(ctx, &cols.p, 11 * N));
     const fe* src = reinterpret_cast<const fe*>(prefetched);
-    if (!src) {
-        TRY(dalloc(ctx, &staged.p, 11 * N));
-        CU(ctx, cudaMemcpyAsync(staged.p, trace->cols.data() + (size_t)s252::CAIRO_PC * N, 11 * N * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
-        src = staged.p;
+    const fe* in_cols = src;
+    if (!src || !prefetched_internal) {
+        TRY(dalloc(ctx, &cols.p, 11 * N));
+        if (!src) {
+            TRY(dalloc(ctx, &staged.p, 11 * N));
+            CU(ctx, cudaMemcpyAsync(staged.p, trace->cols.data() + (size_t)s252::CAIRO_PC * N, 11 * N * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
+            src = staged.p;
+        }
+        TRY(convert_lw_to_internal(ctx, src, cols.p, 11 * N));
+        in_cols = cols.p;
     }
-    TRY(convert_lw_to_internal(ctx, src, cols.p, 11 * N));
     TRY(dalloc(ctx, &aux, (size_t)s252::CAIRO_AUX_COLS * N));
-    const int rc = cairo_build_aux(ctx, cols.p, s252::CAIRO_PC, N, trace->pi, rap, aux);
+    const int rc = cairo_build_aux(ctx, in_cols, s252::CAIRO_PC, N, trace->pi, rap, aux);
     if (rc != S252_OK) { dfree(ctx, aux); return rc; }
     *aux_out = aux;
     return S252_OK;
