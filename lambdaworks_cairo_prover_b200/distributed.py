@@ -251,7 +251,7 @@ def open_many(commits, indices):
 
 
 def interpolate_and_commit_sharded(shard_table, n_rows, n_cols_total, blowup, coset_offset, transcript, backend, group=None,
-                                   pipeline_groups=1):
+                                   pipeline_groups=1, exchange="p2p"):
     """interpolate_and_commit (src/starks/prover.rs:126-159) for ONE trace whose columns are spread
     over the ranks of `group`.  shard_table: this rank's columns as a row-major table
     (n_rows x c_rank, i.e. TraceTable::get_cols, src/starks/trace.rs:31-43) -- or a LIST of such
@@ -288,7 +288,7 @@ def interpolate_and_commit_sharded(shard_table, n_rows, n_cols_total, blowup, co
     else:
         producer = iter([backend.lde(shard_table, n_rows, c_mine, blowup, coset_offset)])
 
-    return exchange_and_commit(producer, ranges, shards, m, n_cols_total, transcript, backend, group)
+    return exchange_and_commit(producer, ranges, shards, m, n_cols_total, transcript, backend, group, exchange=exchange)
 
 
 def exchange_and_commit(producer, ranges, shards, m, n_cols_total, transcript, backend, group=None, exchange="p2p", timings=None):

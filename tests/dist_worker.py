@@ -65,13 +65,14 @@ def main():
         backend = D.GpuBackend(ctx)
         transcript = P.DefaultTranscript()
     groups = int(sys.argv[5]) if len(sys.argv) > 5 else 1
+    exchange = sys.argv[6] if len(sys.argv) > 6 else "p2p"
     if groups > 1:
         tables = [np.ascontiguousarray(shard[:, lo:hi]) for lo, hi in D.group_ranges(b - a, groups)]
         if mode == "nccl":
             tables = [torch.from_numpy(t.view(np.int64)).pin_memory() for t in tables]
         sc = D.interpolate_and_commit_sharded(tables, n, n_cols, blowup, 3, transcript, backend)
     else:
-        sc = D.interpolate_and_commit_sharded(shard.reshape(-1, 4), n, n_cols, blowup, 3, transcript, backend)
+        sc = D.interpolate_and_commit_sharded(shard.reshape(-1, 4), n, n_cols, blowup, 3, transcript, backend, exchange=exchange)
     # single-process answer
     want = O.interpolate_and_commit(trace, blowup, 3, threads=4)
     assert sc.root == want["root"], "rank %d: root differs" % rank
@@ -85,6 +86,11 @@ def main():
         assert (np.asarray(rows[q]).view(np.uint64) == want["lde"][:, i]).all(), (rank, i)
         assert [bytes(p) for p in paths[q]] == [bytes(x) for x in O.merkle_path(want["nodes"], i)], (rank, i)
         assert O.merkle_verify(sc.root, i, np.asarray(rows[q]).view(np.uint64), paths[q])
+    # several commits opened with one exchange (the sharded Cairo prover opens the main and the aux table together)
+    (rows2, paths2), (rows3, paths3) = D.open_many([sc, sc], idx)
+    for q in range(len(idx)):
+        assert (np.asarray(rows2[q]) == np.asarray(rows[q])).all() and (np.asarray(rows3[q]) == np.asarray(rows[q])).all()
+        assert [bytes(p) for p in paths2[q]] == [bytes(p) for p in paths[q]] == [bytes(p) for p in paths3[q]]
     if mode == "nccl":
         # this rank's columns: coefficients and LDE are bit-exact too
         for j in range(b - a):

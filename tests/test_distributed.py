@@ -21,10 +21,10 @@ def free_port():
     return p
 
 
-def launch(mode, world, logn, n_cols, blowup, groups=1, timeout=600):
+def launch(mode, world, logn, n_cols, blowup, groups=1, exchange="p2p", timeout=600):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(free_port()), WORKER, mode, str(logn), str(n_cols), str(blowup),
-           str(groups)]
+           str(groups), exchange]
     env = dict(os.environ, OMP_NUM_THREADS="1")
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
@@ -54,6 +54,11 @@ def test_sharded_commit_gloo(world, logn, n_cols, blowup, groups):
     launch("gloo", world, logn, n_cols, blowup, groups)
 
 
+def test_sharded_commit_gloo_packed_all_to_all():
+    launch("gloo", 2, 5, 7, 4, 1, "a2a")
+    launch("gloo", 4, 4, 9, 2, 1, "a2a")
+
+
 @pytest.mark.gpu
 def test_sharded_commit_nccl():
     import torch
@@ -64,6 +69,7 @@ def test_sharded_commit_nccl():
     launch("nccl", world, 12, 33, 8)
     launch("nccl", 2, 10, 3, 4)
     launch("nccl", world, 12, 33, 8, groups=2)
+    launch("nccl", world, 11, 18, 4, exchange="a2a")
 
 
 @pytest.mark.gpu
