@@ -3,6 +3,7 @@
 #pragma once
 #include "../../include/stark252_cairo.h"
 #include "cairo_host.hpp"
+#include <chrono>
 
 namespace CA = s252::cairo;
 
@@ -20,8 +21,11 @@ struct s252_cairo_trace {
     mutable bool pinned = false;  // `cols` pages registered with the CUDA driver (true DMA for the upload of round 1)
     void make_columns() {
         cols.resize(table.size());
-        for (size_t i = 0; i < n_rows; ++i)
-            for (size_t j = 0; j < n_cols; ++j) cols[j * n_rows + i] = table[i * n_cols + j];
+        CA::parallel_for(n_rows, [&](size_t lo, size_t hi, unsigned) {
+            for (size_t i0 = lo; i0 < hi; i0 += 64)          // 64-row blocks: the strided writes stay within a few pages per column
+                for (size_t j = 0; j < n_cols; ++j)
+                    for (size_t i = i0; i < std::min(hi, i0 + 64); ++i) cols[j * n_rows + i] = table[i * n_cols + j];
+        });
     }
     ~s252_cairo_trace() { if (pinned) cudaHostUnregister((void*)cols.data()); }
 };
@@ -71,10 +75,19 @@ extern "C" void s252_cairo_run_memory_bytes(const s252_cairo_run* run, uint8_t* 
 static int cairo_build_common(bool full, const uint8_t* trace_le, size_t trace_len, const uint8_t* memory_le, size_t memory_len,
                               size_t program_size, const uint64_t* rc_range, const uint64_t* output_range, s252_cairo_trace** out) {
     if (!trace_le || !memory_le || !out) CAIRO_FAIL(S252_ERR_INVALID, "null argument");
+    const bool timing = std::getenv("S252_TIMING") != nullptr;
+    auto t_prev = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        const auto t_now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[s252 front-end] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t_now - t_prev).count());
+        t_prev = t_now;
+    };
     std::vector<CA::RegisterState> regs;
     CA::Memory mem;
     if (!CA::parse_trace_le(trace_le, trace_len, &regs)) CAIRO_FAIL(S252_ERR_INVALID, "IncorrectNumberOfBytes (register trace)");
     if (!CA::parse_memory_le(memory_le, memory_len, &mem)) CAIRO_FAIL(S252_ERR_INVALID, "IncorrectNumberOfBytes (memory)");
+    lap("parse trace + memory files");
     s252_cairo_trace* t = nullptr;
     try {
         t = new s252_cairo_trace();
@@ -82,6 +95,7 @@ static int cairo_build_common(bool full, const uint8_t* trace_le, size_t trace_l
         CA::Table tab;
         bool ok = CA::public_inputs_from_regs_and_mem(regs, mem, program_size, rc_range, output_range, &t->pi, &err);
         if (ok) ok = full ? CA::build_main_trace(regs, mem, &t->pi, &tab, &err) : CA::build_cairo_execution_trace(regs, mem, t->pi, &tab, &err);
+        lap("build_main_trace");
         if (!ok) {
             delete t;
             CAIRO_FAIL(S252_ERR_INVALID, "build_main_trace: " + err);
@@ -89,8 +103,12 @@ static int cairo_build_common(bool full, const uint8_t* trace_le, size_t trace_l
         t->n_cols = tab.n_cols;
         t->n_rows = tab.n_rows();
         t->table.resize(tab.t.size());
-        for (size_t i = 0; i < tab.t.size(); ++i) H::to_lw(tab.t[i], t->table[i].limbs);
+        CA::parallel_for(tab.t.size(), [&](size_t lo, size_t hi, unsigned) {
+            for (size_t i = lo; i < hi; ++i) H::to_lw(tab.t[i], t->table[i].limbs);
+        });
+        lap("table in the LW layout");
         t->make_columns();
+        lap("column-major copy");
     } catch (const std::exception& e) {
         delete t;
         CAIRO_FAIL(S252_ERR_INVALID, std::string("build_main_trace: ") + e.what());

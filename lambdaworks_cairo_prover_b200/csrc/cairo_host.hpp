@@ -16,6 +16,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -25,6 +26,19 @@ namespace s252 {
 namespace cairo {
 
 namespace H = s252::host;
+
+// fn(lo, hi, worker) over [0, n) on the host's cores (the front-end is outside the prover's timed region, but a
+// 2^19-row trace is 18 M field elements: the row loop, the format conversion and the transposition are threaded)
+template <typename F>
+inline void parallel_for(size_t n, F fn) {
+    unsigned nt = std::thread::hardware_concurrency();
+    if (nt == 0) nt = 1;
+    if (nt > 32) nt = 32;
+    if (n < 4096 || nt == 1) { fn((size_t)0, n, 0u); return; }
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t) th.emplace_back([=] { fn(n * t / nt, n * (t + 1) / nt, t); });
+    for (auto& x : th) x.join();
+}
 
 // Column indices of the main trace (src/cairo/air.rs:74-125)
 enum : unsigned {
@@ -294,13 +308,18 @@ inline bool build_cairo_execution_trace(const std::vector<RegisterState>& regs, 
     }
     out->t.assign(n * cols, fe_zero());
     const fe one = H::one();
-    std::vector<size_t> jnz_rows;   // rows whose res is dst^-1: inverted together after the loop
-    for (size_t i = 0; i < n; ++i) {
+    std::vector<std::vector<size_t>> jnz_parts(64);   // rows whose res is dst^-1: inverted together after the loop
+    std::vector<std::string> errs(64);
+    parallel_for(n, [&](size_t lo_, size_t hi_, unsigned worker) {
+    std::vector<size_t>& jnz_rows = jnz_parts[worker];
+    std::string* err = &errs[worker];
+    auto fail = [&](const char* m) { *err = m; };
+    for (size_t i = lo_; i < hi_; ++i) {
         const RegisterState& s = regs[i];
         const fe* instp = mem.get(s.pc);
-        if (!instp) { *err = "InstructionNotFound"; return false; }
+        if (!instp) { fail("InstructionNotFound"); return; }
         Instr in;
-        if (!decode(*instp, &in, err)) return false;
+        if (!decode(*instp, &in, err)) return;
         fe* r = out->row(i);
         for (unsigned b = 0; b < 15; ++b) r[b] = in.bit(b) ? one : fe_zero();
         auto addr_of = [&](uint64_t base, int32_t off, uint64_t* a) -> bool {   // checked_add_signed().unwrap()
@@ -310,10 +329,10 @@ inline bool build_cairo_execution_trace(const std::vector<RegisterState>& regs, 
         };
         uint64_t dst_addr, op0_addr, op1_addr;
         if (!addr_of(in.bit(F_DST_FP) ? s.fp : s.ap, in.soff[0], &dst_addr) || !addr_of(in.bit(F_OP_0_FP) ? s.fp : s.ap, in.soff[1], &op0_addr)) {
-            *err = "address underflow"; return false;
+            fail("address underflow"); return;
         }
         const fe *dstp = mem.get(dst_addr), *op0p = mem.get(op0_addr);
-        if (!dstp || !op0p) { *err = "operand cell missing from memory"; return false; }
+        if (!dstp || !op0p) { fail("operand cell missing from memory"); return; }
         fe dst = *dstp, op0 = *op0p;
         uint64_t op1_base;
         switch (in.op1_src()) {
@@ -322,14 +341,14 @@ inline bool build_cairo_execution_trace(const std::vector<RegisterState>& regs, 
             case 2: op1_base = s.fp; break;
             default: op1_base = s.ap; break;
         }
-        if (!addr_of(op1_base, in.soff[2], &op1_addr)) { *err = "address underflow"; return false; }
+        if (!addr_of(op1_base, in.soff[2], &op1_addr)) { fail("address underflow"); return; }
         const fe* op1p = mem.get(op1_addr);
-        if (!op1p) { *err = "operand cell missing from memory"; return false; }
+        if (!op1p) { fail("operand cell missing from memory"); return; }
         const fe op1 = *op1p;
         // compute_res (execution_trace.rs:381-440)
         fe res;
         if (in.pc_update() == 4) {
-            if (!(in.res_logic() == 0 && in.opcode() == 0)) { *err = "Undefined Behavior"; return false; }
+            if (!(in.res_logic() == 0 && in.opcode() == 0)) { fail("Undefined Behavior"); return; }
             res = dst;                                   // dst == 0 ? dst : dst.inv()  (the inversion is batched below)
             if (!H::is_zero(dst)) jnz_rows.push_back(i);
         } else {
@@ -349,6 +368,10 @@ inline bool build_cairo_execution_trace(const std::vector<RegisterState>& regs, 
         r[FRAME_MUL] = H::mul(op0, op1);
         r[FRAME_SELECTOR] = (i + 1 == n) ? fe_zero() : one;
     }
+    });
+    for (auto& e : errs) if (!e.empty()) { *err = e; return false; }
+    std::vector<size_t> jnz_rows;
+    for (auto& part : jnz_parts) jnz_rows.insert(jnz_rows.end(), part.begin(), part.end());
     if (!jnz_rows.empty()) {   // one field inversion for all jnz rows (Montgomery's trick); t1 = t0 * res follows
         std::vector<fe> pre(jnz_rows.size());
         fe acc = one;
