@@ -60,6 +60,143 @@ def _blob(b):
     return _u64be(len(b)) + b
 
 
+class GpuCairoBackend(D.GpuBackend):
+    """The compute steps of the sharded prover on this rank's GPU, through the C ABI.  Tensors hold field
+    elements in the library's internal format; everything that crosses to the host (roots, challenges,
+    out-of-domain values, opened rows) is in the reference's LW layout.  tests/dist_cairo_worker.py has a
+    CPU double of this class on the oracle, so that the orchestration below is covered by gloo tests."""
+
+    def __init__(self, ctx):
+        super().__init__(ctx)
+        self.L = N.lib()
+
+    def sync(self):
+        torch.cuda.synchronize(self.device)
+
+    # ---- transcript (host)
+    def transcript(self):
+        return DefaultTranscript()
+
+    def to_field(self, t):
+        return transcript_to_field(t)
+
+    def to_usize(self, t):
+        return transcript_to_usize(t)
+
+    # ---- round 1
+    def main_lde(self, trace, lo, hi, opts):
+        """Upload + interpolate + extend main-trace columns [lo, hi): -> (handle, lde[c, M, 4], trace[c, N, 4])."""
+        ctx, L, n = self.ctx, self.L, trace.n_rows()
+        L.s252_cairo_trace_pin(trace.handle)
+        cols_ptr = L.s252_cairo_trace_columns(trace.handle)
+        hnd = C.c_void_p()
+        ctx.check(L.s252_lde_host_columns(ctx.handle, C.c_void_p(cols_ptr + lo * n * 32), n, hi - lo, opts.blowup_factor, opts.coset_offset,
+                                          1, C.byref(hnd)), N.FFTError)
+        commit, lde = _wrap_lde(ctx, hnd, self.device)
+        tr = _dev_tensor(L.s252_commit_device_trace(hnd), (hi - lo) * n * 4, self.device).view(hi - lo, n, 4)
+        return commit, lde, tr
+
+    def new_tensor(self, shape):
+        return torch.empty(shape, dtype=torch.int64, device=self.device)
+
+    def aux_trace(self, trace, aux_in, rap):
+        """build_auxiliary_trace from trace columns 19..29 (aux_in[11, N, 4]) -> aux columns [18, N, 4]."""
+        ctx, L, n = self.ctx, self.L, trace.n_rows()
+        aux_ptr = C.c_void_p()
+        ctx.check(L.s252_cairo_aux_trace_device(ctx.handle, trace.handle, N.ptr(rap), C.c_void_p(aux_in.data_ptr()), 1, C.byref(aux_ptr)))
+        t = _dev_tensor(aux_ptr.value, 18 * n * 4, self.device).view(18, n, 4)
+        t._s252_ptr = aux_ptr.value
+        return t
+
+    def free_tensor(self, t):
+        if getattr(t, "_s252_ptr", None):
+            self.ctx.device_free(t._s252_ptr)
+
+    def cols_lde(self, cols, opts):
+        """Interpolate + extend device columns [c, N, 4] -> (handle, lde[c, M, 4])."""
+        ctx, L = self.ctx, self.L
+        hnd = C.c_void_p()
+        ctx.check(L.s252_lde_device_columns(ctx.handle, C.c_void_p(cols.data_ptr()), cols.shape[1], cols.shape[0], opts.blowup_factor,
+                                            opts.coset_offset, C.byref(hnd)), N.FFTError)
+        return _wrap_lde(ctx, hnd, self.device)
+
+    def evaluate_at(self, handle, points):
+        """poly.evaluate(point) for every polynomial of a handle: -> uint64[n_points, n_cols, 4]."""
+        o = np.empty((len(points), handle.n_cols, 4), dtype=np.uint64)
+        self.ctx.check(self.L.s252_commit_evaluate_at(handle.handle, N.ptr(points), len(points), N.ptr(o), handle.n_cols, 0))
+        return o
+
+    # ---- round 2
+    def constraints_rows(self, trace, mblock, ablock, mhalo, ahalo, row0, rap, bco, tco, opts, out):
+        rows, b = mblock.shape[1], opts.blowup_factor
+        self.ctx.check(self.L.s252_cairo_constraints_rows(
+            self.ctx.handle, trace.handle, C.c_void_p(mblock.data_ptr()), C.c_void_p(ablock.data_ptr()), rows, row0, rows,
+            C.c_void_p(mhalo.data_ptr()), C.c_void_p(ahalo.data_ptr()), b, N.ptr(rap), N.ptr(bco), N.ptr(tco), b, opts.coset_offset,
+            C.c_void_p(out.data_ptr())))
+
+    def composition_commit(self, evals, n, opts, comp_lde_out):
+        """H from its evaluations, H1/H2 LDE + tree: -> (handle, root); the LDE [2, M, 4] is copied into comp_lde_out."""
+        ctx, L = self.ctx, self.L
+        hnd = C.c_void_p()
+        root = np.empty(32, dtype=np.uint8)
+        ctx.check(L.s252_cairo_composition_commit(ctx.handle, C.c_void_p(evals.data_ptr()), n, opts.blowup_factor, opts.coset_offset,
+                                                  C.byref(hnd), N.ptr(root)))
+        comp = DeviceCommit(ctx, hnd, root.tobytes())
+        m = n * opts.blowup_factor
+        comp_lde_out.copy_(_dev_tensor(L.s252_commit_device_lde(hnd), 2 * m * 4, self.device).view(2, m, 4))
+        return comp, root.tobytes()
+
+    # ---- round 4
+    def deep_rows(self, mblock, ablock, comp_lde, row0, n, z, ood, hz, gamma, gamma_p, tg, opts, out):
+        rows, m = mblock.shape[1], comp_lde.shape[1]
+        cblock = comp_lde[:, row0:row0 + rows]                                    # stride m
+        tables = (C.c_void_p * 3)(mblock.data_ptr(), ablock.data_ptr(), cblock.data_ptr())
+        strides = (C.c_size_t * 3)(rows, rows, m)
+        ncs = (C.c_size_t * 3)(mblock.shape[0], ablock.shape[0], 2)
+        offs = np.array([0, 1], dtype=np.uint64)
+        ood_flat = np.ascontiguousarray(ood.reshape(-1, 4))
+        self.ctx.check(self.L.s252_deep_rows(self.ctx.handle, tables, strides, ncs, 3, row0, rows, m, n, N.ptr(felt.from_int(z)), N.ptr(offs), 2,
+                                             N.ptr(ood_flat), N.ptr(np.ascontiguousarray(hz[0])), N.ptr(np.ascontiguousarray(hz[1])),
+                                             N.ptr(gamma), N.ptr(gamma_p), N.ptr(tg), opts.coset_offset, C.c_void_p(out.data_ptr())))
+
+    def fri_commit_phase_evals(self, p0, layers, t, opts):
+        """-> (fri handle, last value LW, roots uint8[layers, 32])"""
+        fri = C.c_void_p()
+        last = np.empty(4, dtype=np.uint64)
+        roots = np.empty((max(layers, 1), 32), dtype=np.uint8)
+        self.ctx.check(self.L.s252_fri_commit_phase_evals(self.ctx.handle, layers, C.c_void_p(p0.data_ptr()), p0.shape[0], t.handle,
+                                                          opts.coset_offset, C.byref(fri), N.ptr(last), N.ptr(roots)))
+        return fri, last, roots[:layers]
+
+    def grind(self, challenge, factor):
+        nonce = C.c_uint64()
+        ch = np.frombuffer(challenge, dtype=np.uint8).copy()
+        self.ctx.check(self.L.s252_generate_nonce_with_grinding(self.ctx.handle, N.ptr(ch), factor, 0, C.byref(nonce)))
+        return int(nonce.value)
+
+    def fri_query(self, fri, idx, layers, depth):
+        q = len(idx)
+        ev = np.empty((q, layers, 4), dtype=np.uint64)
+        evs = np.empty_like(ev)
+        pa = np.empty((q, layers, depth, 32), dtype=np.uint8)
+        pas = np.empty_like(pa)
+        ia = np.array(idx, dtype=np.uint64)
+        self.ctx.check(self.L.s252_fri_query(fri, N.ptr(ia), q, N.ptr(ev), N.ptr(evs), N.ptr(pa), N.ptr(pas), depth))
+        return ev, evs, pa, pas
+
+    def commit_open(self, comp, idx, depth):
+        q = len(idx)
+        rows = np.empty((q, 2, 4), dtype=np.uint64)
+        paths = np.empty((q, depth, 32), dtype=np.uint8)
+        ia = np.array(idx, dtype=np.uint64)
+        self.ctx.check(self.L.s252_commit_open(comp.handle, N.ptr(ia), q, N.ptr(rows), N.ptr(paths)))
+        return rows, paths
+
+    def release(self, fri, comp):
+        self.L.s252_fri_destroy(fri)
+        comp.free()
+
+
 def _bcast_bytes(data, n, device, group):
     t = torch.frombuffer(bytearray(data if data is not None else bytes(n)), dtype=torch.uint8).to(device)
     dist.broadcast(t, src=0 if group is None else dist.get_global_rank(group, 0), group=group)
@@ -67,21 +204,22 @@ def _bcast_bytes(data, n, device, group):
 
 
 def generate_cairo_proof_sharded(trace, options, ctx, group=None, timings=None, exchange="a2a"):
-    """trace: the same MainTrace on every rank (lambdaworks_cairo_prover_b200.cairo).  Returns
-    StarkProof::serialize() bytes on rank 0 and None on the other ranks."""
+    """trace: the same MainTrace on every rank (lambdaworks_cairo_prover_b200.cairo); ctx: this rank's Context (or a
+    backend object with GpuCairoBackend's interface).  Returns StarkProof::serialize() bytes on rank 0 and
+    None on the other ranks."""
     import time
-    L = N.lib()
+    be = ctx if hasattr(ctx, "main_lde") else GpuCairoBackend(ctx)
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    device = torch.device("cuda", ctx.device)
+    device = be.device
+    gr = (lambda r: r) if group is None else (lambda r: dist.get_global_rank(group, r))
     _t = [time.perf_counter()]
 
     def mark(name):
         if timings is not None:
-            torch.cuda.synchronize(device)
+            be.sync()
             now = time.perf_counter()
             timings[name] = timings.get(name, 0.0) + (now - _t[0]) * 1e3
             _t[0] = now
-    backend = D.GpuBackend(ctx)
     n, c_main = trace.n_rows(), trace.n_cols
     b, h = options.blowup_factor, options.coset_offset
     m = n * b
@@ -91,9 +229,7 @@ def generate_cairo_proof_sharded(trace, options, ctx, group=None, timings=None, 
     order = n.bit_length() - 1
     g = pow(_TWO_ADIC_ROOT, 1 << (192 - order), P)
     nt = 50 if c_main > 34 else 49
-    t = DefaultTranscript()
-    L.s252_cairo_trace_pin(trace.handle)
-    cols_ptr = L.s252_cairo_trace_columns(trace.handle)
+    t = be.transcript()
 
     def sharded_commit(n_cols_total, lde_of_my_columns):
         shards = D.column_shards(n_cols_total, world)
@@ -102,116 +238,96 @@ def generate_cairo_proof_sharded(trace, options, ctx, group=None, timings=None, 
         ranges = [D.group_ranges(hi - lo, 1) for lo, hi in shards]
         lo, hi = shards[rank]
         sub = None if timings is None else timings.setdefault("commit_detail", {})
-        return D.exchange_and_commit((lde_of_my_columns(lo, hi) for _ in range(1)), ranges, shards, m, n_cols_total, t, backend, group,
+        return D.exchange_and_commit((lde_of_my_columns(lo, hi) for _ in range(1)), ranges, shards, m, n_cols_total, t, be, group,
                                      exchange=exchange, timings=sub)
 
     # ---- round 1 (prover.rs:186-224)
-    main_handle = []
+    kept = {}
 
     def main_lde(lo, hi):
-        hnd = C.c_void_p()
-        ctx.check(L.s252_lde_host_columns(ctx.handle, C.c_void_p(cols_ptr + lo * n * 32), n, hi - lo, b, h, 1, C.byref(hnd)), N.FFTError)
-        main_handle.append(hnd)
-        return _wrap_lde(ctx, hnd, device)
+        handle, lde, tr = be.main_lde(trace, lo, hi, options)
+        kept["trace"] = tr
+        return handle, lde
     sc_main = sharded_commit(c_main, main_lde)
     mark("main_commit")
-    rap = np.stack([transcript_to_field(t) for _ in range(3)])
-    aux_ptr = C.c_void_p()
+    rap = np.stack([be.to_field(t) for _ in range(3)])
     # build_auxiliary_trace reads main columns 19..29: each is broadcast over NVLink by the rank that holds it on its
     # device (uploading them from the host on every rank would multiply the PCIe traffic by the number of ranks)
-    aux_in = torch.empty((11, n, 4), dtype=torch.int64, device=device)
+    aux_in = be.new_tensor((11, n, 4))
     shards_main = D.column_shards(c_main, world)
     my_lo, my_hi = shards_main[rank]
-    my_trace = _dev_tensor(L.s252_commit_device_trace(main_handle[0]), (my_hi - my_lo) * n * 4, device).view(my_hi - my_lo, n, 4)
-    if world == 1:
-        aux_in.copy_(my_trace[19:30])
-    else:
-        for col in range(19, 30):
-            owner = next(r for r, (lo, hi) in enumerate(shards_main) if lo <= col < hi)
-            if owner == rank:
-                aux_in[col - 19].copy_(my_trace[col - my_lo])
-            dist.broadcast(aux_in[col - 19], src=owner if group is None else dist.get_global_rank(group, owner), group=group)
-    torch.cuda.synchronize(device)
-    ctx.check(L.s252_cairo_aux_trace_device(ctx.handle, trace.handle, N.ptr(rap), C.c_void_p(aux_in.data_ptr()), 1, C.byref(aux_ptr)))
+    my_trace = kept["trace"]
+    for col in range(19, 30):
+        owner = next(r for r, (lo, hi) in enumerate(shards_main) if lo <= col < hi)
+        if owner == rank:
+            aux_in[col - 19].copy_(my_trace[col - my_lo])
+        if world > 1:
+            dist.broadcast(aux_in[col - 19], src=gr(owner), group=group)
+    be.sync()
+    aux_cols = be.aux_trace(trace, aux_in, rap)
 
     def aux_lde(lo, hi):
-        hnd = C.c_void_p()
-        ctx.check(L.s252_lde_device_columns(ctx.handle, C.c_void_p(aux_ptr.value + lo * n * 32), n, hi - lo, b, h, C.byref(hnd)), N.FFTError)
-        return _wrap_lde(ctx, hnd, device)
+        return be.cols_lde(aux_cols[lo:hi], options)
     sc_aux = sharded_commit(18, aux_lde)
-    ctx.device_free(aux_ptr.value)
-    del aux_in
+    be.free_tensor(aux_cols)
+    del aux_in, aux_cols
     mark("aux_commit")
     # ---- round 2 (prover.rs:598-640, 226-283)
     bco = np.zeros((8, 2, 4), dtype=np.uint64)
     tco = np.zeros((nt, 2, 4), dtype=np.uint64)
     for j in range(2):
         for k in range(8):
-            bco[k, j] = transcript_to_field(t)
+            bco[k, j] = be.to_field(t)
     for j in range(2):
         for k in range(nt):
-            tco[k, j] = transcript_to_field(t)
+            tco[k, j] = be.to_field(t)
     mblock, ablock = sc_main.block_tensor, sc_aux.block_tensor                  # [cols, rows_per, 4]
-    mhalo = torch.empty((c_main, b, 4), dtype=mblock.dtype, device=device)
-    ahalo = torch.empty((18, b, 4), dtype=mblock.dtype, device=device)
+    mhalo = be.new_tensor((c_main, b, 4))
+    ahalo = be.new_tensor((18, b, 4))
     if world == 1:
         mhalo.copy_(mblock[:, :b])
         ahalo.copy_(ablock[:, :b])
     else:
-        gr = (lambda r: r) if group is None else (lambda r: dist.get_global_rank(group, r))
         nxt, prv = gr((rank + 1) % world), gr((rank - 1) % world)
         msend, asend = mblock[:, :b].contiguous(), ablock[:, :b].contiguous()
         for w_ in dist.batch_isend_irecv([dist.P2POp(dist.isend, msend, prv, group), dist.P2POp(dist.isend, asend, prv, group),
                                           dist.P2POp(dist.irecv, mhalo, nxt, group), dist.P2POp(dist.irecv, ahalo, nxt, group)]):
             w_.wait()
-    torch.cuda.synchronize(device)
-    evals = torch.empty((m, 4), dtype=mblock.dtype, device=device)
+    be.sync()
+    evals = be.new_tensor((m, 4))
     mine = evals[rank * rows_per:(rank + 1) * rows_per]
-    ctx.check(L.s252_cairo_constraints_rows(ctx.handle, trace.handle, C.c_void_p(mblock.data_ptr()), C.c_void_p(ablock.data_ptr()),
-                                            rows_per, rank * rows_per, rows_per, C.c_void_p(mhalo.data_ptr()), C.c_void_p(ahalo.data_ptr()),
-                                            b, N.ptr(rap), N.ptr(bco), N.ptr(tco), b, h, C.c_void_p(mine.data_ptr())))
+    be.constraints_rows(trace, mblock, ablock, mhalo, ahalo, rank * rows_per, rap, bco, tco, options, mine)
     mark("constraints")
     if world > 1:
         dist.all_gather_into_tensor(evals.view(-1), mine.reshape(-1).clone(), group=group)
-        torch.cuda.synchronize(device)
+        be.sync()
     comp = None
-    comp_lde = torch.empty((2, m, 4), dtype=mblock.dtype, device=device)
+    comp_lde = be.new_tensor((2, m, 4))
     comp_root = None
     if rank == 0:
-        hnd = C.c_void_p()
-        root = np.empty(32, dtype=np.uint8)
-        ctx.check(L.s252_cairo_composition_commit(ctx.handle, C.c_void_p(evals.data_ptr()), n, b, h, C.byref(hnd), N.ptr(root)))
-        comp = DeviceCommit(ctx, hnd, root.tobytes())
-        comp_root = root.tobytes()
-        comp_lde.copy_(_dev_tensor(L.s252_commit_device_lde(hnd), 2 * m * 4, device).view(2, m, 4))
-        torch.cuda.synchronize(device)
+        comp, comp_root = be.composition_commit(evals, n, options, comp_lde)
+        be.sync()
     del evals
     if world > 1:
         comp_root = _bcast_bytes(comp_root, 32, device, group)
-        dist.broadcast(comp_lde, src=0 if group is None else dist.get_global_rank(group, 0), group=group)
-        torch.cuda.synchronize(device)
+        dist.broadcast(comp_lde, src=gr(0), group=group)
+        be.sync()
     t.append(comp_root)
     mark("composition")
     # ---- round 3 (prover.rs:650-690)
     hinv = pow(h, -1, P)
     while True:                                                                  # sample_z_ood, transcript.rs:53-70
-        z = felt.to_int(transcript_to_field(t))
+        z = felt.to_int(be.to_field(t))
         if pow(z * hinv % P, m, P) != 1 and pow(z, n, P) != 1:
             break
     pts = felt.from_ints([z, z * g % P])
 
     def local_ood(local):
-        outs = []
-        for hnd in local.handles:
-            o = np.empty((2, hnd.n_cols, 4), dtype=np.uint64)
-            ctx.check(L.s252_commit_evaluate_at(hnd.handle, N.ptr(pts), 2, N.ptr(o), hnd.n_cols, 0))
-            outs.append(o)
-        return np.concatenate(outs, axis=1)
+        return np.concatenate([be.evaluate_at(hnd, pts) for hnd in local.handles], axis=1)
     mine_ood = (local_ood(sc_main.local), local_ood(sc_aux.local))
     hz = np.zeros((2, 4), dtype=np.uint64)
     if rank == 0:
-        z2 = felt.from_ints([z * z % P])
-        ctx.check(L.s252_commit_evaluate_at(comp.handle, N.ptr(z2), 1, N.ptr(hz), 2, 0))
+        hz = be.evaluate_at(comp, felt.from_ints([z * z % P]))[0]
     if world > 1:
         parts = [None] * world
         dist.all_gather_object(parts, (mine_ood, hz if rank == 0 else None), group=group)
@@ -227,44 +343,30 @@ def generate_cairo_proof_sharded(trace, options, ctx, group=None, timings=None, 
             t.append(felt.to_bytes_be(v))
     mark("ood")
     # ---- round 4 (prover.rs:327-404)
-    gamma, gamma_p = transcript_to_field(t), transcript_to_field(t)
-    tg = np.stack([transcript_to_field(t) for _ in range(2 * ncols)])
-    p0 = torch.empty((m, 4), dtype=mblock.dtype, device=device)
+    gamma, gamma_p = be.to_field(t), be.to_field(t)
+    tg = np.stack([be.to_field(t) for _ in range(2 * ncols)])
+    p0 = be.new_tensor((m, 4))
     mine = p0[rank * rows_per:(rank + 1) * rows_per]
-    cblock = comp_lde[:, rank * rows_per:(rank + 1) * rows_per]                  # stride m
-    tables = (C.c_void_p * 3)(mblock.data_ptr(), ablock.data_ptr(), cblock.data_ptr())
-    strides = (C.c_size_t * 3)(rows_per, rows_per, m)
-    ncs = (C.c_size_t * 3)(c_main, 18, 2)
-    offs = np.array([0, 1], dtype=np.uint64)
-    zlw = felt.from_int(z)
-    ood_flat = np.ascontiguousarray(ood.reshape(-1, 4))
-    ctx.check(L.s252_deep_rows(ctx.handle, tables, strides, ncs, 3, rank * rows_per, rows_per, m, n, N.ptr(zlw), N.ptr(offs), 2,
-                               N.ptr(ood_flat), N.ptr(np.ascontiguousarray(hz[0])), N.ptr(np.ascontiguousarray(hz[1])),
-                               N.ptr(gamma), N.ptr(gamma_p), N.ptr(tg), h, C.c_void_p(mine.data_ptr())))
+    be.deep_rows(mblock, ablock, comp_lde, rank * rows_per, n, z, ood, hz, gamma, gamma_p, tg, options, mine)
     if world > 1:
         dist.all_gather_into_tensor(p0.view(-1), mine.reshape(-1).clone(), group=group)
-        torch.cuda.synchronize(device)
+        be.sync()
     mark("deep")
     layers = order
     q_count = options.fri_number_of_queries if layers else 0
     iotas = np.zeros(max(q_count, 1), dtype=np.uint64)
-    fri = C.c_void_p()
+    fri = None
     if rank == 0:
-        last = np.empty(4, dtype=np.uint64)
-        fri_roots = np.empty((max(layers, 1), 32), dtype=np.uint8)
-        ctx.check(L.s252_fri_commit_phase_evals(ctx.handle, layers, C.c_void_p(p0.data_ptr()), m, t.handle, h, C.byref(fri), N.ptr(last),
-                                                N.ptr(fri_roots)))
-        nonce = C.c_uint64()
-        ch = np.frombuffer(t.challenge(), dtype=np.uint8).copy()
-        ctx.check(L.s252_generate_nonce_with_grinding(ctx.handle, N.ptr(ch), options.grinding_factor, 0, C.byref(nonce)))
-        t.append(_u64be(nonce.value))
+        fri, last, fri_roots = be.fri_commit_phase_evals(p0, layers, t, options)
+        nonce = be.grind(t.challenge(), options.grinding_factor)
+        t.append(_u64be(nonce))
         for q in range(q_count):
-            iotas[q] = transcript_to_usize(t) % m
+            iotas[q] = be.to_usize(t) % m
     del p0
     mark("fri_grind")
     if world > 1:
-        it = torch.from_numpy(iotas.view(np.int64)).to(device)
-        dist.broadcast(it, src=0 if group is None else dist.get_global_rank(group, 0), group=group)
+        it = torch.from_numpy(iotas.view(np.int64).copy()).to(device)
+        dist.broadcast(it, src=gr(0), group=group)
         iotas = it.cpu().numpy().view(np.uint64)
     idx = [int(i) for i in iotas[:q_count]]
     (main_rows, main_paths), (aux_rows, aux_paths) = D.open_many([sc_main, sc_aux], idx) if q_count else (([], []), ([], []))
@@ -272,23 +374,16 @@ def generate_cairo_proof_sharded(trace, options, ctx, group=None, timings=None, 
     proof = None
     if rank == 0:
         depth = m.bit_length() - 1
-        ev = np.empty((q_count, layers, 4), dtype=np.uint64)
-        evs = np.empty_like(ev)
-        pa = np.empty((q_count, layers, depth, 32), dtype=np.uint8)
-        pas = np.empty_like(pa)
-        crow = np.empty((q_count, 2, 4), dtype=np.uint64)
-        cpath = np.empty((q_count, depth, 32), dtype=np.uint8)
         if q_count:
-            ia = np.array(idx, dtype=np.uint64)
-            ctx.check(L.s252_fri_query(fri, N.ptr(ia), q_count, N.ptr(ev), N.ptr(evs), N.ptr(pa), N.ptr(pas), depth))
-            ctx.check(L.s252_commit_open(comp.handle, N.ptr(ia), q_count, N.ptr(crow), N.ptr(cpath)))
+            ev, evs, pa, pas = be.fri_query(fri, idx, layers, depth)
+            crow, cpath = be.commit_open(comp, idx, depth)
         bb = lambda a: felt.to_bytes_be_many(np.asarray(a).view(np.uint64).reshape(-1, 4))               # elements -> wire bytes
         u8 = lambda v: np.frombuffer(_u64be(v), dtype=np.uint8)
         const = lambda v: np.tile(u8(v), (q_count, 1))
         out = _u64be(n) + _u64be(2) + sc_main.root + sc_aux.root                 # StarkProof::serialize, proof/stark.rs:161-218
         frame = _u64be(2 * ncols) + _u64be(32) + bb(ood).tobytes() + _u64be(ncols)
         out += _blob(frame) + comp_root + _u64be(32) + bb(hz).tobytes()
-        out += _u64be(layers) + fri_roots[:layers].tobytes() + bb(last).tobytes() + _u64be(q_count)
+        out += _u64be(layers) + np.ascontiguousarray(fri_roots).tobytes() + bb(last).tobytes() + _u64be(q_count)
         if q_count:
             # every query's blob has the same layout, so all of them are assembled as rows of one byte matrix
             def path_section(paths):                                             # [Q, layers, depth, 32] -> u64(len_k) || path_k for every layer
@@ -306,14 +401,13 @@ def generate_cairo_proof_sharded(trace, options, ctx, group=None, timings=None, 
             as_u8 = lambda paths: np.frombuffer(b"".join(b"".join(bytes(x) for x in p_) for p_ in paths), dtype=np.uint8).reshape(q_count, -1)
             rows52 = np.concatenate([np.stack([np.asarray(r_).view(np.uint64).reshape(-1, 4) for r_ in main_rows]),
                                      np.stack([np.asarray(r_).view(np.uint64).reshape(-1, 4) for r_ in aux_rows])], axis=1)
-            opn = np.concatenate([const(depth), cpath.reshape(q_count, -1), const(32), bb(crow).reshape(q_count, -1), const(2),
+            opn = np.concatenate([const(depth), np.ascontiguousarray(cpath).reshape(q_count, -1), const(32), bb(crow).reshape(q_count, -1), const(2),
                                   const(depth), as_u8(main_paths), const(depth), as_u8(aux_paths), const(ncols),
                                   bb(rows52).reshape(q_count, -1)], axis=1)
             out += np.concatenate([const(opn.shape[1]), opn], axis=1).tobytes()
-        out += _u64be(nonce.value)
+        out += _u64be(nonce)
         proof = out
-        L.s252_fri_destroy(fri)
-        comp.free()
+        be.release(fri, comp)
     mark("serialize")
     sc_main.free()
     sc_aux.free()

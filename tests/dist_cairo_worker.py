@@ -14,9 +14,35 @@ from lambdaworks_cairo_prover_b200 import cairo                                #
 from lambdaworks_cairo_prover_b200.cairo_distributed import generate_cairo_proof_sharded   # noqa: E402
 
 
+def main_gloo(fib_n, opts):
+    """CPU ranks: the orchestration with the oracle double of the GPU backend == the oracle's own prover."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from cairo_oracle_backend import OracleCairoBackend
+    from oracle.cairo_prover import cairo_prove
+    dist.init_process_group("gloo")
+    rank = dist.get_rank()
+    regs, mem, size = cairo.run_program(cairo.fibonacci_program(fib_n))
+    trace = cairo.build_main_trace(regs, mem, size)
+    table = np.array(trace.table).reshape(trace.n_rows(), trace.n_cols, 4)
+    for exchange in ("a2a", "p2p"):
+        proof = generate_cairo_proof_sharded(trace, opts, OracleCairoBackend(table, trace.pub_inputs), exchange=exchange)
+        if rank == 0:
+            want = cairo_prove(table, trace.pub_inputs, opts, threads=1).serialize()
+            assert proof == want, "sharded proof differs from the oracle's (%d vs %d bytes)" % (len(proof), len(want))
+        else:
+            assert proof is None
+    dist.barrier()
+    if rank == 0:
+        print("DIST_CAIRO_OK", dist.get_world_size(), trace.n_rows(), len(proof))
+    dist.destroy_process_group()
+
+
 def main():
     fib_n = int(sys.argv[1])
     opts = P.ProofOptions(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]))
+    if len(sys.argv) > 6 and sys.argv[6] == "gloo":
+        return main_gloo(fib_n, opts)
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))

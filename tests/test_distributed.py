@@ -72,6 +72,19 @@ def test_sharded_commit_nccl():
     launch("nccl", world, 11, 18, 4, exchange="a2a")
 
 
+@pytest.mark.parametrize("world,args", [(2, ("3", "4", "3", "3", "1")), (4, ("10", "2", "4", "5", "3")), (1, ("3", "4", "2", "3", "1"))])
+def test_sharded_cairo_proof_gloo(world, args):
+    """The orchestration of the sharded Cairo prover (column shards, exchange, halos, gathers, transcript replay,
+    openings, serialization) on CPU ranks, with the GPU backend replaced by its oracle double
+    (tests/cairo_oracle_backend.py): bytes == the oracle's single-process prover, for both exchange kinds."""
+    worker = os.path.join(ROOT, "tests", "dist_cairo_worker.py")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", str(free_port()), worker] + list(args) + ["gloo"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, OMP_NUM_THREADS="1"))
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    assert "DIST_CAIRO_OK" in res.stdout
+
+
 @pytest.mark.gpu
 def test_sharded_cairo_proof_nccl():
     """ONE Cairo proof over 2 (and 4) GPUs == the single-GPU proof, byte for byte."""
