@@ -63,8 +63,8 @@ def _blob(b):
 class GpuCairoBackend(D.GpuBackend):
     """The compute steps of the sharded prover on this rank's GPU, through the C ABI.  Tensors hold field
     elements in the library's internal format; everything that crosses to the host (roots, challenges,
-    out-of-domain values, opened rows) is in the reference's LW layout.  tests/dist_cairo_worker.py has a
-    CPU double of this class on the oracle, so that the orchestration below is covered by gloo tests."""
+    out-of-domain values, opened rows) is in the reference's LW layout.  The tests replace this class by a
+    CPU test double with the same interface, so that the orchestration below also runs under gloo."""
 
     def __init__(self, ctx):
         super().__init__(ctx)
