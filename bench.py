@@ -11,14 +11,17 @@ SURVEY.md section 8 config C2): N = 2^19 rows, blowup 4 (M = 2^21), coset offset
         = M*(34+18+2) LDE values + sum of the 19 FRI layer sizes.
 
 `value`  : elems/s with the inputs already resident in HBM (S252_DEVICE buffers).
-`e2e`    : the same step through the host-buffer C ABI: pinned host inputs are copied in inside
-           the timed region, roots / last value / nonce are read back.
+`e2e`    : the same step through the reference-facing C ABI with HOST buffers (S252_HOST): every call gets
+           a pinned host table and uploads it itself inside the timed region (column groups streamed over
+           PCIe under the transforms of the previous group); roots / last value / nonce are read back.
+           `e2e.prefetch_pipeline` is the extra a streaming prover can have on top (next step's inputs
+           prefetched on the copy stream under the current step).
 Timing   : CUDA events on the library's stream, W >= 3 warm-up steps, max over ranks; every step
            streams ~8 GB through HBM (inputs/outputs far larger than the 126 MB L2).
 N > 1    : one process per GPU, each proving an independent trace (weak scaling, no data-path
            collective) -- see DESIGN.md "multi-GPU".
 --impl reference : the CPU restatement of the reference (oracle/, threads over columns as under the
-           reference's `parallel` feature) on a bounded sample of the same workload.
+           reference's `parallel` feature) at the SAME size (N = 2^19), as many steps as fit the time budget.
 """
 import argparse
 import json
@@ -261,7 +264,7 @@ def run_gpu(args):
         return ms, out
 
     ms_e2e, out_e2e = timed_e2e(args.steps, max(args.warmup, 1))
-    ms_sync, out_sync, _, _, _ = timed(N.HOST, max(1, min(args.steps, 2)), 1, False)
+    ms_sync, out_sync, _, _, _ = timed(N.HOST, max(1, min(args.steps, 3)), 3, False)
     assert out_sync[0] == out_dev[0] and out_sync[2] == out_dev[2], "host-buffer path disagrees"
     assert out_dev[0] == out_e2e[0] and out_dev[2] == out_e2e[2], "device-resident and host-buffer paths disagree"
 
@@ -310,22 +313,29 @@ def run_gpu(args):
         # time-weighted fraction of the binding integer pipe over the whole step: IMAD.WIDE issue for the field
         # kernels, LOP3/SHF issue for the Keccak kernels (whichever is larger for the kernel)
         step_frac = sum(k["share"] * max(k["imad_frac"], k["alu_frac"]) for k in kernels.values())
+        sync_steps = max(1, min(args.steps, 3))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32x8 (256-bit Montgomery) / u64 Keccak lanes", "data": "synthetic (splitmix64-seeded field elements)",
             "config": cfg,
-            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": out_e2e[3],
-                    "how": "pinned host inputs -> s252_copy_to_device_async (copy stream, double-buffered, overlaps the "
-                           "previous step's kernels) -> S252_DEVICE calls; roots/last value/nonce read back",
-                    "unpipelined_ms_per_step": ms_sync / max(1, min(args.steps, 2)),
-                    "unpipelined_how": "S252_HOST calls: each call copies its own input on the compute stream"},
+            "e2e": {"value": elems * sync_steps / (ms_sync * 1e-3), "unit": UNIT, "ms_per_step": ms_sync / sync_steps,
+                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": out_e2e[3], "steps": sync_steps,
+                    "how": "the plugin calls with HOST buffers: s252_interpolate_and_commit / s252_lde_and_commit / s252_fri_commit_phase "
+                           "(S252_HOST) on pinned host tables; each call streams its own table over PCIe in column groups under the "
+                           "transforms of the previous group; roots/last value/nonce read back",
+                    "prefetch_pipeline": {"value": e2e_value, "ms_per_step": ms_e2e / args.steps,
+                                          "how": "extra: the NEXT step's inputs prefetched with s252_copy_to_device_async (copy stream, "
+                                                 "double-buffered) under the current step's S252_DEVICE calls"}},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": tname, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                         "note": "integer-pipe bound path: see int_roofline for the binding roof"},
+            "roofline": {"bound": "int_issue", "kernel": tname, "achieved": tstat["muls"] * 80 / (tstat["ms"] * 1e-3) / 1e9 if tstat["ms"] else 0.0,
+                         "peak": imad_peak, "unit": "G lane-op/s (IMAD.WIDE.U32)",
+                         "frac": kernels[tname]["imad_frac"], "traffic": traffic,
+                         "peak_source": "isolated IMAD.WIDE.U32 issue rate measured on this pool's B200 (profiles/int_peaks.json; = 64 lanes/clk/SM); "
+                                        "not in MEASURED_PEAKS.json, which holds HBM and bf16 peaks only",
+                         "work": "80 wide multiply-adds per field multiplication (SURVEY 8d) x the multiplications of the launch (DESIGN.md section 4)",
+                         "hbm": {"achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "peak_source": peak_src}},
             "int_roofline": {"bound": "integer issue (IMAD.WIDE for field kernels, LOP3/SHF for Keccak kernels)",
                              "step_frac": step_frac,
                              "step_frac_how": "sum over kernels of (share of step time) x max(imad_frac, alu_frac); peaks are the "
@@ -336,7 +346,7 @@ def run_gpu(args):
             "result": {"last_root": out_dev[0].hex(), "nonce": out_dev[2]},
         }
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline_sample(args.cpu_log_n)
+            line["cpu_baseline"] = cpu_baseline_sample(args.cpu_log_n or 17)
         if cairo_line is not None:
             line["cairo_prove"] = cairo_line
             if not args.no_cpu_baseline and world == 1:
@@ -398,22 +408,43 @@ def cairo_prove_bench(ctx, args, world, rank, barrier, dist):
                    "N>1: one independent proof per GPU, max over ranks"}
 
 
+def fib_trace_table(fib_n):
+    """The main trace of fibonacci_<n> as (table[n_rows, n_cols, 4], public inputs), built by the library's host front-end in a
+    CHILD process: the process that times the CPU arm never loads the product library."""
+    import pickle
+    import tempfile
+    code = ("import sys, pickle, numpy as np; sys.path.insert(0, %r)\n"
+            "from lambdaworks_cairo_prover_b200 import cairo\n"
+            "regs, mem, size = cairo.run_program(cairo.fibonacci_program(%d))\n"
+            "t = cairo.build_main_trace(regs, mem, size)\n"
+            "table = np.array(t.table).reshape(t.n_rows(), t.n_cols, 4)\n"
+            "p = t.pub_inputs\n"
+            "pub = {k: getattr(p, k) for k in ('pc_init', 'ap_init', 'fp_init', 'pc_final', 'ap_final', 'num_steps', 'range_check_min', "
+            "'range_check_max', 'public_memory')}\n"
+            "pickle.dump((table, pub), open(sys.argv[1], 'wb'), protocol=4)\n" % (ROOT, fib_n))
+    from types import SimpleNamespace
+    with tempfile.NamedTemporaryFile(suffix=".pkl") as f:
+        subprocess.run([sys.executable, "-c", code, f.name], check=True)
+        table, pub = pickle.load(open(f.name, "rb"))
+    return table, SimpleNamespace(**pub)
+
+
 def cpu_cairo_prove_sample(fib_n):
     """The CPU restatement of prove::<CairoAIR> (oracle/, pinned byte-for-byte on the reference's golden
     proof) on a bounded sample: a shorter fibonacci program, same options."""
-    import lambdaworks_cairo_prover_b200 as P
-    from lambdaworks_cairo_prover_b200 import cairo
+    from types import SimpleNamespace
     from oracle.cairo_prover import cairo_prove
-    regs, mem, size = cairo.run_program(cairo.fibonacci_program(fib_n))
-    trace = cairo.build_main_trace(regs, mem, size)
-    table = np.array(trace.table).reshape(trace.n_rows(), trace.n_cols, 4)
+    table, pub = fib_trace_table(fib_n)
+    # ProofOptions::new_secure(SecurityLevel::Provable80Bits, 3), src/starks/proof/options.rs:67-73
+    opts = SimpleNamespace(blowup_factor=4, fri_number_of_queries=80, coset_offset=3, grinding_factor=20)
     cores = os.cpu_count() or 1
     t0 = time.perf_counter()
-    cairo_prove(table, trace.pub_inputs, P.ProofOptions.new_secure("Provable80Bits", 3), threads=cores)
+    cairo_prove(table, pub, opts, threads=cores)
     dt = time.perf_counter() - t0
-    return {"value": dt * 1e3, "unit": "ms", "cores": cores, "kind": "port", "trace_rows": trace.n_rows(),
+    rows = table.shape[0]
+    return {"value": dt * 1e3, "unit": "ms", "cores": cores, "kind": "port", "trace_rows": rows,
             "sample": "fibonacci_%d (2^%d rows instead of 2^19), same options; oracle/ restatement of the reference prover "
-                      "(C kernels, python round structure; LDE and constraint evaluation threaded)" % (fib_n, trace.n_rows().bit_length() - 1)}
+                      "(C kernels, python round structure; LDE and constraint evaluation threaded)" % (fib_n, rows.bit_length() - 1)}
 
 
 def run_gpu_sharded(args):
@@ -545,38 +576,46 @@ def cpu_commit_sample(log_n, threads):
 def cpu_baseline_sample(log_n):
     cores = os.cpu_count() or 1
     value, dt = cpu_commit_sample(log_n, cores)
-    return {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "same step at N=2^%d rows instead of 2^%d (all 54 columns, %d FRI layers, grinding %d); "
-                      "C restatement of the reference, LDE threaded over columns like the reference's `parallel` "
-                      "feature, everything else sequential as in the reference; %.1f s" % (log_n, LOG_N, log_n, GRIND, dt)}
+    return {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "trace_rows": 1 << log_n,
+            "sample": "the same step at N=2^%d rows instead of 2^%d (all 54 columns, %d FRI layers, grinding %d): %.1f s of CPU work; "
+                      "C restatement of the reference (the Rust reference cannot be built here: no cargo), LDE threaded over columns "
+                      "like the reference's `parallel` feature (prover.rs:169-183), Merkle trees and FRI sequential as in the reference, "
+                      "so most of the run uses ONE core" % (log_n, LOG_N, log_n, GRIND, dt)}
 
 
 def run_reference(args):
+    """The reference arm: the CPU restatement at the SAME configuration as the GPU arm (N = 2^19 by default).  One such step is
+    ~45 s of CPU work, so the arm runs as many full-size steps as fit --cpu-budget-s (at least one) and says how many."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    for _ in range(args.warmup and 1):
-        cpu_commit_sample(max(args.cpu_log_n - 3, 4), cores)
+    log_n = args.cpu_log_n if args.cpu_log_n else args.log_n
+    cpu_commit_sample(8, cores)                      # loads the checker library, touches every code path once
     t0 = time.perf_counter()
-    total_elems = 0
-    for _ in range(args.steps):
-        v, dt = cpu_commit_sample(args.cpu_log_n, cores)
-        total_elems += workload_config(args.cpu_log_n)["elems_per_step"]
+    total_elems, steps_done, last = 0, 0, 0.0
+    while steps_done < args.steps and (steps_done == 0 or time.perf_counter() - t0 + last < args.cpu_budget_s):
+        _, last = cpu_commit_sample(log_n, cores)
+        total_elems += workload_config(log_n)["elems_per_step"]
+        steps_done += 1
     wall = time.perf_counter() - t0
     value = total_elems / wall
-    sample = ("each step = the C2 commit phase at N=2^%d rows instead of 2^%d (54 columns, blowup %d, %d FRI layers, "
-              "grinding %d); oracle/ C restatement (the Rust reference cannot be built here: no cargo, un-vendored "
-              "git dependencies), LDE threaded over columns as under `parallel`" % (args.cpu_log_n, LOG_N, BLOWUP, args.cpu_log_n, GRIND))
-    print(json.dumps({
+    cfg = workload_config(log_n)
+    cfg["parallelism"] = "host cores only"
+    sample = ("%d step(s) of the C2 commit phase at N=2^%d rows (54 columns, blowup %d, %d FRI layers, grinding %d), %.0f s each; oracle/ C "
+              "restatement (the Rust reference cannot be built here: no cargo, un-vendored git dependencies), LDE threaded over columns as "
+              "under `parallel`, Merkle trees and FRI sequential as in the reference" % (steps_done, log_n, BLOWUP, log_n, GRIND, wall / steps_done))
+    line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall * 1e3 / args.steps, "higher_is_better": True,
+        "steps": steps_done, "steps_requested": args.steps, "warmup": 0, "ms_per_step": wall * 1e3 / steps_done, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u64x4 (256-bit Montgomery)", "data": "synthetic",
-        "config": workload_config(LOG_N),
+        "config": cfg,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        **({} if args.no_cairo else {"cairo_prove": cpu_cairo_prove_sample(args.cpu_fib_n)}),
-    }))
+    }
+    if not args.no_cairo:
+        line["cairo_prove"] = cpu_cairo_prove_sample(args.cpu_fib_n)
+    print(json.dumps(line))
 
 
 def main():
@@ -589,7 +628,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log-n", type=int, default=LOG_N, help="trace length exponent (default: the C2 size)")
-    ap.add_argument("--cpu-log-n", type=int, default=15, help="trace length exponent of the bounded CPU sample")
+    ap.add_argument("--cpu-log-n", type=int, default=0,
+                    help="trace length exponent of the CPU runs (default: --impl reference runs the full size, the cpu_baseline "
+                         "object of the GPU line a 2^17-row sample)")
+    ap.add_argument("--cpu-budget-s", type=float, default=150.0, help="--impl reference: stop starting new full-size steps after this long")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cairo", action="store_true", help="skip the Cairo fib prove-time measurement")
     ap.add_argument("--fib-n", type=int, default=70000, help="fibonacci program of the prove-time measurement")

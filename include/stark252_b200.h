@@ -72,6 +72,12 @@ int s252_device_alloc(s252_ctx *ctx, size_t bytes, void **out);
 int s252_device_free(s252_ctx *ctx, void *ptr);
 int s252_copy_to_device(s252_ctx *ctx, void *dst, const void *src, size_t bytes);
 int s252_copy_to_host(s252_ctx *ctx, void *dst, const void *src, size_t bytes);
+/* Page-lock a caller buffer (a Rust Vec<FE>, say) so that S252_HOST calls can stream it: with pinned memory
+ * s252_interpolate_and_commit / s252_interpolate_and_lde read the table over PCIe one column group at a time while
+ * the previous group is being transformed (pageable memory is copied in one piece first).  Registration costs
+ * about a millisecond per 10 MB: do it once for a buffer that is reused. */
+int s252_host_register(void *ptr, size_t bytes);
+int s252_host_unregister(void *ptr);
 /* Prefetch of the NEXT trace while the current one is being committed: the copy is queued on a
  * second stream and returns at once (pinned host memory gives a true asynchronous DMA);
  * s252_copy_stream_wait makes all later work on the compute stream wait for the prefetches issued

@@ -1,4 +1,5 @@
 """Builds lambdaworks_cairo_prover_b200/lib/libstark252_b200.so (sm_100a only, in-tree)."""
+import glob
 import os
 import shutil
 import subprocess
@@ -9,8 +10,6 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 SO = os.path.join(LIBDIR, "libstark252_b200.so")
 SOURCES = ["runtime.cu"]
-HEADERS = ["fe.cuh", "ntt.cuh", "keccak.cuh", "commit.cuh", "deep.cuh", "microbench.cuh", "host_field.hpp",
-           "cairo_host.hpp", "cairo_api.cuh"]
 
 
 def nvcc_path():
@@ -24,8 +23,10 @@ def needs_build():
     if not os.path.exists(SO):
         return True
     t = os.path.getmtime(SO)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS]
-    deps += [os.path.join(os.path.dirname(HERE), "include", h) for h in ("stark252_b200.h", "stark252_cairo.h")]
+    # every file the translation unit can include: the list is globbed so that it cannot drift from the sources
+    deps = [f for pat in ("*.cu", "*.cuh", "*.hpp", "*.h") for f in glob.glob(os.path.join(CSRC, pat))]
+    deps += glob.glob(os.path.join(os.path.dirname(HERE), "include", "*.h"))
+    deps.append(os.path.abspath(__file__))
     return any(os.path.getmtime(d) > t for d in deps)
 
 

@@ -176,6 +176,9 @@ class Keccak256 {
             if (fill_ == 136) { permute(); fill_ = 0; }
         }
     }
+    // the sponge as it stands (absorbed bytes are XORed into the lanes): what a device-side continuation needs
+    const uint64_t* lanes() const { return s_; }
+    size_t fill() const { return fill_; }
     void finalize(uint8_t out[32]) {
         s_[fill_ >> 3] ^= (uint64_t)0x01 << (8 * (fill_ & 7));
         s_[16] ^= 0x8000000000000000ULL;

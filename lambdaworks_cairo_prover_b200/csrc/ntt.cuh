@@ -97,43 +97,55 @@ __device__ __forceinline__ Tile make_tile(unsigned char* smem, unsigned logE, un
     return t;
 }
 
-// (a, b) -> (a + w*b, a - w*b + 2p); `plain` skips the multiplication when w is known to be 1
-__device__ __forceinline__ void bfly(fe& a, fe& b, const fe* __restrict__ tw, bool unit) {
-    const fe v = unit ? b : fe_mul(b, ldg_fe(tw));
+// (a, b) -> (a + w*b, a - w*b + 2p); UNIT (compile time) skips the multiplication when w is known to be 1
+template <bool UNIT>
+__device__ __forceinline__ void bfly(fe& a, fe& b, const fe* __restrict__ tw) {
+    fe v;
+    if constexpr (UNIT) v = b; else v = fe_mul(b, ldg_fe(tw));
     const fe s = fe_add_lazy(a, v);
     b = fe_sub_lazy<2>(a, v);
     a = s;
 }
 
+// One radix-4 step (DIT levels lev and lev+1) over the whole tile: four elements, four butterflies, three
+// twiddle loads per work item.  FIRST_UNIT: lev == 0 of a transform without coset shift, where the level-1
+// twiddle and the first level-2 twiddle are 1 -- three of the four multiplications disappear at compile time.
+template <bool FIRST_UNIT>
+__device__ __forceinline__ void radix4_step(const Tile& sm, const fe* __restrict__ lvl, unsigned logL, unsigned logT, unsigned lev) {
+    const unsigned T = 1u << logT;
+    const unsigned half = 1u << lev;
+    const unsigned items = (1u << (logL - 2)) << logT;
+    for (unsigned w = threadIdx.x; w < items; w += NTT_THREADS) {
+        const unsigned t = w & (T - 1);
+        const unsigned j = w >> logT;
+        const unsigned jj = j & (half - 1);
+        const unsigned i0 = ((j >> lev) << (lev + 2)) + jj;
+        const unsigned e0 = (i0 << logT) + t, es = half << logT;
+        fe x0 = sm.ld(e0), x1 = sm.ld(e0 + es), x2 = sm.ld(e0 + 2 * es), x3 = sm.ld(e0 + 3 * es);
+        bfly<FIRST_UNIT>(x0, x1, lvl + half + jj);
+        bfly<FIRST_UNIT>(x2, x3, lvl + half + jj);
+        bfly<FIRST_UNIT>(x0, x2, lvl + 2 * half + jj);      // level-2 twiddles are {1, w_4}: the first is 1 too
+        bfly<false>(x1, x3, lvl + 3 * half + jj);
+        sm.st(e0, x0); sm.st(e0 + es, x1); sm.st(e0 + 2 * es, x2); sm.st(e0 + 3 * es, x3);
+    }
+    __syncthreads();
+}
+
 // All levels of a size-L DIT transform on every one of the T sequences held in the tile (input
-// already in bit-reversed position order).  Levels are taken two at a time in registers (four
-// elements, four butterflies, three twiddle loads per work item), which halves the shared-memory
-// traffic and the number of barriers of a level-by-level radix-2 loop.  first_unit: the level-1
-// twiddle is 1 (every transform except the first pass of a coset evaluation), so that level is
-// add/sub only.
+// already in bit-reversed position order).  Levels are taken two at a time in registers, which halves
+// the shared-memory traffic and the number of barriers of a level-by-level radix-2 loop.  first_unit: the
+// level-1 twiddle is 1 (every transform except the first pass of a coset evaluation).
 __device__ __forceinline__ void block_dit(const Tile& sm, const fe* __restrict__ lvl, unsigned logL, unsigned logT,
                                           bool first_unit) {
     const unsigned T = 1u << logT;
     unsigned lev = 0;
-    for (; lev + 1 < logL; lev += 2) {
-        const unsigned half = 1u << lev;
-        const unsigned items = (1u << (logL - 2)) << logT;
-        for (unsigned w = threadIdx.x; w < items; w += NTT_THREADS) {
-            const unsigned t = w & (T - 1);
-            const unsigned j = w >> logT;
-            const unsigned jj = j & (half - 1);
-            const unsigned i0 = ((j >> lev) << (lev + 2)) + jj;
-            const unsigned e0 = (i0 << logT) + t, es = half << logT;
-            fe x0 = sm.ld(e0), x1 = sm.ld(e0 + es), x2 = sm.ld(e0 + 2 * es), x3 = sm.ld(e0 + 3 * es);
-            const bool unit = first_unit && lev == 0;
-            bfly(x0, x1, lvl + half + jj, unit);
-            bfly(x2, x3, lvl + half + jj, unit);
-            bfly(x0, x2, lvl + 2 * half + jj, unit);      // level-2 twiddles are {1, w_4}: the first is 1 too
-            bfly(x1, x3, lvl + 3 * half + jj, false);
-            sm.st(e0, x0); sm.st(e0 + es, x1); sm.st(e0 + 2 * es, x2); sm.st(e0 + 3 * es, x3);
-        }
-        __syncthreads();
+    if (logL >= 2) {
+        if (first_unit) radix4_step<true>(sm, lvl, logL, logT, 0);
+        else radix4_step<false>(sm, lvl, logL, logT, 0);
+        lev = 2;
     }
+#pragma unroll 1
+    for (; lev + 1 < logL; lev += 2) radix4_step<false>(sm, lvl, logL, logT, lev);
     if (lev < logL) {   // odd number of levels: one radix-2 level remains
         const unsigned half = 1u << lev;
         const unsigned items = (1u << (logL - 1)) << logT;
@@ -144,7 +156,8 @@ __device__ __forceinline__ void block_dit(const Tile& sm, const fe* __restrict__
             const unsigned i0 = ((j >> lev) << (lev + 1)) + jj;
             const unsigned e0 = (i0 << logT) + t, es = half << logT;
             fe a = sm.ld(e0), b = sm.ld(e0 + es);
-            bfly(a, b, lvl + half + jj, first_unit && lev == 0);
+            if (first_unit && lev == 0) bfly<true>(a, b, lvl + half + jj);
+            else bfly<false>(a, b, lvl + half + jj);
             sm.st(e0, a); sm.st(e0 + es, b);
         }
         __syncthreads();

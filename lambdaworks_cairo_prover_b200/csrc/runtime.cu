@@ -29,6 +29,7 @@ struct s252_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // host->device prefetch of the next trace, overlapping compute
     cudaEvent_t copy_event = nullptr;
+    unsigned* ticket = nullptr;           // device counter of merkle_finish (zero between launches)
     std::string err;
     uint64_t launches = 0;
     std::map<std::string, fe*> tables;   // cached twiddle tables (device)
@@ -219,6 +220,7 @@ extern "C" int s252_ctx_create(int device, s252_ctx** out) {
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return S252_ERR_CUDA; }
     if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->copy_event, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return S252_ERR_CUDA; }
+    if (cudaMalloc((void**)&ctx->ticket, 64) != cudaSuccess || cudaMemset(ctx->ticket, 0, 64) != cudaSuccess) { delete ctx; return S252_ERR_CUDA; }
     cudaFuncSetAttribute(s252::ntt_pass_strided, cudaFuncAttributeMaxDynamicSharedMemorySize, s252::NTT_TILE * 32);
     cudaFuncSetAttribute(s252::ntt_pass_final, cudaFuncAttributeMaxDynamicSharedMemorySize, s252::NTT_TILE * 32);
     if (const char* e = std::getenv("S252_MAX_LOGL")) {
@@ -235,6 +237,7 @@ extern "C" void s252_ctx_destroy(s252_ctx* ctx) {
     arena_trim(ctx);
     for (auto& kv : ctx->arena_size) cudaFree(kv.first);   // blocks still owned by live handles
     for (auto& kv : ctx->tables) cudaFree(kv.second);
+    cudaFree(ctx->ticket);
     cudaStreamSynchronize(ctx->copy_stream);
     cudaEventDestroy(ctx->copy_event);
     cudaStreamDestroy(ctx->copy_stream);
@@ -294,6 +297,16 @@ extern "C" int s252_device_free(s252_ctx* ctx, void* ptr) {
 extern "C" int s252_copy_to_device(s252_ctx* ctx, void* dst, const void* src, size_t bytes) {
     CU(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return S252_OK;
+}
+extern "C" int s252_host_register(void* ptr, size_t bytes) {
+    if (!ptr || !bytes) return S252_ERR_INVALID;
+    if (cudaHostRegister(ptr, bytes, cudaHostRegisterDefault) != cudaSuccess) { cudaGetLastError(); return S252_ERR_CUDA; }
+    return S252_OK;
+}
+extern "C" int s252_host_unregister(void* ptr) {
+    if (!ptr) return S252_ERR_INVALID;
+    if (cudaHostUnregister(ptr) != cudaSuccess) { cudaGetLastError(); return S252_ERR_CUDA; }
     return S252_OK;
 }
 // Prefetch: enqueue a host->device copy on the context's copy stream (returns immediately; use
@@ -516,13 +529,12 @@ static int run_ntt(s252_ctx* ctx, const Xform& X, const fe* in, size_t in_col_st
 }
 
 // Node levels of a tree whose 2^depth leaf digests are in place.  Wide levels go three at a time
-// through merkle_subtrees (every thread busy); the last MERKLE_TOP levels, where there is no
-// parallelism left to lose, are finished by one block.
-static const unsigned MERKLE_TOP = 9;
-static int build_tree_nodes(s252_ctx* ctx, size_t n_rows, uint64_t* nodes) {
+// through merkle_subtrees (every thread busy); from level 15..17 down one launch of merkle_finish
+// reaches the root (and, for a FRI layer, advances the device-side transcript chain).
+static int build_tree_nodes(s252_ctx* ctx, size_t n_rows, uint64_t* nodes, s252::FriChain* chain = nullptr) {
     unsigned level = ilog2(n_rows);
-    while (level > MERKLE_TOP) {
-        const unsigned lv = std::min(3u, level - MERKLE_TOP);
+    while (level > 17) {
+        const unsigned lv = std::min(3u, level - 15);
         const size_t groups = (size_t)1 << (level - lv);
         const unsigned blocks = (unsigned)((groups + 127) / 128);
         const double parents = (double)((size_t)1 << level) - (double)groups;
@@ -534,25 +546,27 @@ static int build_tree_nodes(s252_ctx* ctx, size_t n_rows, uint64_t* nodes) {
         LAUNCH_CHECK(ctx);
         level -= lv;
     }
-    if (level > 0) {
+    if (level > 0 || chain) {
         const size_t nchildren = (size_t)1 << level;
-        prof_begin(ctx, "merkle_nodes");
-        prof_work(ctx, 64.0 * nchildren, 0, (double)(nchildren - 1));
-        s252::merkle_nodes<<<1, s252::MERKLE_BLOCK, 0, ctx->stream>>>(nodes, level, level);
+        const unsigned blocks = level > (unsigned)s252::MERKLE_FUSED_LEVELS ? 1u << (level - s252::MERKLE_FUSED_LEVELS) : 1u;
+        prof_begin(ctx, "merkle_finish");
+        prof_work(ctx, 64.0 * nchildren, 0, (double)(nchildren - 1) + (chain ? 1.0 : 0.0));
+        s252::merkle_finish<<<blocks, s252::MERKLE_BLOCK, 0, ctx->stream>>>(nodes, level, ctx->ticket, chain);
         LAUNCH_CHECK(ctx);
     }
     return S252_OK;
 }
 
 // Batched Merkle tree over `n_rows` rows of column-major `cols`.
-static int build_tree(s252_ctx* ctx, const fe* cols, size_t col_stride, unsigned ncols, size_t n_rows, uint64_t* nodes) {
+static int build_tree(s252_ctx* ctx, const fe* cols, size_t col_stride, unsigned ncols, size_t n_rows, uint64_t* nodes,
+                      s252::FriChain* chain = nullptr) {
     if (!is_pow2(n_rows)) FAIL(ctx, S252_ERR_INVALID, "merkle tree needs a power-of-two number of leaves (got %zu)", n_rows);
     prof_begin(ctx, "merkle_leaves");
     prof_work(ctx, 32.0 * n_rows * ncols + 32.0 * n_rows, 0.2 * n_rows * ncols, (double)n_rows * ((32 * ncols) / 136 + 1));
     s252::merkle_leaves<<<(unsigned)((n_rows + 127) / 128), 128, 0, ctx->stream>>>(cols, col_stride, ncols, n_rows,
                                                                                 nodes + 4 * (n_rows - 1));
     LAUNCH_CHECK(ctx);
-    return build_tree_nodes(ctx, n_rows, nodes);
+    return build_tree_nodes(ctx, n_rows, nodes, chain);
 }
 
 // Bring a caller buffer of `count` LW elements onto the device (no format change).
@@ -736,6 +750,110 @@ static int lde_from_cols(s252_ctx* ctx, const fe* cols, size_t N, unsigned c, si
     }
     return S252_OK;
 }
+// Column groups of the upload -> transform pipeline of a host-resident table: a short first group (its upload is
+// the only one nothing can hide), then growing ones.  Returns K+1 boundaries.
+static std::vector<unsigned> upload_groups(unsigned c) {
+    unsigned K = 6;
+    if (const char* e = std::getenv("S252_HOST_GROUPS")) { const int v = std::atoi(e); if (v >= 1 && v <= 64) K = (unsigned)v; }
+    K = std::min(K, c);
+    std::vector<unsigned> cum(K + 1, 0);
+    for (unsigned g = 1; g <= K; ++g) cum[g] = cum[g - 1] + std::min(g, 4u);      // weights 1,2,3,4,4,4,..
+    std::vector<unsigned> lo(K + 1, 0);
+    for (unsigned g = 1; g <= K; ++g) lo[g] = std::max(lo[g - 1] + 1, (unsigned)(((uint64_t)c * cum[g] + cum[K] / 2) / cum[K]));
+    lo[K] = c;
+    for (unsigned g = K; g-- > 1;) lo[g] = std::min(lo[g], lo[g + 1] - 1);     // K <= c: every group keeps at least one column
+    return lo;
+}
+// How a host table reaches the device (S252_HOST callers):
+//   2 = pinned memory, read over PCIe by the transposing kernel itself (rows_lw_to_cols_stream), column group by
+//       column group on the copy stream while the previous group is transformed;
+//   1 = pinned memory, strided 2-D DMA of each column group + tile transpose (S252_HOST_UPLOAD=dma2d);
+//   0 = pageable memory (or S252_HOST_UPLOAD=copy): one copy of the whole table on the compute stream.
+static int host_upload_mode(const void* p, const void** dev_alias) {
+    *dev_alias = nullptr;
+    const char* e = std::getenv("S252_HOST_UPLOAD");
+    if (e && !std::strcmp(e, "copy")) return 0;
+    cudaPointerAttributes attr{};
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (attr.type != cudaMemoryTypeHost) return 0;
+    if (e && !std::strcmp(e, "dma2d")) return 1;
+    if (!attr.devicePointer) return 1;
+    *dev_alias = attr.devicePointer;
+    return 2;
+}
+
+static int lde_from_cols(s252_ctx* ctx, const fe* cols, size_t N, unsigned c, size_t blowup, uint64_t coset_offset, bool with_tree,
+                         s252_commit* cm, uint8_t root[32]);
+// interpolate_and_commit from a ROW-major LW table in pinned host memory, pipelined: the upload (+ transposition
+// + format change) of column group g+1 runs on the copy stream while group g is interpolated and extended.
+static int lde_from_pinned_rows(s252_ctx* ctx, const s252_fe* trace, int mode, const void* dev_alias, size_t N, unsigned c,
+                                size_t blowup, uint64_t coset_offset, bool with_tree, bool keep_trace, s252_commit* cm,
+                                uint8_t root[32]) {
+    const size_t M = N * blowup;
+    const std::vector<unsigned> lo = upload_groups(c);
+    const unsigned K = (unsigned)lo.size() - 1;
+    std::vector<cudaEvent_t> ev(K, nullptr);
+    cudaEvent_t start = nullptr;
+    int rc = [&]() -> int {
+        Tmp<fe> staged(ctx), cols(ctx);
+        if (mode == 1) TRY(dalloc(ctx, &staged.p, N * c));
+        TRY(dalloc(ctx, &cols.p, N * c));
+        TRY(dalloc(ctx, &cm->coeffs, N * c));
+        TRY(dalloc(ctx, &cm->lde, M * c));
+        // the blocks may be recycled ones: the copy stream must not overtake work already queued on the compute stream
+        CU(ctx, cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
+        CU(ctx, cudaEventRecord(start, ctx->stream));
+        CU(ctx, cudaStreamWaitEvent(ctx->copy_stream, start, 0));
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+        for (unsigned g = 0; g < K; ++g) {
+            const unsigned cg = lo[g + 1] - lo[g];
+            const size_t off = (size_t)lo[g] * N;
+            if (mode == 2) {
+                const fe* src = reinterpret_cast<const fe*>(dev_alias) + lo[g];
+                s252::rows_lw_to_cols_stream<<<(unsigned)sms / 2, 256, 0, ctx->copy_stream>>>(src, N, c, cg, cols.p + off, N);
+                ctx->launches++;
+                CU(ctx, cudaGetLastError());
+            } else {
+                CU(ctx, cudaMemcpy2DAsync(staged.p + off, (size_t)cg * sizeof(fe), reinterpret_cast<const fe*>(trace) + lo[g],
+                                          (size_t)c * sizeof(fe), (size_t)cg * sizeof(fe), N, cudaMemcpyHostToDevice, ctx->copy_stream));
+            }
+            CU(ctx, cudaEventCreateWithFlags(&ev[g], cudaEventDisableTiming));
+            CU(ctx, cudaEventRecord(ev[g], ctx->copy_stream));
+        }
+        Xform I;
+        I.logn = ilog2(N);
+        I.inverse = true;
+        for (unsigned g = 0; g < K; ++g) {
+            const unsigned cg = lo[g + 1] - lo[g];
+            const size_t off = (size_t)lo[g] * N;
+            CU(ctx, cudaStreamWaitEvent(ctx->stream, ev[g], 0));
+            if (mode == 1) {
+                prof_begin(ctx, "rows_lw_to_cols");
+                prof_work(ctx, 64.0 * N * cg, 0, 0);
+                s252::rows_lw_to_cols<<<dim3((unsigned)((N + 31) / 32), (cg + 31) / 32), 256, 0, ctx->stream>>>(staged.p + off, N, cg, cols.p + off, N);
+                LAUNCH_CHECK(ctx);
+            }
+            TRY(run_ntt(ctx, I, cols.p + off, N, false, cm->coeffs + off, N, false, cg));                 // compute_trace_polys
+            TRY(evaluate_cosets(ctx, cm->coeffs + off, N, false, ilog2(N), (unsigned)blowup, H::from_u64(coset_offset),
+                                cm->lde + (size_t)lo[g] * M, M, false, cg));                              // compute_lde_trace_evaluations
+        }
+        if (with_tree) {
+            TRY(dalloc(ctx, &cm->nodes, 4 * (2 * M - 1)));
+            TRY(build_tree(ctx, cm->lde, M, c, M, cm->nodes));                                           // batch_commit
+            TRY(fetch_root(ctx, cm->nodes, root));
+        } else {
+            CU(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+        if (keep_trace) { cm->trace = cols.p; cols.p = nullptr; }
+        return S252_OK;
+    }();
+    if (rc != S252_OK) cudaStreamSynchronize(ctx->copy_stream);
+    for (auto e : ev) if (e) cudaEventDestroy(e);
+    if (start) cudaEventDestroy(start);
+    return rc;
+}
+
 static int interpolate_lde_impl(s252_ctx* ctx, const s252_fe* trace, size_t n_rows, size_t n_cols, size_t blowup,
                                 uint64_t coset_offset, int mem, bool with_tree, s252_commit** out, uint8_t root[32],
                                 bool keep_trace = false) {
@@ -749,7 +867,10 @@ static int interpolate_lde_impl(s252_ctx* ctx, const s252_fe* trace, size_t n_ro
     const unsigned c = (unsigned)n_cols;
     s252_commit* cm = new s252_commit();
     cm->ctx = ctx; cm->n_cols = n_cols; cm->n_rows = M; cm->n_coeffs = N;
-    int rc = [&]() -> int {
+    const void* dev_alias = nullptr;
+    const int upload = mem == S252_HOST ? host_upload_mode(trace, &dev_alias) : 0;
+    int rc = upload ? lde_from_pinned_rows(ctx, trace, upload, dev_alias, N, c, blowup, coset_offset, with_tree, keep_trace, cm, root)
+                    : [&]() -> int {
         Tmp<fe> staged(ctx), cols(ctx);
         const fe* dtrace;
         TRY(stage_in(ctx, trace, N * c, mem, staged, &dtrace));
@@ -979,6 +1100,15 @@ static void fri_free(s252_fri* f) {
 }
 // FRI commit phase once layer 0 (f->layers[0].evals, domain_size evaluations on the coset h*<w>) is
 // resident: trees, transcript, folds, last value (fri/mod.rs:33-69).
+//
+// The whole phase is queued without a host round trip: the DefaultTranscript sponge continues on the device
+// (s252::FriChain), every tree's last block appends its root and samples the next zeta, layers of at most
+// 2^FRI_TAIL_LOG_MAX evaluations are finished by one single-block kernel, and the host reads all roots and the
+// last value back ONCE and replays the same appends on its own transcript (checking the last zeta).
+static unsigned fri_tail_log_max() {
+    if (const char* e = std::getenv("S252_FRI_TAIL_LOG")) { const int v = std::atoi(e); if (v >= 0 && v <= (int)s252::FRI_TAIL_LOG_MAX) return (unsigned)v; }
+    return 13;
+}
 static int fri_from_layer0(s252_ctx* ctx, s252_fri* f, size_t number_layers, s252_transcript* transcript, fe h,
                            size_t domain_size, s252_fe* last_value, uint8_t* roots_out) {
     const unsigned logM = ilog2(domain_size);
@@ -988,60 +1118,130 @@ static int fri_from_layer0(s252_ctx* ctx, s252_fri* f, size_t number_layers, s25
     const fe* inv_tw = nullptr;
     if (domain_size >= 2) TRY(get_power_table(ctx, domain_size / 2, w_inv, H::one(), &inv_tw));
     const fe inv2 = H::inv(H::from_u64(2));
-    uint8_t root[32];
-    if (number_layers > 0) {
-        TRY(dalloc(ctx, &f->layers[0].nodes, 4 * (2 * domain_size - 1)));
-        TRY(build_tree(ctx, f->layers[0].evals, domain_size, 1, domain_size, f->layers[0].nodes));
-        TRY(fetch_root(ctx, f->layers[0].nodes, root));
-        transcript->append(root, 32);                       // fri/mod.rs:37
-        if (roots_out) std::memcpy(roots_out, root, 32);
-    }
-    size_t size = domain_size;
-    const size_t folds = number_layers == 0 ? 1 : number_layers;
-    for (size_t k = 1; k <= folds; ++k) {
-        // fri/mod.rs:43-54 (k < number_layers) and :58-60 (the last fold)
+    const size_t L = number_layers;
+    if (L > (size_t)s252::FRI_MAX_LAYERS) FAIL(ctx, S252_ERR_INVALID, "at most %d FRI layers are supported", s252::FRI_MAX_LAYERS);
+    if ((domain_size >> (L ? L : 1)) == 0) FAIL(ctx, S252_ERR_INVALID, "FRI layer of size %zu cannot be folded", domain_size >> (L ? L - 1 : 0));
+    fe lv;
+    if (L == 0) {
+        // no layer is committed (fri/mod.rs:58-69 only): zeta comes straight from the host transcript
         const fe zeta = transcript->to_field();
-        const fe cfac = H::mul(zeta, H::mul(inv2, H::inv(h)));   // zeta / (2 h_k)
-        const size_t half = size / 2;
-        if (half == 0) FAIL(ctx, S252_ERR_INVALID, "FRI layer of size %zu cannot be folded", size);
-        const bool commit = k < number_layers;
-        FriLayerDev nxt;
-        nxt.size = half;
-        TRY(dalloc(ctx, &nxt.evals, half));
-        f->layers.push_back(nxt);
-        FriLayerDev& L = f->layers.back();
-        if (commit) TRY(dalloc(ctx, &L.nodes, 4 * (2 * half - 1)));
+        const fe cfac = H::mul(zeta, H::mul(inv2, H::inv(h)));
+        const size_t half = domain_size / 2;
+        Tmp<fe> rem(ctx);
+        TRY(dalloc(ctx, &rem.p, half));
         prof_begin(ctx, "fri_fold_commit");
-        prof_work(ctx, 32.0 * size + 32.0 * half + (commit ? 32.0 * half : 0.0), 3.2 * half, commit ? (double)half : 0.0);
-        s252::fri_fold_commit<<<(unsigned)((half + 127) / 128), 128, 0, ctx->stream>>>(
-            f->layers[k - 1].evals, half, inv_tw, (unsigned long long)(domain_size / size), cfac, inv2, L.evals,
-            commit ? L.nodes + 4 * (half - 1) : nullptr);
+        prof_work(ctx, 32.0 * domain_size + 32.0 * half, 3.2 * half, 0);
+        s252::fri_fold_commit<<<(unsigned)((half + 127) / 128), 128, 0, ctx->stream>>>(f->layers[0].evals, half, inv_tw, 1ull, cfac, nullptr,
+                                                                                      inv2, rem.p, nullptr);
         LAUNCH_CHECK(ctx);
-        h = H::sqr(h);
-        size = half;
-        if (commit) {
-            TRY(build_tree_nodes(ctx, half, L.nodes));
-            TRY(fetch_root(ctx, L.nodes, root));
-            transcript->append(root, 32);                   // fri/mod.rs:54
-            if (roots_out) std::memcpy(roots_out + 32 * k, root, 32);
+        std::vector<fe> tail(half);
+        CU(ctx, cudaMemcpyAsync(tail.data(), rem.p, half * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        fe acc = H::zero();
+        for (size_t i = 0; i < half; ++i) acc = H::add(acc, tail[i]);
+        lv = H::mul(acc, H::inv(H::from_u64((uint64_t)half)));
+        dfree(ctx, f->layers.back().evals);
+        f->layers.pop_back();
+    } else {
+        // ---- the chain: the transcript as it stands + 1/(2 h^(2^k)) for every fold
+        std::vector<s252::FriChain> hc(1);
+        std::memset(hc.data(), 0, sizeof(s252::FriChain));
+        std::memcpy(hc[0].sponge, transcript->k.lanes(), 200);
+        hc[0].fill = (unsigned)transcript->k.fill();
+        {
+            fe hk = h;
+            for (size_t k = 0; k < L; ++k) { hc[0].inv2h[k] = H::mul(inv2, H::inv(hk)); hk = H::sqr(hk); }
         }
+        Tmp<s252::FriChain> chain(ctx);
+        TRY(dalloc(ctx, &chain.p, 1));
+        CU(ctx, cudaMemcpyAsync(chain.p, hc.data(), sizeof(s252::FriChain), cudaMemcpyHostToDevice, ctx->stream));
+        // ---- layer 0 (fri/mod.rs:33-37)
+        TRY(dalloc(ctx, &f->layers[0].nodes, 4 * (2 * domain_size - 1)));
+        TRY(build_tree(ctx, f->layers[0].evals, domain_size, 1, domain_size, f->layers[0].nodes, chain.p));
+        // ---- folds k = 1..L: fold k turns layer k-1 (size M >> (k-1)) into layer k; committed iff k < L
+        const unsigned tail_log = fri_tail_log_max();
+        size_t k = 1;
+        for (; k <= L && ilog2(domain_size >> (k - 1)) > tail_log; ++k) {
+            const size_t size = domain_size >> (k - 1), half = size / 2;
+            const bool commit = k < L;
+            FriLayerDev nxt;
+            nxt.size = half;
+            TRY(dalloc(ctx, &nxt.evals, half));
+            f->layers.push_back(nxt);
+            FriLayerDev& Lk = f->layers.back();
+            if (commit) TRY(dalloc(ctx, &Lk.nodes, 4 * (2 * half - 1)));
+            prof_begin(ctx, "fri_fold_commit");
+            prof_work(ctx, 32.0 * size + 32.0 * half + (commit ? 32.0 * half : 0.0), 3.2 * half, commit ? (double)half : 0.0);
+            s252::fri_fold_commit<<<(unsigned)((half + 127) / 128), 128, 0, ctx->stream>>>(
+                f->layers[k - 1].evals, half, inv_tw, (unsigned long long)(domain_size / size), fe{}, chain.p, inv2, Lk.evals,
+                commit ? Lk.nodes + 4 * (half - 1) : nullptr);
+            LAUNCH_CHECK(ctx);
+            if (commit) TRY(build_tree_nodes(ctx, half, Lk.nodes, chain.p));
+        }
+        const bool tail = k <= L;
+        if (tail) {
+            s252::FriTail T{};
+            T.chain = chain.p;
+            T.in = f->layers[k - 1].evals;
+            T.log_size = ilog2(domain_size >> (k - 1));
+            T.n_commit = (unsigned)(L - k);
+            T.inv_tw = inv_tw;
+            T.tw_stride = (unsigned long long)(domain_size / (domain_size >> (k - 1)));
+            T.inv2 = inv2;
+            T.inv_last = H::inv(H::from_u64((uint64_t)(domain_size >> L)));
+            double perms = 0, muls = 0;
+            for (size_t j = k; j <= L; ++j) {
+                const size_t half = domain_size >> j;
+                FriLayerDev nxt;
+                nxt.size = half;
+                TRY(dalloc(ctx, &nxt.evals, half));
+                f->layers.push_back(nxt);
+                if (j < L) TRY(dalloc(ctx, &f->layers.back().nodes, 4 * (2 * half - 1)));
+                T.evals[j - k] = f->layers.back().evals;
+                T.nodes[j - k] = f->layers.back().nodes;
+                muls += 3.2 * half;
+                if (j < L) perms += 2.0 * half;
+            }
+            prof_begin(ctx, "fri_tail_kernel");
+            prof_work(ctx, 32.0 * 3 * (domain_size >> (k - 1)), muls, perms);
+            s252::fri_tail_kernel<<<1, s252::FRI_TAIL_THREADS, 0, ctx->stream>>>(T);
+            LAUNCH_CHECK(ctx);
+        }
+        // ---- one read-back: roots, last zeta, last value
+        CU(ctx, cudaMemcpyAsync(hc.data(), chain.p, sizeof(s252::FriChain), cudaMemcpyDeviceToHost, ctx->stream));
+        std::vector<fe> rem;
+        const size_t left = domain_size >> L;
+        if (!tail) {
+            rem.resize(left);
+            CU(ctx, cudaMemcpyAsync(rem.data(), f->layers.back().evals, left * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        // ---- replay on the host transcript (fri/mod.rs:37,41,54,58)
+        fe zeta = H::zero();
+        for (size_t j = 0; j < L; ++j) {
+            if (j > 0) zeta = transcript->to_field();
+            transcript->append(reinterpret_cast<const uint8_t*>(hc[0].roots[j]), 32);
+            if (roots_out) std::memcpy(roots_out + 32 * j, hc[0].roots[j], 32);
+        }
+        zeta = transcript->to_field();
+        if (hc[0].layer != L || !H::eq(zeta, hc[0].zeta)) FAIL(ctx, S252_ERR_CUDA, "internal: the device-side transcript diverged from the host's");
+        if (tail) {
+            lv = hc[0].last_value;
+        } else {
+            // last_value = coefficient 0 of the fully folded polynomial = mean of its evaluations on the remaining
+            // coset (it has at most `left` coefficients because p0 has at most domain_size)
+            fe acc = H::zero();
+            for (size_t i = 0; i < left; ++i) acc = H::add(acc, rem[i]);
+            lv = H::mul(acc, H::inv(H::from_u64((uint64_t)left)));
+        }
+        // the folded remainder is not a FriLayer of the reference: drop it
+        dfree(ctx, f->layers.back().evals);
+        f->layers.pop_back();
     }
-    // last_value = coefficient 0 of the fully folded polynomial = mean of its evaluations on the
-    // remaining coset (it has at most `size` coefficients because p0 has at most domain_size).
-    std::vector<fe> tail(size);
-    CU(ctx, cudaMemcpyAsync(tail.data(), f->layers.back().evals, size * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
-    fe acc = H::zero();
-    for (size_t i = 0; i < size; ++i) acc = H::add(acc, tail[i]);
-    const fe lv = H::mul(acc, H::inv(H::from_u64((uint64_t)size)));
     H::to_lw(lv, last_value->limbs);
     uint8_t be[32];
     H::to_bytes_be(lv, be);
     transcript->append(be, 32);                             // fri/mod.rs:69
-    // the folded tail is not a FriLayer of the reference: drop it
-    dfree(ctx, f->layers.back().evals);
-    f->layers.pop_back();
-    if (number_layers == 0) { dfree(ctx, f->layers.back().evals); f->layers.pop_back(); }
     return S252_OK;
 }
 
@@ -1400,22 +1600,27 @@ extern "C" int s252_generate_nonce_with_grinding(s252_ctx* ctx, const uint8_t ch
     std::memcpy(lanes, challenge, 32);   // little-endian host
     Tmp<unsigned long long> best(ctx);
     TRY(dalloc(ctx, &best.p, 1));
-    // windows grow from 2^16 to 2^26 candidates: small factors finish in one tiny launch
+    CU(ctx, cudaMemsetAsync(best.p, 0xff, 8, ctx->stream));
+    // One persistent launch walks the nonces in batches of grid*256 and drains as soon as every nonce below the
+    // best hit has been tested (grind_kernel); small factors finish in the first batch, factor 20 in ~4 batches.
+    // A launch is bounded to 2^32 candidates; the host relaunches from where it stopped while nothing is found.
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    const unsigned grid = (unsigned)sms * 8;
+    const unsigned long long span = (unsigned long long)grid * 256;
+    const unsigned batches = (unsigned)std::max<unsigned long long>(1, (1ull << 32) / span);
     uint64_t base = 0;
-    unsigned long long window = 1ull << 16;
     while (base < limit) {
-        const unsigned long long count = std::min<unsigned long long>(window, limit - base);
-        CU(ctx, cudaMemsetAsync(best.p, 0xff, 8, ctx->stream));
         prof_begin(ctx, "grind_kernel");
-        s252::grind_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(lanes[0], lanes[1], lanes[2], lanes[3], base, count,
-                                                                                   grinding_factor, best.p);
+        s252::grind_kernel<<<grid, 256, 0, ctx->stream>>>(lanes[0], lanes[1], lanes[2], lanes[3], base, limit, batches, grinding_factor, best.p);
         LAUNCH_CHECK(ctx);
         unsigned long long found;
         CU(ctx, cudaMemcpyAsync(&found, best.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
         CU(ctx, cudaStreamSynchronize(ctx->stream));
         if (found != ~0ull) { *nonce = found; return S252_OK; }
-        base += count;
-        if (window < (1ull << 26)) window <<= 2;
+        const uint64_t next = base + span * batches;
+        if (next <= base) break;                              // wrapped around 2^64
+        base = next;
     }
     FAIL(ctx, S252_ERR_NOT_FOUND, "nonce not found below %llu", (unsigned long long)limit);
 }
