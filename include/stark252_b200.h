@@ -191,6 +191,15 @@ int s252_fri_commit_phase_deep(s252_ctx *ctx, size_t number_layers, s252_commit 
 int s252_fri_commit_phase_evals(s252_ctx *ctx, size_t number_layers, const void *p0_evals, size_t domain_size,
                                 s252_transcript *transcript, uint64_t coset_offset, s252_fri **out, s252_fe *last_value,
                                 uint8_t *roots_out);
+/* Building blocks of a commit phase sharded over several GPUs by row blocks (SURVEY.md section 8e, row 5;
+ * lambdaworks_cairo_prover_b200/fri_distributed.py): one fold of fri/mod.rs:43-51 on the rows [i0, i0+count) of the next
+ * layer with its operands given separately (v[j] = layer_k[i0+j], s[j] = layer_k[i0+j+layer_size/2]; they arrive from
+ * two other GPUs), and the rest of the phase on one GPU from layer `layer_index` on, given in full. */
+int s252_fri_fold_rows(s252_ctx *ctx, const void *v, const void *s, size_t count, size_t i0, size_t layer_size,
+                       size_t domain_size, size_t layer_index, const s252_fe *zeta, uint64_t coset_offset, void *out);
+int s252_fri_commit_phase_from_layer(s252_ctx *ctx, size_t number_layers, const void *evals, size_t layer_size,
+                                     s252_transcript *transcript, uint64_t coset_offset, size_t layer_index, s252_fri **out,
+                                     s252_fe *last_value, uint8_t *roots_out);
 void s252_fri_destroy(s252_fri *f);
 size_t s252_fri_n_layers(const s252_fri *f);
 /* FriLayer.evaluation[first..first+count) of layer k */
@@ -208,6 +217,13 @@ int s252_fri_query(s252_fri *f, const uint64_t *iotas, size_t n_queries, s252_fe
  * Returns the SMALLEST nonce; S252_ERR_NOT_FOUND if none below `limit` (0 = 2^64-1). */
 int s252_generate_nonce_with_grinding(s252_ctx *ctx, const uint8_t challenge[32], uint8_t grinding_factor,
                                       uint64_t limit, uint64_t *nonce);
+
+/* The same search shared by `parts` GPUs (one process per GPU): one round over the window [base, base + 2^32), of
+ * which this GPU tests batches part, part + parts, .. of 2^18 nonces.  *found = this GPU's smallest accepted nonce or
+ * UINT64_MAX.  The caller takes the MIN over the GPUs (an all-reduce) -- that is the reference's nonce -- and calls
+ * again with base + 2^32 if no GPU found one. */
+int s252_grind_round(s252_ctx *ctx, const uint8_t challenge[32], uint8_t grinding_factor, uint64_t base, uint64_t limit,
+                     unsigned part, unsigned parts, uint64_t *found);
 
 /* ByteConversion::to_bytes_be for n elements on the host (the proof's wire format): out = n x 32 bytes. */
 void s252_fe_to_bytes_be(const s252_fe *in, size_t n, uint8_t *out);

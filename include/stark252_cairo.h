@@ -154,6 +154,9 @@ int s252_cairo_constraints_rows(s252_ctx *ctx, const s252_cairo_trace *trace, co
  * interpolate_offset_fft, even/odd split, LDE of H1/H2, batch_commit. */
 int s252_cairo_composition_commit(s252_ctx *ctx, const void *evals, size_t n_rows, size_t blowup, uint64_t coset_offset,
                                   s252_commit **out, uint8_t root[32]);
+/* The same without the tree (a rank of a sharded proof hashes only its own block of rows of (H1, H2)). */
+int s252_cairo_composition_lde(s252_ctx *ctx, const void *evals, size_t n_rows, size_t blowup, uint64_t coset_offset,
+                               s252_commit **out);
 /* The DEEP composition polynomial (prover.rs:410-482 as the verifier's formula, verifier.rs:526-557) on
  * LDE rows [row0, row0+rows): tables[t] = block of table t (trace tables first, (H1, H2) last).
  * Argument meaning as in s252_fri_commit_phase_deep.  out: device, [rows]. */

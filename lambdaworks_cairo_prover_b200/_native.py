@@ -63,12 +63,15 @@ SIGNATURES = {
     "s252_fri_commit_phase_deep": (_i, [_vp, _sz, _vp, _sz, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u64,
                                         C.POINTER(_vp), _vp, _vp]),
     "s252_fri_commit_phase_evals": (_i, [_vp, _sz, _vp, _sz, _vp, _u64, C.POINTER(_vp), _vp, _vp]),
+    "s252_fri_fold_rows": (_i, [_vp, _vp, _vp, _sz, _sz, _sz, _sz, _sz, _vp, _u64, _vp]),
+    "s252_fri_commit_phase_from_layer": (_i, [_vp, _sz, _vp, _sz, _vp, _u64, _sz, C.POINTER(_vp), _vp, _vp]),
     "s252_fri_destroy": (None, [_vp]),
     "s252_fri_n_layers": (_sz, [_vp]),
     "s252_fri_read_layer": (_i, [_vp, _sz, _sz, _sz, _vp]),
     "s252_fri_read_nodes": (_i, [_vp, _sz, _sz, _sz, _vp]),
     "s252_fri_query": (_i, [_vp, _vp, _sz, _vp, _vp, _vp, _vp, _sz]),
     "s252_generate_nonce_with_grinding": (_i, [_vp, _vp, _u8, _u64, C.POINTER(_u64)]),
+    "s252_grind_round": (_i, [_vp, _vp, _u8, _u64, _u64, C.c_uint, C.c_uint, C.POINTER(_u64)]),
     "s252_fe_to_bytes_be": (None, [_vp, _sz, _vp]),
     "s252_keccak256": (None, [_vp, _sz, _vp]),
     "s252_transcript_new": (_vp, []),
@@ -113,6 +116,7 @@ SIGNATURES = {
     "s252_cairo_aux_trace_device": (_i, [_vp, _vp, _vp, _vp, _i, C.POINTER(_vp)]),
     "s252_cairo_constraints_rows": (_i, [_vp, _vp, _vp, _vp, _sz, _sz, _sz, _vp, _vp, _sz, _vp, _vp, _vp, _sz, _u64, _vp]),
     "s252_cairo_composition_commit": (_i, [_vp, _vp, _sz, _sz, _u64, C.POINTER(_vp), _vp]),
+    "s252_cairo_composition_lde": (_i, [_vp, _vp, _sz, _sz, _u64, C.POINTER(_vp)]),
     "s252_deep_rows": (_i, [_vp, _vp, _vp, _vp, _sz, _sz, _sz, _sz, _sz, _vp, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _vp]),
     "s252_cairo_prove": (_i, [_vp, _vp, _sz, _sz, _u64, _u8, C.POINTER(_vp), C.POINTER(_sz)]),
     "s252_cairo_proof_free": (None, [_vp]),
@@ -207,6 +211,10 @@ class Context:
 
     def synchronize(self):
         self.check(lib().s252_ctx_synchronize(self.handle))
+
+    def trim(self):
+        """Return the arena's cached (unused) device blocks to the driver."""
+        self.check(lib().s252_ctx_trim(self.handle))
 
     @property
     def stream(self):

@@ -9,13 +9,16 @@ building blocks of include/stark252_cairo.h).  What is sharded and how:
             built REDUNDANTLY on every rank (1 ms; the 11 main columns it needs are broadcast over NVLink
             by the ranks that hold them) and its 18 columns are then sharded the same way.
   round 2   every rank evaluates the constraints on its row block (the frame's next row for the last
-            `blowup` rows comes from the next rank: a 7 KB halo); the evaluations are all-gathered and
-            rank 0 interpolates H, extends H1/H2 and commits them; root and LDE are broadcast.
+            `blowup` rows comes from the next rank: a 7 KB halo); the evaluations are all-gathered; H is one
+            polynomial of 2N coefficients, so every rank interpolates it and extends H1/H2 itself (2 columns:
+            cheaper than shipping the LDE), but the TREE over the rows of (H1, H2) is sharded like every other
+            tree: each rank hashes its row block, the subtree roots are gathered (prover.rs:254-276).
   round 3   every rank evaluates ITS polynomials at z and z*g; the values are all-gathered.
-  round 4   every rank builds the DEEP composition polynomial on its row block; the blocks are gathered
-            and rank 0 runs FRI, grinding and the query sampling; the trace openings come from the ranks
-            that own the rows.
-Every rank runs the same Fiat-Shamir transcript up to the FRI phase, so no challenge is ever sent.
+  round 4   every rank builds the DEEP composition polynomial on its row block, which is its block of FRI layer 0:
+            the commit phase runs sharded (fri_distributed.py: row-block trees, one pairwise exchange of half a
+            layer per fold, collapse to one GPU once the layers are small), grinding is split over the ranks
+            (MIN all-reduce), and every opening is served by the rank that owns the row.
+Every rank runs the same Fiat-Shamir transcript, so no challenge is ever sent.
 The proof bytes are identical to the single-GPU prover's (tests/test_distributed.py).
 """
 import ctypes as C
@@ -27,6 +30,7 @@ import torch.distributed as dist
 from . import _native as N
 from . import distributed as D
 from . import felt
+from . import fri_distributed as F
 from .merkle import DeviceCommit
 from .transcript import DefaultTranscript, transcript_to_field, transcript_to_usize
 
@@ -69,9 +73,6 @@ class GpuCairoBackend(D.GpuBackend):
     def __init__(self, ctx):
         super().__init__(ctx)
         self.L = N.lib()
-
-    def sync(self):
-        torch.cuda.synchronize(self.device)
 
     # ---- transcript (host)
     def transcript(self):
@@ -159,6 +160,40 @@ class GpuCairoBackend(D.GpuBackend):
                                              N.ptr(ood_flat), N.ptr(np.ascontiguousarray(hz[0])), N.ptr(np.ascontiguousarray(hz[1])),
                                              N.ptr(gamma), N.ptr(gamma_p), N.ptr(tg), opts.coset_offset, C.c_void_p(out.data_ptr())))
 
+    def composition_lde(self, evals, n, opts):
+        """H from its evaluations, H1/H2 coefficients + LDE, no tree: -> (handle, lde[2, M, 4] view of the handle's memory)."""
+        hnd = C.c_void_p()
+        self.ctx.check(self.L.s252_cairo_composition_lde(self.ctx.handle, C.c_void_p(evals.data_ptr()), n, opts.blowup_factor,
+                                                         opts.coset_offset, C.byref(hnd)))
+        return _wrap_lde(self.ctx, hnd, self.device)
+
+    # ---- FRI building blocks (fri_distributed.py)
+    def fri_fold_rows(self, v, s, i0, size, domain_size, k, zeta, coset_offset, out):
+        self.ctx.check(self.L.s252_fri_fold_rows(self.ctx.handle, C.c_void_p(v.data_ptr()), C.c_void_p(s.data_ptr()), v.shape[0], i0, size,
+                                                 domain_size, k, N.ptr(np.ascontiguousarray(zeta)), coset_offset, C.c_void_p(out.data_ptr())))
+
+    def fri_continue(self, evals, n_layers, t, coset_offset, k, domain_size):
+        """The rest of the commit phase on this GPU from layer k (given in full): -> (fri handle, last value LW, roots)."""
+        fri = C.c_void_p()
+        last = np.empty(4, dtype=np.uint64)
+        roots = np.empty((max(n_layers, 1), 32), dtype=np.uint8)
+        self.ctx.check(self.L.s252_fri_commit_phase_from_layer(self.ctx.handle, n_layers, C.c_void_p(evals.data_ptr()), evals.shape[0], t.handle,
+                                                               coset_offset, k, C.byref(fri), N.ptr(last), N.ptr(roots)))
+        return fri, last, roots[:n_layers]
+
+    def release_fri(self, fri):
+        self.L.s252_fri_destroy(fri)
+
+    def grind_round(self, challenge, factor, base, part, parts):
+        found = C.c_uint64()
+        ch = np.frombuffer(challenge, dtype=np.uint8).copy()
+        self.ctx.check(self.L.s252_grind_round(self.ctx.handle, N.ptr(ch), factor, base, 0, part, parts, C.byref(found)))
+        return int(found.value)
+
+    @staticmethod
+    def to_bytes_be(v):
+        return felt.to_bytes_be(v)
+
     def fri_commit_phase_evals(self, p0, layers, t, opts):
         """-> (fri handle, last value LW, roots uint8[layers, 32])"""
         fri = C.c_void_p()
@@ -203,12 +238,35 @@ def _bcast_bytes(data, n, device, group):
     return bytes(t.cpu().numpy().tobytes())
 
 
-def generate_cairo_proof_sharded(trace, options, ctx, group=None, timings=None, exchange="a2a"):
+def generate_cairo_proof_sharded(trace, options, ctx, group=None, timings=None, exchange="a2a", fri_collapse_log=None):
     """trace: the same MainTrace on every rank (lambdaworks_cairo_prover_b200.cairo); ctx: this rank's Context (or a
     backend object with GpuCairoBackend's interface).  Returns StarkProof::serialize() bytes on rank 0 and
-    None on the other ranks."""
-    import time
+    None on the other ranks.  A failure on any rank (an unsatisfied AIR, say) raises on EVERY rank."""
     be = ctx if hasattr(ctx, "main_lde") else GpuCairoBackend(ctx)
+    with D.backend_scope(be):
+        return _prove_sharded(trace, options, be, group, timings, exchange, fri_collapse_log)
+
+
+def _all_ranks_ok(step, be, group):
+    """Runs a rank-local step; if it raises on any rank, every rank raises (instead of the others waiting forever in
+    the next collective)."""
+    err = None
+    try:
+        out = step()
+    except Exception as e:                                   # noqa: BLE001 - re-raised below on every rank
+        err, out = e, None
+    if dist.get_world_size(group) > 1:
+        flag = torch.tensor([1 if err is not None else 0], dtype=torch.int64, device=be.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+        if int(flag.item()) and err is None:
+            err = RuntimeError("a peer rank failed in a rank-local step of the sharded prover")
+    if err is not None:
+        raise err
+    return out
+
+
+def _prove_sharded(trace, options, be, group, timings, exchange, fri_collapse_log):
+    import time
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     device = be.device
     gr = (lambda r: r) if group is None else (lambda r: dist.get_global_rank(group, r))
@@ -263,8 +321,7 @@ def generate_cairo_proof_sharded(trace, options, ctx, group=None, timings=None, 
             aux_in[col - 19].copy_(my_trace[col - my_lo])
         if world > 1:
             dist.broadcast(aux_in[col - 19], src=gr(owner), group=group)
-    be.sync()
-    aux_cols = be.aux_trace(trace, aux_in, rap)
+    aux_cols = _all_ranks_ok(lambda: be.aux_trace(trace, aux_in, rap), be, group)
 
     def aux_lde(lo, hi):
         return be.cols_lde(aux_cols[lo:hi], options)
@@ -293,26 +350,19 @@ def generate_cairo_proof_sharded(trace, options, ctx, group=None, timings=None, 
         for w_ in dist.batch_isend_irecv([dist.P2POp(dist.isend, msend, prv, group), dist.P2POp(dist.isend, asend, prv, group),
                                           dist.P2POp(dist.irecv, mhalo, nxt, group), dist.P2POp(dist.irecv, ahalo, nxt, group)]):
             w_.wait()
-    be.sync()
     evals = be.new_tensor((m, 4))
     mine = evals[rank * rows_per:(rank + 1) * rows_per]
-    be.constraints_rows(trace, mblock, ablock, mhalo, ahalo, rank * rows_per, rap, bco, tco, options, mine)
+    _all_ranks_ok(lambda: be.constraints_rows(trace, mblock, ablock, mhalo, ahalo, rank * rows_per, rap, bco, tco, options, mine), be, group)
     mark("constraints")
     if world > 1:
         dist.all_gather_into_tensor(evals.view(-1), mine.reshape(-1).clone(), group=group)
-        be.sync()
-    comp = None
-    comp_lde = be.new_tensor((2, m, 4))
-    comp_root = None
-    if rank == 0:
-        comp, comp_root = be.composition_commit(evals, n, options, comp_lde)
-        be.sync()
+    # H from its evaluations and the LDE of (H1, H2) on every rank; an H above its degree bound (the trace does not
+    # satisfy the AIR) is detected here, on every rank alike
+    comp, comp_lde = _all_ranks_ok(lambda: be.composition_lde(evals, n, options), be, group)
     del evals
-    if world > 1:
-        comp_root = _bcast_bytes(comp_root, 32, device, group)
-        dist.broadcast(comp_lde, src=gr(0), group=group)
-        be.sync()
-    t.append(comp_root)
+    cblock = comp_lde[:, rank * rows_per:(rank + 1) * rows_per].contiguous()
+    sc_comp = F.commit_row_block(cblock, m, t, be, group)                       # appends the root (prover.rs:635)
+    comp_root = sc_comp.root
     mark("composition")
     # ---- round 3 (prover.rs:650-690)
     hinv = pow(h, -1, P)
@@ -325,14 +375,11 @@ def generate_cairo_proof_sharded(trace, options, ctx, group=None, timings=None, 
     def local_ood(local):
         return np.concatenate([be.evaluate_at(hnd, pts) for hnd in local.handles], axis=1)
     mine_ood = (local_ood(sc_main.local), local_ood(sc_aux.local))
-    hz = np.zeros((2, 4), dtype=np.uint64)
-    if rank == 0:
-        hz = be.evaluate_at(comp, felt.from_ints([z * z % P]))[0]
+    hz = be.evaluate_at(comp, felt.from_ints([z * z % P]))[0]                    # H1(z^2), H2(z^2): every rank holds H1, H2
     if world > 1:
         parts = [None] * world
-        dist.all_gather_object(parts, (mine_ood, hz if rank == 0 else None), group=group)
-        ood = np.concatenate([p_[0][0] for p_ in parts] + [p_[0][1] for p_ in parts], axis=1)        # [2, 52, 4]
-        hz = parts[0][1]
+        dist.all_gather_object(parts, mine_ood, group=group)
+        ood = np.concatenate([p_[0] for p_ in parts] + [p_[1] for p_ in parts], axis=1)        # [2, 52, 4]
     else:
         ood = np.concatenate(mine_ood, axis=1)
     ncols = ood.shape[1]
@@ -345,45 +392,34 @@ def generate_cairo_proof_sharded(trace, options, ctx, group=None, timings=None, 
     # ---- round 4 (prover.rs:327-404)
     gamma, gamma_p = be.to_field(t), be.to_field(t)
     tg = np.stack([be.to_field(t) for _ in range(2 * ncols)])
-    p0 = be.new_tensor((m, 4))
-    mine = p0[rank * rows_per:(rank + 1) * rows_per]
-    be.deep_rows(mblock, ablock, comp_lde, rank * rows_per, n, z, ood, hz, gamma, gamma_p, tg, options, mine)
-    if world > 1:
-        dist.all_gather_into_tensor(p0.view(-1), mine.reshape(-1).clone(), group=group)
-        be.sync()
+    p0_block = be.new_tensor((rows_per, 4))
+    _all_ranks_ok(lambda: be.deep_rows(mblock, ablock, comp_lde, rank * rows_per, n, z, ood, hz, gamma, gamma_p, tg, options, p0_block), be, group)
     mark("deep")
     layers = order
     q_count = options.fri_number_of_queries if layers else 0
-    iotas = np.zeros(max(q_count, 1), dtype=np.uint64)
-    fri = None
-    if rank == 0:
-        fri, last, fri_roots = be.fri_commit_phase_evals(p0, layers, t, options)
-        nonce = be.grind(t.challenge(), options.grinding_factor)
-        t.append(_u64be(nonce))
-        for q in range(q_count):
-            iotas[q] = be.to_usize(t) % m
-    del p0
-    mark("fri_grind")
-    if world > 1:
-        it = torch.from_numpy(iotas.view(np.int64).copy()).to(device)
-        dist.broadcast(it, src=gr(0), group=group)
-        iotas = it.cpu().numpy().view(np.uint64)
-    idx = [int(i) for i in iotas[:q_count]]
-    (main_rows, main_paths), (aux_rows, aux_paths) = D.open_many([sc_main, sc_aux], idx) if q_count else (([], []), ([], []))
-    mark("trace_openings")
+    fri = F.fri_commit_phase_sharded(p0_block, m, layers, t, h, be, group, collapse_log=fri_collapse_log)
+    mark("fri")
+    nonce = F.generate_nonce_with_grinding_sharded(t.challenge(), options.grinding_factor, be, group)
+    t.append(_u64be(nonce))                                                      # prover.rs:385
+    idx = [be.to_usize(t) % m for _ in range(q_count)]                           # every rank samples the same indices
+    mark("grinding")
+    opened = D.open_many([sc_main, sc_aux, sc_comp], idx) if q_count else [([], [])] * 3
+    (main_rows, main_paths), (aux_rows, aux_paths), (comp_rows, comp_paths) = opened
+    fq = F.fri_query_sharded(fri, idx, layers, be, group) if q_count else None
+    mark("openings")
     proof = None
     if rank == 0:
         depth = m.bit_length() - 1
         if q_count:
-            ev, evs, pa, pas = be.fri_query(fri, idx, layers, depth)
-            crow, cpath = be.commit_open(comp, idx, depth)
+            ev, evs, pa, pas = fq
+            crow = np.stack([np.asarray(r_).view(np.uint64).reshape(-1, 4) for r_ in comp_rows])
         bb = lambda a: felt.to_bytes_be_many(np.asarray(a).view(np.uint64).reshape(-1, 4))               # elements -> wire bytes
         u8 = lambda v: np.frombuffer(_u64be(v), dtype=np.uint8)
         const = lambda v: np.tile(u8(v), (q_count, 1))
         out = _u64be(n) + _u64be(2) + sc_main.root + sc_aux.root                 # StarkProof::serialize, proof/stark.rs:161-218
         frame = _u64be(2 * ncols) + _u64be(32) + bb(ood).tobytes() + _u64be(ncols)
         out += _blob(frame) + comp_root + _u64be(32) + bb(hz).tobytes()
-        out += _u64be(layers) + np.ascontiguousarray(fri_roots).tobytes() + bb(last).tobytes() + _u64be(q_count)
+        out += _u64be(layers) + b"".join(fri.roots) + bb(fri.last_value).tobytes() + _u64be(q_count)
         if q_count:
             # every query's blob has the same layout, so all of them are assembled as rows of one byte matrix
             def path_section(paths):                                             # [Q, layers, depth, 32] -> u64(len_k) || path_k for every layer
@@ -401,14 +437,16 @@ def generate_cairo_proof_sharded(trace, options, ctx, group=None, timings=None, 
             as_u8 = lambda paths: np.frombuffer(b"".join(b"".join(bytes(x) for x in p_) for p_ in paths), dtype=np.uint8).reshape(q_count, -1)
             rows52 = np.concatenate([np.stack([np.asarray(r_).view(np.uint64).reshape(-1, 4) for r_ in main_rows]),
                                      np.stack([np.asarray(r_).view(np.uint64).reshape(-1, 4) for r_ in aux_rows])], axis=1)
-            opn = np.concatenate([const(depth), np.ascontiguousarray(cpath).reshape(q_count, -1), const(32), bb(crow).reshape(q_count, -1), const(2),
+            opn = np.concatenate([const(depth), as_u8(comp_paths), const(32), bb(crow).reshape(q_count, -1), const(2),
                                   const(depth), as_u8(main_paths), const(depth), as_u8(aux_paths), const(ncols),
                                   bb(rows52).reshape(q_count, -1)], axis=1)
             out += np.concatenate([const(opn.shape[1]), opn], axis=1).tobytes()
         out += _u64be(nonce)
         proof = out
-        be.release(fri, comp)
     mark("serialize")
+    fri.free(be)
+    comp.free()
+    sc_comp.free()
     sc_main.free()
     sc_aux.free()
     mark("free")

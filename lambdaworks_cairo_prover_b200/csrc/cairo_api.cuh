@@ -576,7 +576,7 @@ extern "C" int s252_cairo_constraint_evaluations(s252_ctx* ctx, const s252_cairo
 // evaluations on the coset (interpolate_offset_fft, evaluation_table.rs:27-33), even/odd split, LDE of H1 and
 // H2, batch_commit.  The handle keeps the H1, H2 coefficients.
 static int cairo_composition_commit(s252_ctx* ctx, const fe* evals, size_t N, size_t blowup, uint64_t coset_offset,
-                                    s252_commit** out, uint8_t root[32]) {
+                                    s252_commit** out, uint8_t root[32], bool with_tree = true) {
     const size_t M = N * blowup;
     s252_commit* cm = new s252_commit();
     cm->ctx = ctx; cm->n_cols = 2; cm->n_rows = M; cm->n_coeffs = N;
@@ -605,9 +605,11 @@ static int cairo_composition_commit(s252_ctx* ctx, const fe* evals, size_t N, si
         // evaluate_polynomial_on_lde_domain(H1), (H2) + batch_commit (prover.rs:254-276)
         TRY(dalloc(ctx, &cm->lde, 2 * M));
         TRY(evaluate_cosets(ctx, cm->coeffs, N, false, ilog2(N), (unsigned)blowup, H::from_u64(coset_offset), cm->lde, M, false, 2));
-        TRY(dalloc(ctx, &cm->nodes, 4 * (2 * M - 1)));
-        TRY(build_tree(ctx, cm->lde, M, 2, M, cm->nodes));
-        TRY(fetch_root(ctx, cm->nodes, root));
+        if (with_tree) {
+            TRY(dalloc(ctx, &cm->nodes, 4 * (2 * M - 1)));
+            TRY(build_tree(ctx, cm->lde, M, 2, M, cm->nodes));
+            TRY(fetch_root(ctx, cm->nodes, root));
+        }
         return S252_OK;
     }();
     if (rc != S252_OK) { commit_free(cm); return rc; }
@@ -721,6 +723,15 @@ extern "C" int s252_cairo_composition_commit(s252_ctx* ctx, const void* evals, s
     CU(ctx, cudaSetDevice(ctx->device));
     if (!is_pow2(n_rows) || !is_pow2(blowup) || coset_offset == 0) FAIL(ctx, S252_ERR_INVALID, "bad composition shape");
     return cairo_composition_commit(ctx, reinterpret_cast<const fe*>(evals), n_rows, blowup, coset_offset, out, root);
+}
+// The same without the tree: H1/H2 coefficients + their LDE (a rank of a sharded proof hashes only its own rows).
+extern "C" int s252_cairo_composition_lde(s252_ctx* ctx, const void* evals, size_t n_rows, size_t blowup, uint64_t coset_offset,
+                                          s252_commit** out) {
+    if (!ctx || !evals || !out) return S252_ERR_INVALID;
+    *out = nullptr;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (!is_pow2(n_rows) || !is_pow2(blowup) || coset_offset == 0) FAIL(ctx, S252_ERR_INVALID, "bad composition shape");
+    return cairo_composition_commit(ctx, reinterpret_cast<const fe*>(evals), n_rows, blowup, coset_offset, out, nullptr, false);
 }
 extern "C" int s252_deep_rows(s252_ctx* ctx, const void* const* tables, const size_t* strides, const size_t* n_cols, size_t n_tables,
                               size_t row0, size_t rows, size_t lde_rows, size_t trace_rows, const s252_fe* z,

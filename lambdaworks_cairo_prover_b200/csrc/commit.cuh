@@ -335,6 +335,16 @@ __global__ void __launch_bounds__(128) fri_fold_commit(const fe* __restrict__ la
     }
 }
 
+// The fold on a block of rows of the next layer, operands given separately (a rank of a sharded FRI: v and s arrive
+// from the two ranks that hold layer[i] and layer[i + size/2]): out[j] = fold(v[j], s[j]) for row i0 + j.
+__global__ void __launch_bounds__(128) fri_fold_rows_kernel(const fe* __restrict__ v, const fe* __restrict__ s, unsigned long long count,
+                                                            const fe* __restrict__ inv_tw, unsigned long long tw_stride,
+                                                            unsigned long long i0, fe c, fe inv2, fe* __restrict__ out) {
+    const unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    st_fe(out + j, fri_fold_value(ld_fe(v + j), ld_fe(s + j), ldg_fe(inv_tw + (i0 + j) * tw_stride), c, inv2));
+}
+
 // The tail of the commit phase in ONE block: once a layer has at most FRI_TAIL_MAX evaluations, every remaining
 // fold, leaf hash, tree, transcript step and the final  last_value = mean of the last evaluations  (fri/mod.rs:43-69)
 // run here back to back -- a launch + root read-back per layer costs more than these layers' arithmetic.
@@ -433,12 +443,16 @@ __device__ __forceinline__ bool grind_accepts(uint64_t c0, uint64_t c1, uint64_t
 // thread leaves only when its batch starts above the best nonce found so far, so every nonce below the reported
 // one has been tested by the time the grid drains: the result is the minimum, as in the sequential search.
 // `batches` bounds the launch (the host relaunches from where it stopped if nothing was found).
+// Several GPUs share one search by taking the batches round-robin: GPU `part` of `parts` tests batches
+// part, part + parts, ..; the minimum over the GPUs' results is the global minimum (a GPU only skips batches
+// that lie above a hit of its own).
 __global__ void __launch_bounds__(256) grind_kernel(uint64_t c0, uint64_t c1, uint64_t c2, uint64_t c3, uint64_t base,
-                                                   uint64_t limit, unsigned batches, unsigned factor,
-                                                   unsigned long long* __restrict__ best) {
+                                                   uint64_t limit, unsigned batches, unsigned part, unsigned parts,
+                                                   unsigned factor, unsigned long long* __restrict__ best) {
     const unsigned long long span = (unsigned long long)gridDim.x * blockDim.x;
-    uint64_t start = base;
-    for (unsigned b = 0; b < batches; ++b, start += span) {
+    for (unsigned b = 0; b < batches; ++b) {
+        const unsigned long long off = ((unsigned long long)b * parts + part) * span;
+        const uint64_t start = base + off;
         if (start >= limit || start < base) break;                               // end of range / wrapped around 2^64
         if (*(volatile unsigned long long*)best < start) break;
         const uint64_t nonce = start + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;

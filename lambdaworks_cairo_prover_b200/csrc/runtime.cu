@@ -1521,6 +1521,60 @@ extern "C" int s252_fri_commit_phase_evals(s252_ctx* ctx, size_t number_layers, 
     *out = f;
     return S252_OK;
 }
+// fri_commit_phase continued from layer `layer_index` (a sharded commit phase collapses to one GPU once the
+// layers are small): evals = the layer_size evaluations of that layer on the coset h^(2^layer_index) <w_layer_size>,
+// resident on this device (internal format); number_layers = layers still to commit, this one included.  The
+// transcript must be in the state the reference's is in before it appends this layer's root.
+extern "C" int s252_fri_commit_phase_from_layer(s252_ctx* ctx, size_t number_layers, const void* evals, size_t layer_size,
+                                                s252_transcript* transcript, uint64_t coset_offset, size_t layer_index, s252_fri** out,
+                                                s252_fe* last_value, uint8_t* roots_out) {
+    if (!ctx || !evals || !transcript || !out || !last_value) return S252_ERR_INVALID;
+    *out = nullptr;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (!is_pow2(layer_size) || number_layers > ilog2(layer_size) || coset_offset == 0 || layer_index >= 64) FAIL(ctx, S252_ERR_INVALID, "bad domain sizes for FRI");
+    fe hk = H::from_u64(coset_offset);
+    for (size_t j = 0; j < layer_index; ++j) hk = H::sqr(hk);
+    s252_fri* f = new s252_fri();
+    f->ctx = ctx; f->domain_size = layer_size;
+    int rc = [&]() -> int {
+        FriLayerDev cur;
+        cur.size = layer_size;
+        TRY(dalloc(ctx, &cur.evals, layer_size));
+        f->layers.push_back(cur);
+        CU(ctx, cudaMemcpyAsync(f->layers[0].evals, evals, layer_size * sizeof(fe), cudaMemcpyDeviceToDevice, ctx->stream));
+        return fri_from_layer0(ctx, f, number_layers, transcript, hk, layer_size, last_value, roots_out);
+    }();
+    if (rc != S252_OK) { fri_free(f); return rc; }
+    *out = f;
+    return S252_OK;
+}
+// One fold of the commit phase on a block of rows (fri/mod.rs:43-51 as the verifier's formula, verifier.rs:511-512):
+// out[j] = (v[j] + s[j])/2 + zeta (v[j] - s[j]) / (2 h_k w^(i0+j)),  v[j] = layer_k[i0 + j], s[j] = layer_k[i0 + j + layer_size/2],
+// h_k = coset_offset^(2^k), w of order layer_size = domain_size >> k.  v, s, out: device, internal format, `count` elements.
+extern "C" int s252_fri_fold_rows(s252_ctx* ctx, const void* v, const void* s, size_t count, size_t i0, size_t layer_size,
+                                  size_t domain_size, size_t layer_index, const s252_fe* zeta, uint64_t coset_offset, void* out) {
+    if (!ctx || !v || !s || !zeta || !out) return S252_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (!is_pow2(layer_size) || layer_size < 2 || i0 + count > layer_size / 2 || coset_offset == 0 || layer_index >= 64 ||
+        (layer_size << layer_index) != domain_size)
+        FAIL(ctx, S252_ERR_INVALID, "bad FRI fold block");
+    if (count == 0) return S252_OK;
+    fe hk = H::from_u64(coset_offset);
+    for (size_t j = 0; j < layer_index; ++j) hk = H::sqr(hk);
+    fe w;
+    H::primitive_root(ilog2(domain_size), &w);
+    const fe* inv_tw;                                       // w_domain^(-i): the table the single-GPU path uses, stride domain/layer
+    TRY(get_power_table(ctx, domain_size / 2, H::inv(w), H::one(), &inv_tw));
+    const fe inv2 = H::inv(H::from_u64(2));
+    const fe cfac = H::mul(H::from_lw(zeta->limbs), H::mul(inv2, H::inv(hk)));
+    prof_begin(ctx, "fri_fold_rows");
+    prof_work(ctx, 96.0 * count, 3.2 * count, 0);
+    s252::fri_fold_rows_kernel<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(
+        reinterpret_cast<const fe*>(v), reinterpret_cast<const fe*>(s), count, inv_tw, (unsigned long long)(domain_size / layer_size), i0, cfac,
+        inv2, reinterpret_cast<fe*>(out));
+    LAUNCH_CHECK(ctx);
+    return S252_OK;
+}
 extern "C" void s252_fri_destroy(s252_fri* f) {
     if (!f) return;
     cudaSetDevice(f->ctx->device);
@@ -1590,39 +1644,57 @@ extern "C" int s252_fri_query(s252_fri* f, const uint64_t* iotas, size_t n_queri
 
 // --------------------------------------------------------------------------------------------
 // grinding
+// One round of the search: the window [base, base + 2^32) in batches of 2^18 nonces, of which this GPU takes
+// batches part, part + parts, ...  *found = smallest accepted nonce of this GPU's batches (~0: none).
+static const unsigned GRIND_GRID = 1024;                       // x 256 threads = 2^18 nonces per batch
+static const unsigned GRIND_BATCHES = 1u << 14;                // per round, over all parts
+static int grind_round(s252_ctx* ctx, const uint8_t challenge[32], uint8_t grinding_factor, uint64_t base, uint64_t limit,
+                       unsigned part, unsigned parts, uint64_t* found) {
+    uint64_t lanes[4];
+    std::memcpy(lanes, challenge, 32);   // little-endian host
+    Tmp<unsigned long long> best(ctx);
+    TRY(dalloc(ctx, &best.p, 1));
+    CU(ctx, cudaMemsetAsync(best.p, 0xff, 8, ctx->stream));
+    const uint64_t window_end = base + (1ull << 32) > base ? std::min<uint64_t>(limit, base + (1ull << 32)) : limit;
+    prof_begin(ctx, "grind_kernel");
+    s252::grind_kernel<<<GRIND_GRID, 256, 0, ctx->stream>>>(lanes[0], lanes[1], lanes[2], lanes[3], base, window_end,
+                                                            (GRIND_BATCHES + parts - 1) / parts, part, parts, grinding_factor, best.p);
+    LAUNCH_CHECK(ctx);
+    unsigned long long f;
+    CU(ctx, cudaMemcpyAsync(&f, best.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    *found = f;
+    return S252_OK;
+}
 extern "C" int s252_generate_nonce_with_grinding(s252_ctx* ctx, const uint8_t challenge[32], uint8_t grinding_factor,
                                                  uint64_t limit, uint64_t* nonce) {
     if (!ctx || !challenge || !nonce) return S252_ERR_INVALID;
     CU(ctx, cudaSetDevice(ctx->device));
     if (grinding_factor > 64) FAIL(ctx, S252_ERR_NOT_FOUND, "a 64-bit head cannot have %u trailing zeros", grinding_factor);
     if (limit == 0) limit = ~0ull;   // the reference searches 0..u64::MAX
-    uint64_t lanes[4];
-    std::memcpy(lanes, challenge, 32);   // little-endian host
-    Tmp<unsigned long long> best(ctx);
-    TRY(dalloc(ctx, &best.p, 1));
-    CU(ctx, cudaMemsetAsync(best.p, 0xff, 8, ctx->stream));
-    // One persistent launch walks the nonces in batches of grid*256 and drains as soon as every nonce below the
-    // best hit has been tested (grind_kernel); small factors finish in the first batch, factor 20 in ~4 batches.
-    // A launch is bounded to 2^32 candidates; the host relaunches from where it stopped while nothing is found.
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-    const unsigned grid = (unsigned)sms * 8;
-    const unsigned long long span = (unsigned long long)grid * 256;
-    const unsigned batches = (unsigned)std::max<unsigned long long>(1, (1ull << 32) / span);
+    // One persistent launch per 2^32-nonce window: the grid walks it in batches and drains as soon as every nonce
+    // below the best hit has been tested (grind_kernel); factor 20 finishes in ~4 batches of the first window.
     uint64_t base = 0;
     while (base < limit) {
-        prof_begin(ctx, "grind_kernel");
-        s252::grind_kernel<<<grid, 256, 0, ctx->stream>>>(lanes[0], lanes[1], lanes[2], lanes[3], base, limit, batches, grinding_factor, best.p);
-        LAUNCH_CHECK(ctx);
-        unsigned long long found;
-        CU(ctx, cudaMemcpyAsync(&found, best.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        uint64_t found;
+        TRY(grind_round(ctx, challenge, grinding_factor, base, limit, 0, 1, &found));
         if (found != ~0ull) { *nonce = found; return S252_OK; }
-        const uint64_t next = base + span * batches;
-        if (next <= base) break;                              // wrapped around 2^64
-        base = next;
+        if (base + (1ull << 32) <= base) break;               // wrapped around 2^64
+        base += 1ull << 32;
     }
     FAIL(ctx, S252_ERR_NOT_FOUND, "nonce not found below %llu", (unsigned long long)limit);
+}
+// The same search shared by `parts` GPUs (disjoint nonce ranges + a `min` all-reduce): one round over the
+// window [base, base + 2^32) of which this GPU tests its round-robin share of the 2^18-nonce batches.  *found is this
+// GPU's smallest accepted nonce or UINT64_MAX; the caller takes the minimum over the GPUs and, if none found
+// anything, calls again with base + 2^32.  The minimum over the parts is the reference's nonce (grinding.rs:44-47).
+extern "C" int s252_grind_round(s252_ctx* ctx, const uint8_t challenge[32], uint8_t grinding_factor, uint64_t base, uint64_t limit,
+                                unsigned part, unsigned parts, uint64_t* found) {
+    if (!ctx || !challenge || !found || parts == 0 || part >= parts) return S252_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (grinding_factor > 64) FAIL(ctx, S252_ERR_NOT_FOUND, "a 64-bit head cannot have %u trailing zeros", grinding_factor);
+    if (limit == 0) limit = ~0ull;
+    return grind_round(ctx, challenge, grinding_factor, base, limit, part, parts, found);
 }
 
 // --------------------------------------------------------------------------------------------

@@ -12,7 +12,12 @@ the same authentication paths as the single-GPU (and the reference's) tree.
 
 torch.distributed is the plumbing (NCCL over NVLink on GPUs; gloo in the CPU tests, where the two
 compute steps are injected).  The compute steps are the library's own kernels through the C ABI.
+
+Ordering between the library's kernels and the collectives is by stream, never by a device-wide synchronisation:
+the orchestration runs with the library's stream as torch's current stream (GpuBackend.scope()), so NCCL waits for
+the kernels queued before it and the kernels queued after it wait for NCCL, while the host runs ahead.
 """
+import contextlib
 import ctypes as C
 
 import numpy as np
@@ -80,7 +85,12 @@ class GpuBackend:
     def __init__(self, ctx):
         self.ctx = ctx
         self.device = torch.device("cuda", ctx.device)
+        self.stream = torch.cuda.ExternalStream(ctx.stream, device=self.device)
         self._staging = {}
+
+    def scope(self):
+        """Everything torch does inside (copies, allocations, NCCL collectives) is ordered on the library's stream."""
+        return torch.cuda.stream(self.stream)
 
     def _wrap(self, h, n_rows, n_cols, blowup):
         commit = DeviceCommit.__new__(DeviceCommit)
@@ -139,9 +149,14 @@ class GpuBackend:
         return commit, root.tobytes()
 
     def before_collective(self):
-        self.ctx.synchronize()          # the library's stream -> visible to NCCL's stream
+        pass                            # stream-ordered: see scope()
 
     def after_collective(self):
+        pass
+
+    def sync(self):
+        """Host waits for this rank's queue (timing marks only)."""
+        self.ctx.synchronize()
         torch.cuda.synchronize(self.device)
 
     def open_block(self, block, local_idx):
@@ -212,17 +227,20 @@ class ShardedCommit:
                 h.free()
 
 
-def open_many(commits, indices):
-    """ShardedCommit.open for several commits over the same row partition with ONE exchange: returns
-    [(rows, paths), ...] in the order of `commits`."""
+def open_many(commits, indices, index_lists=None):
+    """ShardedCommit.open for several commits with ONE exchange: returns [(rows, paths), ...] in the order of
+    `commits`.  indices: the same positions for every commit (tables over one row partition), or index_lists: one
+    list of positions per commit (FRI layers: iota mod the layer size and its symmetric)."""
     first = commits[0]
     world = dist.get_world_size(first.group)
     rank = dist.get_rank(first.group)
-    rows_per = first.n_rows // world
-    mine = [(q, i % rows_per) for q, i in enumerate(indices) if i // rows_per == rank]
+    if index_lists is None:
+        index_lists = [indices] * len(commits)
     part = {}
-    if mine:
-        for ci, sc in enumerate(commits):
+    for ci, sc in enumerate(commits):
+        rows_per = sc.n_rows // world
+        mine = [(q, i % rows_per) for q, i in enumerate(index_lists[ci]) if i // rows_per == rank]
+        if mine:
             rows, paths = sc.backend.open_block(sc.block, [i for _, i in mine])
             for k, (q, _) in enumerate(mine):
                 part[(ci, q)] = (np.asarray(rows[k]).copy(), [bytes(np.asarray(p).tobytes()) for p in paths[k]])
@@ -237,7 +255,8 @@ def open_many(commits, indices):
     out = []
     for ci, sc in enumerate(commits):
         out_rows, out_paths = [], []
-        for q, i in enumerate(indices):
+        rows_per = sc.n_rows // world
+        for q, i in enumerate(index_lists[ci]):
             rows, path = merged[(ci, q)]
             node = (world - 1) + i // rows_per
             while node != 0:
@@ -288,7 +307,12 @@ def interpolate_and_commit_sharded(shard_table, n_rows, n_cols_total, blowup, co
     else:
         producer = iter([backend.lde(shard_table, n_rows, c_mine, blowup, coset_offset)])
 
-    return exchange_and_commit(producer, ranges, shards, m, n_cols_total, transcript, backend, group, exchange=exchange)
+    with backend_scope(backend):
+        return exchange_and_commit(producer, ranges, shards, m, n_cols_total, transcript, backend, group, exchange=exchange)
+
+
+def backend_scope(backend):
+    return backend.scope() if hasattr(backend, "scope") else contextlib.nullcontext()
 
 
 def exchange_and_commit(producer, ranges, shards, m, n_cols_total, transcript, backend, group=None, exchange="p2p", timings=None):
@@ -308,7 +332,8 @@ def exchange_and_commit(producer, ranges, shards, m, n_cols_total, transcript, b
 
     def mark(name):
         if timings is not None:
-            backend.after_collective()
+            if hasattr(backend, "sync"):
+                backend.sync()
             now = time.perf_counter()
             timings[name] = timings.get(name, 0.0) + (now - clock[0]) * 1e3
             clock[0] = now

@@ -138,6 +138,53 @@ class OracleCairoBackend:
         hnd.lde, hnd.nodes = lde, nodes
         return hnd, root
 
+    def composition_lde(self, evals, n, opts):
+        off = O.fe_from_u64(opts.coset_offset)
+        hco = O.interpolate_offset_fft(_a(evals), off)
+        assert not hco[2 * n:].any(), "composition polynomial exceeds its degree bound"
+        h1, h2 = np.ascontiguousarray(hco[0:2 * n:2]), np.ascontiguousarray(hco[1:2 * n:2])
+        lde = np.stack([O.evaluate_polynomial_on_lde_domain(h1, opts.blowup_factor, n, off),
+                        O.evaluate_polynomial_on_lde_domain(h2, opts.blowup_factor, n, off)])
+        return _Handle(np.stack([h1, h2]), 2), _t(lde)
+
+    # ---- FRI building blocks (fri_distributed.py)
+    def fri_fold_rows(self, v, s, i0, size, domain_size, k, zeta, coset_offset, out):
+        w = O.lw_to_int(O.primitive_root(size.bit_length() - 1))
+        hk = pow(coset_offset, 1 << k, P)
+        z = O.lw_to_int(zeta)
+        inv2 = pow(2, -1, P)
+        va, sa = _a(v), _a(s)
+        res = np.zeros((va.shape[0], 4), dtype=np.uint64)
+        for j in range(va.shape[0]):
+            a, b = O.lw_to_int(va[j]), O.lw_to_int(sa[j])
+            x = hk * pow(w, i0 + j, P) % P
+            res[j] = O.int_to_lw(((a + b) * inv2 + z * (a - b) * pow(2 * x, -1, P)) % P)
+        out.copy_(_t(res))
+
+    def fri_continue(self, evals, n_layers, t, coset_offset, k, domain_size):
+        size = evals.shape[0]
+        off = O.int_to_lw(pow(coset_offset, 1 << k, P))
+        coeffs = O.interpolate_offset_fft(_a(evals), off)
+        nz = np.nonzero(coeffs.any(axis=1))[0]
+        coeffs = coeffs[: (nz[-1] + 1 if nz.size else 0)]
+        last, roots, ev, nodes = O.fri_commit_phase(n_layers, coeffs, t, off, size)
+        return (ev, nodes), last, roots
+
+    def release_fri(self, fri):
+        pass
+
+    def grind_round(self, challenge, factor, base, part, parts):
+        batch = 1 << 18
+        for b in range(part, 1 << 14, parts):
+            for nonce in range(base + b * batch, base + (b + 1) * batch):
+                if O.grinding_zeros(challenge, nonce) >= factor:
+                    return nonce
+        return (1 << 64) - 1
+
+    @staticmethod
+    def to_bytes_be(v):
+        return O.fe_to_bytes_be(v)
+
     # ---- round 4: the DEEP polynomial on a row block (verifier.rs:526-557)
     def deep_rows(self, mblock, ablock, comp_lde, row0, n, z, ood, hz, gamma, gamma_p, tg, opts, out):
         b, h = opts.blowup_factor, opts.coset_offset

@@ -25,8 +25,11 @@ def main_gloo(fib_n, opts):
     regs, mem, size = cairo.run_program(cairo.fibonacci_program(fib_n))
     trace = cairo.build_main_trace(regs, mem, size)
     table = np.array(trace.table).reshape(trace.n_rows(), trace.n_cols, 4)
-    for exchange in ("a2a", "p2p"):
-        proof = generate_cairo_proof_sharded(trace, opts, OracleCairoBackend(table, trace.pub_inputs), exchange=exchange)
+    # fri_collapse_log 2: FRI layers stay sharded (row-block trees, pairwise fold exchange) down to 8 evaluations;
+    # None: the default threshold, far above these sizes, so the whole commit phase runs on rank 0 after one gather
+    for exchange, collapse in (("a2a", 2), ("p2p", None), ("p2p", 4)):
+        proof = generate_cairo_proof_sharded(trace, opts, OracleCairoBackend(table, trace.pub_inputs), exchange=exchange,
+                                             fri_collapse_log=collapse)
         if rank == 0:
             want = cairo_prove(table, trace.pub_inputs, opts, threads=1).serialize()
             assert proof == want, "sharded proof differs from the oracle's (%d vs %d bytes)" % (len(proof), len(want))
@@ -50,12 +53,13 @@ def main():
     ctx = P.Context(local)
     regs, mem, size = cairo.run_program(cairo.fibonacci_program(fib_n))
     trace = cairo.build_main_trace(regs, mem, size)
-    proof = generate_cairo_proof_sharded(trace, opts, ctx)
-    if rank == 0:
-        want = cairo.generate_cairo_proof(trace, opts, ctx)
-        assert proof == want, "sharded proof differs from the single-GPU proof (%d vs %d bytes)" % (len(proof), len(want))
-    else:
-        assert proof is None
+    want = cairo.generate_cairo_proof(trace, opts, ctx) if rank == 0 else None
+    for collapse in (None, 5, 9):
+        proof = generate_cairo_proof_sharded(trace, opts, ctx, fri_collapse_log=collapse)
+        if rank == 0:
+            assert proof == want, "sharded proof differs from the single-GPU proof (%d vs %d bytes)" % (len(proof), len(want))
+        else:
+            assert proof is None
     dist.barrier()
     if rank == 0:
         print("DIST_CAIRO_OK", dist.get_world_size(), trace.n_rows(), len(proof))
