@@ -351,9 +351,20 @@ def run_gpu(args):
             line["cairo_prove"] = cairo_line
             if not args.no_cpu_baseline and world == 1:
                 line["cairo_prove"]["cpu_baseline"] = cpu_cairo_prove_sample(args.cpu_fib_n)
-        print(json.dumps(line))
     for p in list(dev.values()) + [q for s in staging for q in s.values()]:
         ctx.device_free(p)
+    if rank == 0:
+        if world == 1 and not args.no_c4:
+            # the strong-scaling workload of the N > 1 runs (ONE C4 commit) on this one GPU: the N = 1 point of that curve
+            ctx.trim()
+            try:
+                res = subprocess.run([sys.executable, os.path.abspath(__file__), "--mode", "sharded", "--steps", "3", "--warmup", "3", "--no-cairo"],
+                                     capture_output=True, text=True, timeout=900)
+                c4 = json.loads(res.stdout.strip().splitlines()[-1])
+                line["c4_one_gpu"] = {k: c4[k] for k in ("value", "unit", "ms_per_step", "scaling", "parity_ok", "e2e", "stages_ms", "config", "result")}
+            except Exception as e:
+                line["c4_one_gpu"] = {"error": "%s: %s" % (type(e).__name__, e)}
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -447,106 +458,221 @@ def cpu_cairo_prove_sample(fib_n):
                       "(C kernels, python round structure; LDE and constraint evaluation threaded)" % (fib_n, rows.bit_length() - 1)}
 
 
-def run_gpu_sharded(args):
-    """ONE C2 trace on N GPUs: columns of the main and aux tables are sharded (LDE without
-    communication, all-to-all to row blocks, per-GPU subtrees, roots gathered); the 2-column round-2
-    commit, FRI and grinding run on rank 0.  Strong scaling."""
-    import ctypes as C
+C4_LOG_N, C4_COLS, C4_BLOWUP, C4_SEED = 22, 33, 8, 0xB2040000
 
+
+def c4_config(log_n, world):
+    n = 1 << log_n
+    m = n * C4_BLOWUP
+    return {
+        "workload": "C4 (BASELINE configs[3]): ONE interpolate_and_commit of a synthetic 2^%d-row x %d-column Cairo-layout trace, blowup %d, "
+                    "columns sharded over %d GPU(s)" % (log_n, C4_COLS, C4_BLOWUP, world),
+        "trace_rows": n, "lde_rows": m, "columns": [C4_COLS], "blowup": C4_BLOWUP, "coset_offset": OFFSET, "elems_per_step": m * C4_COLS,
+        "l2_policy": "inputs and outputs of every kernel exceed L2 (126 MB); no flush needed",
+        "parallelism": "one trace: columns sharded for iNTT + coset LDE (no communication), all-to-all (grouped NCCL point-to-point chunks, "
+                       "pipelined per column group under the LDE of the next group) to row blocks, per-GPU leaf hashing + subtree, subtree roots "
+                       "all-gathered, top levels on every rank",
+    }
+
+
+def golden_case(name):
+    try:
+        return json.load(open(os.path.join(ROOT, "tests", "golden", "synthetic", "big_configs.json")))["cases"].get(name)
+    except Exception:
+        return None
+
+
+def run_gpu_sharded(args):
+    """N > 1 (default): ONE trace on N GPUs, strong scaling -- the C4 commit (north_star's 2^22-row target), then ONE Cairo
+    proof sharded over the same GPUs.  `value`: shards resident in HBM when the timed region starts; `e2e`: pinned host shards, upload
+    inside.  The root must equal the one the CPU oracle pinned offline (tests/golden/synthetic/big_configs.json)."""
     import torch
     import torch.distributed as dist
 
     import lambdaworks_cairo_prover_b200 as P
-    from lambdaworks_cairo_prover_b200 import _native as N, felt
     from lambdaworks_cairo_prover_b200 import distributed as D
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from util import random_felts
 
-    world, rank, local_rank = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
+    world, rank, local_rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    log_n = args.log_n
-    cfg = workload_config(log_n)
-    cfg["parallelism"] = "one trace, columns sharded over %d GPUs; all-to-all (NCCL) before leaf hashing; FRI on rank 0" % world
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%d" % (29400 + os.getpid() % 500), rank=0, world_size=1,
+                                device_id=torch.device("cuda", local_rank))
+    log_n = args.c4_log_n
+    cfg = c4_config(log_n, world)
     n, m = cfg["trace_rows"], cfg["lde_rows"]
     ctx = P.Context(local_rank)
     backend = D.GpuBackend(ctx)
-    L = N.lib()
     stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
-    seed = 0xB200 + 2
-    shards = {}
-    for key, sd, cols in (("main", seed, COLS_MAIN), ("aux", seed + 1, COLS_AUX)):
-        a, b = D.column_shards(cols, world)[rank]
-        full = splitmix_felts(sd, n * cols).reshape(n, cols, 4)
-        t = torch.empty((n * (b - a) * 32,), dtype=torch.uint8, pin_memory=True)
-        t.numpy()[:] = np.ascontiguousarray(full[:, a:b]).reshape(-1).view(np.uint8)
-        shards[key] = (t, b - a, cols)
-        del full
-    comp = splitmix_felts(seed + 2, n * COLS_COMP)
-    p0 = splitmix_felts(seed + 3, n)
-    offset_fe = felt.from_int(OFFSET)
+    a, b = D.column_shards(C4_COLS, world)[rank]
+    groups = max(1, min(args.pipeline_groups, b - a))
+    ranges = D.group_ranges(b - a, groups)
+    host, dev = [], []
+    for lo, hi in ranges:                                     # TraceTable::get_cols per pipeline group (set-up, not timed)
+        t = torch.empty((n, hi - lo, 4), dtype=torch.int64, pin_memory=True)
+        v = t.numpy().view(np.uint64)
+        for j in range(lo, hi):
+            v[:, j - lo, :] = random_felts(C4_SEED + a + j, n)
+        host.append(t)
+        dev.append(t.to(torch.device("cuda", local_rank)))
 
-    def step():
+    def step(tables, timings=None):
         tr = P.DefaultTranscript()
-        keep = []
-        for key in ("main", "aux"):
-            t, c_mine, cols = shards[key]
-            sc = D.interpolate_and_commit_sharded(t.numpy().view(np.uint64).reshape(-1, 4), n, cols, BLOWUP, OFFSET, tr, backend)
-            keep.append(sc)
-        result = None
-        if rank == 0:
-            h = C.c_void_p()
-            root = np.empty(32, dtype=np.uint8)
-            ctx.check(L.s252_lde_and_commit(ctx.handle, N.ptr(comp), n, COLS_COMP, n, BLOWUP, OFFSET, N.HOST, C.byref(h), N.ptr(root)))
-            tr.append(root.tobytes())
-            fh = C.c_void_p()
-            last = np.empty(4, dtype=np.uint64)
-            roots = np.empty((log_n, 32), dtype=np.uint8)
-            ctx.check(L.s252_fri_commit_phase(ctx.handle, log_n, N.ptr(p0), n, tr.handle, N.ptr(offset_fe), m, N.HOST,
-                                              C.byref(fh), N.ptr(last), N.ptr(roots)))
-            nonce = P.generate_nonce_with_grinding(tr.challenge(), GRIND, ctx)
-            L.s252_commit_destroy(h)
-            L.s252_fri_destroy(fh)
-            result = (roots[-1].tobytes(), nonce)
-        for sc in keep:
-            sc.free()
-        return result
+        shards = D.column_shards(C4_COLS, world)
+        all_ranges = [D.group_ranges(hi - lo, groups) for lo, hi in shards]
+        with D.backend_scope(backend):
+            sc = D.exchange_and_commit(backend.lde_pipeline(tables, n, C4_BLOWUP, OFFSET), all_ranges, shards, m, C4_COLS, tr, backend,
+                                       exchange="p2p", timings=timings)
+        root = sc.root
+        sc.free()
+        return root
 
-    for _ in range(args.warmup):
-        step()
-    dist.barrier()
-    torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(tables, steps, warmup, profile):
+        for _ in range(warmup):
+            step(tables)
+        barrier()
+        if profile:
+            ctx.profile(True, reset=True)
+        launches0 = ctx.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler = ClockSampler(local_rank)
+        if rank == 0 and profile:
+            sampler.start()
+        t0 = time.perf_counter()
+        e0.record(stream)
+        root = None
+        for _ in range(steps):
+            root = step(tables)
+        e1.record(stream)
+        ctx.synchronize()
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        sampler.stop_flag = True
+        ms = e0.elapsed_time(e1)
+        prof = ctx.profile_read() if profile else None
+        if profile:
+            ctx.profile(False)
+        tt = torch.tensor([ms, wall], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        if rank == 0 and profile:
+            sampler.join(timeout=2)
+        return float(tt[0].item()), float(tt[1].item()), root, prof, ctx.launch_count - launches0, sampler.summary()
+
+    ms_dev, wall_dev, root, prof, launches, clocks = timed(dev, args.steps, args.warmup, True)
+    e2e_steps = max(1, min(args.steps, 3))
+    ms_e2e, wall_e2e, root_e2e, _, _, _ = timed(host, e2e_steps, 2, False)
+    stages = {}
+    step(dev, stages)                                          # one more, instrumented (host waits at every mark)
+    stage_t = torch.tensor([stages.get(k, 0.0) for k in ("lde", "exchange", "hash", "roots")], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(stage_t, op=dist.ReduceOp.MAX)
+    golden = golden_case("c4" if log_n == C4_LOG_N else "c4_small" if log_n == 14 else "")
+    parity_ok = None if golden is None else (root.hex() == golden["root"] and root_e2e == root)
+    cairo_line = None
+    if not args.no_cairo:
+        try:
+            cairo_line = cairo_prove_sharded_bench(ctx, args, world, rank, barrier, dist)
+        except Exception as e:                                # the commit line must survive a failure of the extra
+            cairo_line = {"error": "%s: %s" % (type(e).__name__, e)}
     if rank == 0:
-        sampler.start()
-    launches0 = ctx.launch_count
-    t0 = time.perf_counter()
-    out = None
-    for _ in range(args.steps):
-        out = step()
-    ctx.synchronize()
-    torch.cuda.synchronize()
-    dist.barrier()
-    ms = (time.perf_counter() - t0) * 1e3
-    sampler.stop_flag = True
-    tt = torch.tensor([ms], device="cuda", dtype=torch.float64)
-    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms = float(tt.item())
-    if rank == 0:
-        sampler.join(timeout=2)
-    if rank == 0:
-        value = cfg["elems_per_step"] * args.steps / (ms * 1e-3)
-        h2d = sum(t.numel() for t, _, _ in shards.values()) + comp.nbytes + p0.nbytes
-        print(json.dumps({
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "u32x8 (256-bit Montgomery) / u64 Keccak lanes", "data": "synthetic (splitmix64-seeded field elements)",
+        elems = cfg["elems_per_step"]
+        int_peaks = {}
+        try:
+            int_peaks = json.load(open(os.path.join(ROOT, "profiles", "int_peaks.json")))
+        except Exception:
+            pass
+        imad_peak = float(int_peaks.get("imad_wide_gops", 18300.0))
+        lop_peak = float(int_peaks.get("lop3_gops", 18450.0))
+        total_kernel_ms = sum(v["ms"] for v in prof.values()) or 1.0
+        kernels = {}
+        for name, st in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
+            sec = st["ms"] * 1e-3
+            kernels[name] = {"launches_per_step": st["launches"] / args.steps, "ms_per_step": st["ms"] / args.steps, "share": st["ms"] / total_kernel_ms,
+                             "imad_frac": (st["muls"] * 80 / sec / 1e9) / imad_peak if sec else 0.0,
+                             "alu_frac": (st["perms"] * 4320 / sec / 1e9) / lop_peak if sec else 0.0}
+        tname = next(iter(kernels))
+        tstat = prof[tname]
+        line = {
+            "metric": METRIC, "value": elems * args.steps / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u32x8 (256-bit Montgomery) / u64 Keccak lanes", "data": "synthetic (splitmix64-seeded field elements, one stream per column)",
             "config": cfg,
-            "e2e": {"value": value, "unit": UNIT, "ms_per_step": ms / args.steps, "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": 32 * (3 + log_n) + 32 * BLOWUP + 8,
-                    "note": "sharded mode is timed end to end only: host shards in, roots out, barrier-to-barrier wall clock"},
-            "gpu_launches": ctx.launch_count - launches0, "clocks": sampler.summary(),
-            "result": {"last_root": out[0].hex(), "nonce": out[1]},
-        }))
+            "parity_ok": parity_ok,
+            "result": {"root": root.hex(), "golden_root": None if golden is None else golden["root"],
+                       "golden_source": "tests/golden/synthetic/big_configs.json (CPU oracle, offline)"},
+            "e2e": {"value": elems * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
+                    "h2d_bytes_per_step": int(n * C4_COLS * 32), "d2h_bytes_per_step": 32 * world,
+                    "how": "every rank's column shard in pinned host memory, uploaded group by group on the copy stream under the previous "
+                           "group's transforms; subtree roots read back"},
+            "wall_ms_per_step": wall_dev / args.steps,
+            "stages_ms": dict(zip(("lde", "exchange_exposed", "hash", "roots"), [round(float(x), 3) for x in stage_t.tolist()])),
+            "stages_how": "one extra step with a host wait at every mark (max over ranks): `exchange_exposed` is what is left of the all-to-all "
+                          "after the LDE of the later column groups has hidden the earlier groups' transfers",
+            "pipeline_groups": groups, "gpu_launches": launches, "clocks": clocks,
+            "roofline": {"bound": "int_issue", "kernel": tname, "achieved": tstat["muls"] * 80 / (tstat["ms"] * 1e-3) / 1e9 if tstat["ms"] else 0.0,
+                         "peak": imad_peak, "unit": "G lane-op/s (IMAD.WIDE.U32)", "frac": kernels[tname]["imad_frac"], "traffic": None,
+                         "peak_source": "isolated IMAD.WIDE.U32 issue rate measured on this pool's B200 (profiles/int_peaks.json)",
+                         "scope": "rank 0's launches"},
+            "kernels_rank0": kernels,
+        }
+        if cairo_line is not None:
+            line["cairo_prove"] = cairo_line
+        print(json.dumps(line))
+    for t in dev:
+        del t
     dist.destroy_process_group()
+    if parity_ok is False:
+        raise SystemExit("bench.py: the sharded commit's root differs from the pinned oracle root")
+
+
+def cairo_prove_sharded_bench(ctx, args, world, rank, barrier, dist):
+    """ONE Cairo proof on N GPUs (cairo_distributed.py): fibonacci_70000 under Provable80Bits (the options of
+    benches/criterion_prover_70k.rs) and a 4x longer trace; the proof must have the digest pinned by the CPU oracle."""
+    import hashlib
+
+    import lambdaworks_cairo_prover_b200 as P
+    from lambdaworks_cairo_prover_b200 import _native as N, cairo
+    from lambdaworks_cairo_prover_b200.cairo_distributed import generate_cairo_proof_sharded
+    out = {"metric": "cairo_fib_prove_time", "unit": "ms", "higher_is_better": False, "n_gpus": world,
+           "how": "wall clock, barrier to barrier, max over ranks: the host trace table of every rank in, StarkProof::serialize bytes out on "
+                  "rank 0; ONE proof sharded over the GPUs"}
+    opts = P.ProofOptions.new_secure("Provable80Bits", 3)
+    for fib_n, key in ((args.fib_n, "fib"), (args.fib_n_large, "fib_large")):
+        if not fib_n:
+            continue
+        regs, mem, size = cairo.run_program(cairo.fibonacci_program(fib_n))
+        trace = cairo.build_main_trace(regs, mem, size)
+        N.lib().s252_cairo_trace_pin(trace.handle)
+        times, proof, stages = [], None, {}
+        for it in range(2 + min(args.steps, 5)):
+            barrier()
+            t0 = time.perf_counter()
+            proof = generate_cairo_proof_sharded(trace, opts, ctx)
+            barrier()
+            if it >= 2:
+                times.append((time.perf_counter() - t0) * 1e3)
+        generate_cairo_proof_sharded(trace, opts, ctx, timings=stages)
+        golden = golden_case("fib%d_80bits" % fib_n)
+        entry = {"program": "cairo0 fibonacci_%d" % fib_n, "trace_rows": trace.n_rows(), "value": float(np.median(times)),
+                 "ms_all": [round(x, 2) for x in times], "stages_ms": {k: round(v, 3) for k, v in stages.items() if not isinstance(v, dict)},
+                 "commit_detail_ms": {k: round(v, 3) for k, v in stages.get("commit_detail", {}).items()}}
+        if rank == 0:
+            entry["proof_bytes"] = len(proof)
+            entry["proof_sha256"] = hashlib.sha256(proof).hexdigest()
+            entry["parity_ok"] = None if golden is None else entry["proof_sha256"] == golden["sha256"]
+        out[key] = entry
+        trace.free()
+    if "fib" in out:
+        out["value"] = out["fib"]["value"]
+    return out
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
@@ -590,6 +716,9 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
+    n_gpus = max(args.gpus, int(os.environ.get("WORLD_SIZE", "1")))
+    if n_gpus > 1 and args.mode != "traces":
+        return run_reference_c4(args, cores, n_gpus)
     log_n = args.cpu_log_n if args.cpu_log_n else args.log_n
     cpu_commit_sample(8, cores)                      # loads the checker library, touches every code path once
     t0 = time.perf_counter()
@@ -618,6 +747,43 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_reference_c4(args, cores, n_gpus):
+    """The reference arm beside the sharded arm (N > 1): the same C4-shaped commit (33 columns, blowup 8) on the host cores.  The full
+    2^22-row table is ~9 minutes of CPU work per step, so each step is a 2^17-row sample of it (elems/s is size-normalised; the workload
+    string says so)."""
+    from oracle import pyoracle as O
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from util import random_felts
+    log_n = args.cpu_log_n or 17
+    n = 1 << log_n
+    trace = np.empty((n, C4_COLS, 4), dtype=np.uint64)
+    for j in range(C4_COLS):
+        trace[:, j, :] = random_felts(C4_SEED + j, n)
+    O.interpolate_and_commit(trace[:256], C4_BLOWUP, OFFSET, threads=cores, want_lde=False, want_nodes=False)
+    t0 = time.perf_counter()
+    steps_done, last = 0, 0.0
+    while steps_done < args.steps and (steps_done == 0 or time.perf_counter() - t0 + last < args.cpu_budget_s):
+        a = time.perf_counter()
+        O.interpolate_and_commit(trace, C4_BLOWUP, OFFSET, threads=cores, want_lde=False, want_nodes=False)
+        last = time.perf_counter() - a
+        steps_done += 1
+    wall = time.perf_counter() - t0
+    cfg = c4_config(log_n, 0)
+    cfg["workload"] = ("bounded CPU sample of C4: ONE interpolate_and_commit of a 2^%d-row x %d-column trace, blowup %d (the GPU arm commits 2^%d "
+                       "rows; a full-size CPU step is ~9 minutes)" % (log_n, C4_COLS, C4_BLOWUP, C4_LOG_N))
+    cfg["parallelism"] = "host cores only"
+    value = cfg["elems_per_step"] * steps_done / wall
+    sample = ("%d step(s), %.0f s each; oracle/ C restatement (no cargo here), LDE threaded over columns as under the reference's `parallel` "
+              "feature, leaf hashing and tree sequential as in the reference" % (steps_done, wall / steps_done))
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": steps_done, "steps_requested": args.steps,
+        "warmup": 0, "ms_per_step": wall * 1e3 / steps_done, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u64x4 (256-bit Montgomery)", "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
 def main():
     # stdout carries exactly one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
     if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
@@ -634,17 +800,22 @@ def main():
     ap.add_argument("--cpu-budget-s", type=float, default=150.0, help="--impl reference: stop starting new full-size steps after this long")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cairo", action="store_true", help="skip the Cairo fib prove-time measurement")
+    ap.add_argument("--no-c4", action="store_true", help="N=1: skip the one-GPU point of the sharded C4 commit")
     ap.add_argument("--fib-n", type=int, default=70000, help="fibonacci program of the prove-time measurement")
     ap.add_argument("--cpu-fib-n", type=int, default=4000, help="fibonacci program of the bounded CPU prove sample")
-    ap.add_argument("--mode", default="traces", choices=["traces", "sharded"],
-                    help="N>1: 'traces' = one independent trace per GPU (weak scaling, default); 'sharded' = ONE trace, "
-                         "columns sharded over the GPUs with an all-to-all before leaf hashing (strong scaling)")
+    ap.add_argument("--mode", default=None, choices=["traces", "sharded"],
+                    help="'sharded' (default for N>1) = ONE C4 trace, columns sharded over the GPUs with an all-to-all before leaf "
+                         "hashing, and ONE Cairo proof on all GPUs (strong scaling); 'traces' (default for N=1) = the C2 commit phase, "
+                         "one independent trace per GPU (weak scaling)")
+    ap.add_argument("--c4-log-n", type=int, default=C4_LOG_N, help="trace length exponent of the sharded C4 commit")
+    ap.add_argument("--pipeline-groups", type=int, default=4, help="sharded mode: column groups per rank of the LDE -> exchange pipeline")
+    ap.add_argument("--fib-n-large", type=int, default=280000, help="sharded mode: the longer fibonacci program (0 = skip)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)
-    elif args.mode == "sharded" and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+    elif args.mode == "sharded" or (args.mode is None and int(os.environ.get("WORLD_SIZE", "1")) > 1):
         run_gpu_sharded(args)
     else:
         run_gpu(args)

@@ -165,6 +165,15 @@ const void *s252_commit_device_nodes(const s252_commit *c);
 int s252_fri_commit_phase(s252_ctx *ctx, size_t number_layers, const s252_fe *p0, size_t n_coeffs,
                           s252_transcript *transcript, const s252_fe *coset_offset, size_t domain_size, int mem,
                           s252_fri **out, s252_fe *last_value, uint8_t *roots_out);
+/* The same phase layer by layer, for a caller that keeps its own (Rust) transcript between the calls:
+ *   s252_fri_layer0       FriLayer::new(p0, coset_offset, domain_size)          -- fri/mod.rs:33-35, fri_commitment.rs:30-47
+ *   s252_fri_fold_commit  fold_polynomial(zeta) + FriLayer::new of the next layer -- fri/mod.rs:43-51; returns its root
+ *   s252_fri_fold_last    the last fold and fri_last_value                      -- fri/mod.rs:58-66
+ * The handle grows by one layer per s252_fri_fold_commit and serves s252_fri_query / s252_fri_read_* as usual. */
+int s252_fri_layer0(s252_ctx *ctx, const s252_fe *p0, size_t n_coeffs, const s252_fe *coset_offset, size_t domain_size, int mem,
+                    s252_fri **out, uint8_t root[32]);
+int s252_fri_fold_commit(s252_fri *f, const s252_fe *zeta, uint8_t root[32]);
+int s252_fri_fold_last(s252_fri *f, const s252_fe *zeta, s252_fe *last_value);
 /* Round 3 reads: Frame::get_trace_evaluations (src/starks/frame.rs:67-83) and
  * H1(z^2), H2(z^2) (prover.rs:296-300) from the coefficients resident in a commit:
  * out[p*out_stride + col_offset + j] = poly_j(points[p]).  Several commits (main, aux) fill one

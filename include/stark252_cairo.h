@@ -83,7 +83,11 @@ void s252_cairo_trace_public_memory(const s252_cairo_trace *t, uint64_t *addrs, 
 size_t s252_cairo_trace_serialize_public_inputs(const s252_cairo_trace *t, uint8_t *out);
 
 /* A trace handle around a caller-built table (a Rust TraceTable + PublicInputs): table row-major LW
- * (copied), public memory as parallel arrays. */
+ * (copied), public memory as parallel arrays.  n_rows must be a power of two.
+ * LIMIT: build_auxiliary_trace on the device sorts the four address columns by their low 64 bits and the three
+ * offset columns by their low 16 bits (machine words: what build_main_trace produces); the reference sorts full
+ * representatives (air.rs:529-533,684-689), so a hand-made table with wider values in those columns is outside
+ * the supported range. */
 int s252_cairo_trace_from_table(const s252_fe *table, size_t n_rows, size_t n_cols, const s252_cairo_public_inputs *pub,
                                 const uint64_t *pub_addrs, const s252_fe *pub_values, s252_cairo_trace **out);
 

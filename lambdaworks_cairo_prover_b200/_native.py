@@ -59,6 +59,9 @@ SIGNATURES = {
     "s252_commit_device_coeffs": (_vp, [_vp]),
     "s252_commit_device_nodes": (_vp, [_vp]),
     "s252_fri_commit_phase": (_i, [_vp, _sz, _vp, _sz, _vp, _vp, _sz, _i, C.POINTER(_vp), _vp, _vp]),
+    "s252_fri_layer0": (_i, [_vp, _vp, _sz, _vp, _sz, _i, C.POINTER(_vp), _vp]),
+    "s252_fri_fold_commit": (_i, [_vp, _vp, _vp]),
+    "s252_fri_fold_last": (_i, [_vp, _vp, _vp]),
     "s252_commit_evaluate_at": (_i, [_vp, _vp, _sz, _vp, _sz, _sz]),
     "s252_fri_commit_phase_deep": (_i, [_vp, _sz, _vp, _sz, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u64,
                                         C.POINTER(_vp), _vp, _vp]),

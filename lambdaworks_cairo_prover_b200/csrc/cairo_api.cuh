@@ -195,25 +195,26 @@ extern "C" int s252_cairo_trace_from_table(const s252_fe* table, size_t n_rows, 
                                            const uint64_t* pub_addrs, const s252_fe* pub_values, s252_cairo_trace** out) {
     if (!table || !pub || !out || (pub->n_public_memory && (!pub_addrs || !pub_values))) CAIRO_FAIL(S252_ERR_INVALID, "null argument");
     if (n_cols != CA::MAIN_COLS && n_cols != CA::MAIN_COLS + CA::RC_BUILTIN_COLS) CAIRO_FAIL(S252_ERR_INVALID, "a Cairo main trace has 34 or 43 columns");
+    if (n_rows == 0 || !is_pow2(n_rows) || n_rows > ((size_t)1 << 40) / n_cols) CAIRO_FAIL(S252_ERR_INVALID, "the trace length must be a power of two (and n_rows * n_cols must not overflow)");
     s252_cairo_trace* t = nullptr;
-    try {
+    try {                                                                  // nothing may unwind across the C boundary
         t = new s252_cairo_trace();
         t->table.assign(table, table + n_rows * n_cols);
+        t->n_rows = n_rows; t->n_cols = n_cols;
+        CA::PublicInputs& p = t->pi;
+        p.pc_init = pub->pc_init; p.ap_init = pub->ap_init; p.fp_init = pub->fp_init; p.pc_final = pub->pc_final; p.ap_final = pub->ap_final;
+        p.num_steps = pub->num_steps;
+        p.has_rc = pub->has_range_check_bounds; p.range_check_min = pub->range_check_min; p.range_check_max = pub->range_check_max;
+        p.has_rc_segment = pub->has_rc_segment; p.has_output_segment = pub->has_output_segment;
+        p.rc_segment[0] = pub->rc_segment[0]; p.rc_segment[1] = pub->rc_segment[1];
+        p.output_segment[0] = pub->output_segment[0]; p.output_segment[1] = pub->output_segment[1];
+        for (size_t i = 0; i < pub->n_public_memory; ++i) p.public_memory.push_back({pub_addrs[i], H::from_lw(pub_values[i].limbs)});
+        std::sort(p.public_memory.begin(), p.public_memory.end(), [](const std::pair<uint64_t, fe>& a, const std::pair<uint64_t, fe>& b) { return a.first < b.first; });
+        t->make_columns();
     } catch (const std::exception& e) {
         delete t;
         CAIRO_FAIL(S252_ERR_INVALID, std::string("s252_cairo_trace_from_table: ") + e.what());
     }
-    t->n_rows = n_rows; t->n_cols = n_cols;
-    CA::PublicInputs& p = t->pi;
-    p.pc_init = pub->pc_init; p.ap_init = pub->ap_init; p.fp_init = pub->fp_init; p.pc_final = pub->pc_final; p.ap_final = pub->ap_final;
-    p.num_steps = pub->num_steps;
-    p.has_rc = pub->has_range_check_bounds; p.range_check_min = pub->range_check_min; p.range_check_max = pub->range_check_max;
-    p.has_rc_segment = pub->has_rc_segment; p.has_output_segment = pub->has_output_segment;
-    p.rc_segment[0] = pub->rc_segment[0]; p.rc_segment[1] = pub->rc_segment[1];
-    p.output_segment[0] = pub->output_segment[0]; p.output_segment[1] = pub->output_segment[1];
-    for (size_t i = 0; i < pub->n_public_memory; ++i) p.public_memory.push_back({pub_addrs[i], H::from_lw(pub_values[i].limbs)});
-    std::sort(p.public_memory.begin(), p.public_memory.end(), [](const std::pair<uint64_t, fe>& a, const std::pair<uint64_t, fe>& b) { return a.first < b.first; });
-    t->make_columns();
     *out = t;
     return S252_OK;
 }
@@ -417,6 +418,7 @@ static int commit_from_host_columns(s252_ctx* ctx, const s252_fe* cols_lw, size_
 
 extern "C" int s252_cairo_round1(s252_ctx* ctx, const s252_cairo_trace* trace, size_t blowup, uint64_t coset_offset,
                                  s252_transcript* transcript, s252_commit** main_out, s252_commit** aux_out, s252_fe rap_out[3]) {
+    NVTX_RANGE("s252_cairo_round1");
     if (!ctx || !trace || !transcript || !main_out || !aux_out || !rap_out) return S252_ERR_INVALID;
     *main_out = *aux_out = nullptr;
     CU(ctx, cudaSetDevice(ctx->device));
@@ -558,6 +560,7 @@ static int cairo_eval_constraints_rows(s252_ctx* ctx, const s252_cairo_trace* tr
 extern "C" int s252_cairo_constraint_evaluations(s252_ctx* ctx, const s252_cairo_trace* trace, s252_commit* mainc, s252_commit* auxc,
                                                  const s252_fe rap_lw[3], const s252_fe* boundary_coeffs, const s252_fe* transition_coeffs,
                                                  size_t blowup, uint64_t coset_offset, s252_fe* out) {
+    NVTX_RANGE("s252_cairo_constraint_evaluations");
     if (!ctx || !trace || !mainc || !auxc || !rap_lw || !boundary_coeffs || !transition_coeffs || !out) return S252_ERR_INVALID;
     CU(ctx, cudaSetDevice(ctx->device));
     const int nt = trace->n_cols > CA::MAIN_COLS ? 50 : 49;
@@ -620,6 +623,7 @@ static int cairo_composition_commit(s252_ctx* ctx, const fe* evals, size_t N, si
 extern "C" int s252_cairo_round2(s252_ctx* ctx, const s252_cairo_trace* trace, s252_commit* mainc, s252_commit* auxc,
                                  const s252_fe rap_lw[3], size_t blowup, uint64_t coset_offset, s252_transcript* transcript,
                                  s252_commit** composition_out) {
+    NVTX_RANGE("s252_cairo_round2");
     if (!ctx || !trace || !mainc || !auxc || !rap_lw || !transcript || !composition_out) return S252_ERR_INVALID;
     *composition_out = nullptr;
     CU(ctx, cudaSetDevice(ctx->device));
@@ -649,6 +653,7 @@ extern "C" const s252_fe* s252_cairo_trace_columns(const s252_cairo_trace* t) { 
 
 extern "C" int s252_lde_host_columns(s252_ctx* ctx, const s252_fe* cols_lw, size_t n_rows, size_t n_cols, size_t blowup,
                                      uint64_t coset_offset, int keep_trace, s252_commit** out) {
+    NVTX_RANGE("s252_lde_host_columns");
     if (!ctx || !cols_lw || !out) return S252_ERR_INVALID;
     *out = nullptr;
     CU(ctx, cudaSetDevice(ctx->device));
@@ -657,6 +662,7 @@ extern "C" int s252_lde_host_columns(s252_ctx* ctx, const s252_fe* cols_lw, size
 extern "C" const void* s252_commit_device_trace(const s252_commit* c) { return c->trace; }
 extern "C" int s252_lde_device_columns(s252_ctx* ctx, const void* cols, size_t n_rows, size_t n_cols, size_t blowup,
                                        uint64_t coset_offset, s252_commit** out) {
+    NVTX_RANGE("s252_lde_device_columns");
     if (!ctx || !cols || !out) return S252_ERR_INVALID;
     *out = nullptr;
     CU(ctx, cudaSetDevice(ctx->device));
@@ -673,6 +679,7 @@ extern "C" int s252_lde_device_columns(s252_ctx* ctx, const void* cols, size_t n
 // with s252_device_free).
 extern "C" int s252_cairo_aux_trace_device(s252_ctx* ctx, const s252_cairo_trace* trace, const s252_fe rap_lw[3], const void* prefetched,
                                            int prefetched_internal, void** aux_out) {
+    NVTX_RANGE("s252_cairo_aux_trace_device");
     if (!ctx || !trace || !rap_lw || !aux_out) return S252_ERR_INVALID;
     *aux_out = nullptr;
     CU(ctx, cudaSetDevice(ctx->device));
@@ -704,6 +711,7 @@ extern "C" int s252_cairo_constraints_rows(s252_ctx* ctx, const s252_cairo_trace
                                            size_t stride, size_t row0, size_t rows, const void* main_halo, const void* aux_halo,
                                            size_t halo_stride, const s252_fe rap_lw[3], const s252_fe* boundary_coeffs,
                                            const s252_fe* transition_coeffs, size_t blowup, uint64_t coset_offset, void* evals_out) {
+    NVTX_RANGE("s252_cairo_constraints_rows");
     if (!ctx || !trace || !main_block || !aux_block || !main_halo || !aux_halo || !rap_lw || !boundary_coeffs || !transition_coeffs || !evals_out)
         return S252_ERR_INVALID;
     CU(ctx, cudaSetDevice(ctx->device));
@@ -718,6 +726,7 @@ extern "C" int s252_cairo_constraints_rows(s252_ctx* ctx, const s252_cairo_trace
 }
 extern "C" int s252_cairo_composition_commit(s252_ctx* ctx, const void* evals, size_t n_rows, size_t blowup, uint64_t coset_offset,
                                              s252_commit** out, uint8_t root[32]) {
+    NVTX_RANGE("s252_cairo_composition_commit");
     if (!ctx || !evals || !out || !root) return S252_ERR_INVALID;
     *out = nullptr;
     CU(ctx, cudaSetDevice(ctx->device));
@@ -727,6 +736,7 @@ extern "C" int s252_cairo_composition_commit(s252_ctx* ctx, const void* evals, s
 // The same without the tree: H1/H2 coefficients + their LDE (a rank of a sharded proof hashes only its own rows).
 extern "C" int s252_cairo_composition_lde(s252_ctx* ctx, const void* evals, size_t n_rows, size_t blowup, uint64_t coset_offset,
                                           s252_commit** out) {
+    NVTX_RANGE("s252_cairo_composition_lde");
     if (!ctx || !evals || !out) return S252_ERR_INVALID;
     *out = nullptr;
     CU(ctx, cudaSetDevice(ctx->device));
@@ -738,6 +748,7 @@ extern "C" int s252_deep_rows(s252_ctx* ctx, const void* const* tables, const si
                               const uint64_t* transition_offsets, size_t n_offsets, const s252_fe* trace_ood, const s252_fe* h1_z2,
                               const s252_fe* h2_z2, const s252_fe* gamma, const s252_fe* gamma_p, const s252_fe* trace_gammas,
                               uint64_t coset_offset, void* out) {
+    NVTX_RANGE("s252_deep_rows");
     if (!ctx || !tables || !strides || !n_cols || !z || !transition_offsets || !trace_ood || !h1_z2 || !h2_z2 || !gamma || !gamma_p ||
         !trace_gammas || !out || n_tables < 2 || n_tables > (size_t)s252::DEEP_MAX_TABLES)
         return S252_ERR_INVALID;
@@ -763,6 +774,7 @@ struct ByteSink {
 
 extern "C" int s252_cairo_prove(s252_ctx* ctx, const s252_cairo_trace* trace, size_t blowup, size_t n_queries, uint64_t coset_offset,
                                 uint8_t grinding_factor, uint8_t** proof_out, size_t* proof_len) {
+    NVTX_RANGE("s252_cairo_prove");
     if (!ctx || !trace || !proof_out || !proof_len) return S252_ERR_INVALID;
     *proof_out = nullptr; *proof_len = 0;
     CU(ctx, cudaSetDevice(ctx->device));
@@ -779,6 +791,7 @@ extern "C" int s252_cairo_prove(s252_ctx* ctx, const s252_cairo_trace* trace, si
         TRY(s252_cairo_round2(ctx, trace, mainc, auxc, rap, blowup, coset_offset, &t, &comp));
         ST.mark("round2");
         // ---- round 3 (prover.rs:650-690): z, H1(z^2), H2(z^2), t_j(z g^k)
+        nvtxRangePushA("round3_ood");
         fe g;
         H::primitive_root(ilog2(N), &g);
         const fe hinv = H::inv(H::from_u64(coset_offset));
@@ -798,6 +811,7 @@ extern "C" int s252_cairo_prove(s252_ctx* ctx, const s252_cairo_trace* trace, si
         uint8_t be[32];
         for (int k = 0; k < 2; ++k) { H::to_bytes_be(H::from_lw(hz[k].limbs), be); t.append(be, 32); }
         for (auto& v : ood) { H::to_bytes_be(H::from_lw(v.limbs), be); t.append(be, 32); }
+        nvtxRangePop();
         ST.mark("round3");
         // ---- round 4 (prover.rs:327-404)
         s252_fe gamma, gamma_p;

@@ -16,6 +16,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <exception>
 #include <thread>
 #include <unordered_map>
 #include <vector>
@@ -35,9 +36,16 @@ inline void parallel_for(size_t n, F fn) {
     if (nt == 0) nt = 1;
     if (nt > 32) nt = 32;
     if (n < 4096 || nt == 1) { fn((size_t)0, n, 0u); return; }
+    // an exception inside a worker (std::bad_alloc from a push_back, say) must not end in std::terminate: it is carried
+    // to the calling thread and rethrown there, where the C entry points catch it
     std::vector<std::thread> th;
-    for (unsigned t = 0; t < nt; ++t) th.emplace_back([=] { fn(n * t / nt, n * (t + 1) / nt, t); });
+    std::vector<std::exception_ptr> errs(nt);
+    for (unsigned t = 0; t < nt; ++t)
+        th.emplace_back([=, &errs] {
+            try { fn(n * t / nt, n * (t + 1) / nt, t); } catch (...) { errs[t] = std::current_exception(); }
+        });
     for (auto& x : th) x.join();
+    for (auto& e : errs) if (e) std::rethrow_exception(e);
 }
 
 // Column indices of the main trace (src/cairo/air.rs:74-125)
@@ -119,7 +127,10 @@ inline bool vm_run(const std::vector<fe>& program, uint64_t entry_offset, uint64
     const uint64_t P = program.size();
     const uint64_t exec_base = 1 + P;
     const uint64_t SENT_FP = (1ULL << 62), SENT_PC = (1ULL << 62) + 1;
-    const uint64_t MAX_ADDRESS = 1ULL << 28;      // flat memory: a stray write far away must not allocate terabytes
+    // Flat memory: a stray write far away must not allocate gigabytes.  The segments of a run are contiguous after
+    // relocation, so every legitimate address is below program + 4 cells per step (+ slack); S252_CAIRO_MAX_ADDRESS raises the cap.
+    uint64_t MAX_ADDRESS = std::min<uint64_t>(1ULL << 28, (uint64_t)program.size() + 4 * std::min<uint64_t>(max_steps, 1ULL << 26) + (1u << 16));
+    if (const char* e = std::getenv("S252_CAIRO_MAX_ADDRESS")) { const unsigned long long v = std::strtoull(e, nullptr, 0); if (v) MAX_ADDRESS = v; }
     std::vector<fe> mem;          // index = address
     std::vector<uint8_t> known;
     auto ensure = [&](uint64_t a) { if (a >= mem.size()) { size_t n = std::max<size_t>(a + 1, mem.size() * 2); mem.resize(n, fe_zero()); known.resize(n, 0); } };
@@ -441,11 +452,16 @@ inline bool build_main_trace(const std::vector<RegisterState>& regs, const Memor
     const uint64_t codelen = pi->public_memory.size();
     std::vector<uint64_t> mholes;
     uint64_t prev = addrs[0];
+    // a caller-supplied memory file may contain a gap of 2^40 addresses: holes beyond a few times the trace length
+    // cannot belong to a real execution (every hole costs a third of a padding row) -- refuse instead of exhausting RAM
+    const size_t max_holes = 16 * (size_t)T.n_rows() + (1u << 16);
     for (uint64_t a : addrs) {
         const uint64_t diff = a - prev;
-        if (diff != 1 && diff != 0 && a > codelen)
+        if (diff != 1 && diff != 0 && a > codelen) {
+            if (diff > max_holes || mholes.size() + diff > max_holes) { *err = "memory holes exceed 16x the trace length"; return false; }
             for (uint64_t h = prev + 1; h < a; ++h)
                 if (h > codelen) mholes.push_back(h);
+        }
         prev = a;
     }
     if (!mholes.empty()) {

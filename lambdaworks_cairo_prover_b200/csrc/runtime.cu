@@ -10,6 +10,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/stark252_b200.h"
 #include "cairo.cuh"
 #include "commit.cuh"
@@ -118,7 +120,17 @@ struct s252_fri {
     s252_ctx* ctx = nullptr;
     size_t domain_size = 0;
     std::vector<FriLayerDev> layers;
+    fe h0 = s252::fe_one();     // coset offset of layer 0 (layer-by-layer interface)
 };
+
+// NVTX range per entry point / prover stage (visible in Nsight Systems; a no-op without a profiler attached)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+#define NVTX_RANGE(name) NvtxRange _nvtx_range_(name)
 
 #define FAIL(ctx, code, ...)                                     \
     do {                                                         \
@@ -622,10 +634,12 @@ static int interpolate_common(s252_ctx* ctx, const s252_fe* evals, size_t n, con
     return S252_OK;
 }
 extern "C" int s252_interpolate_fft(s252_ctx* ctx, const s252_fe* evals, size_t n, s252_fe* coeffs, int mem) {
+    NVTX_RANGE("s252_interpolate_fft");
     return interpolate_common(ctx, evals, n, nullptr, coeffs, mem);
 }
 extern "C" int s252_interpolate_offset_fft(s252_ctx* ctx, const s252_fe* evals, size_t n, const s252_fe* offset,
                                            s252_fe* coeffs, int mem) {
+    NVTX_RANGE("s252_interpolate_offset_fft");
     if (!offset) return S252_ERR_INVALID;
     return interpolate_common(ctx, evals, n, offset, coeffs, mem);
 }
@@ -666,6 +680,7 @@ static int evaluate_from_lw(s252_ctx* ctx, const fe* dcoeffs_lw, size_t n_coeffs
 
 extern "C" int s252_evaluate_offset_fft(s252_ctx* ctx, const s252_fe* coeffs, size_t n_coeffs, size_t blowup,
                                         size_t domain_size, const s252_fe* offset, s252_fe* out, size_t out_capacity, int mem) {
+    NVTX_RANGE("s252_evaluate_offset_fft");
     if (!ctx || !offset || !out || (!coeffs && n_coeffs)) return S252_ERR_INVALID;
     CU(ctx, cudaSetDevice(ctx->device));
     if (!is_pow2(blowup)) FAIL(ctx, S252_ERR_INVALID, "blowup factor %zu is not a power of two", blowup);
@@ -682,6 +697,7 @@ extern "C" int s252_evaluate_offset_fft(s252_ctx* ctx, const s252_fe* coeffs, si
 }
 extern "C" int s252_evaluate_polynomial_on_lde_domain(s252_ctx* ctx, const s252_fe* coeffs, size_t n_coeffs, size_t blowup,
                                                       size_t domain_size, const s252_fe* offset, s252_fe* out, int mem) {
+    NVTX_RANGE("s252_evaluate_polynomial_on_lde_domain");
     if (!ctx || !offset || !out || (!coeffs && n_coeffs)) return S252_ERR_INVALID;
     CU(ctx, cudaSetDevice(ctx->device));
     if (!is_pow2(blowup) || !is_pow2(domain_size)) FAIL(ctx, S252_ERR_INVALID, "blowup and domain size must be powers of two");
@@ -890,10 +906,12 @@ static int interpolate_lde_impl(s252_ctx* ctx, const s252_fe* trace, size_t n_ro
 }
 extern "C" int s252_interpolate_and_commit(s252_ctx* ctx, const s252_fe* trace, size_t n_rows, size_t n_cols, size_t blowup,
                                            uint64_t coset_offset, int mem, s252_commit** out, uint8_t root[32]) {
+    NVTX_RANGE("s252_interpolate_and_commit");
     return interpolate_lde_impl(ctx, trace, n_rows, n_cols, blowup, coset_offset, mem, true, out, root);
 }
 extern "C" int s252_interpolate_and_lde(s252_ctx* ctx, const s252_fe* trace, size_t n_rows, size_t n_cols, size_t blowup,
                                         uint64_t coset_offset, int mem, s252_commit** out) {
+    NVTX_RANGE("s252_interpolate_and_lde");
     return interpolate_lde_impl(ctx, trace, n_rows, n_cols, blowup, coset_offset, mem, false, out, nullptr);
 }
 // batch_commit over column-major columns that are already on this device in the library's internal
@@ -901,6 +919,7 @@ extern "C" int s252_interpolate_and_lde(s252_ctx* ctx, const s252_fe* trace, siz
 // are copied into the handle.
 extern "C" int s252_commit_device_columns(s252_ctx* ctx, const void* cols, size_t col_stride, size_t n_cols, size_t n_rows,
                                           s252_commit** out, uint8_t root[32]) {
+    NVTX_RANGE("s252_commit_device_columns");
     if (!ctx || !cols || !out || !root) return S252_ERR_INVALID;
     *out = nullptr;
     CU(ctx, cudaSetDevice(ctx->device));
@@ -926,6 +945,7 @@ extern "C" int s252_commit_device_columns(s252_ctx* ctx, const void* cols, size_
 // unchanged for as long as the handle is used (a multi-GB row block assembled by an all-to-all).
 extern "C" int s252_commit_device_columns_inplace(s252_ctx* ctx, const void* cols, size_t col_stride, size_t n_cols, size_t n_rows,
                                                   s252_commit** out, uint8_t root[32]) {
+    NVTX_RANGE("s252_commit_device_columns_inplace");
     if (!ctx || !cols || !out || !root) return S252_ERR_INVALID;
     *out = nullptr;
     CU(ctx, cudaSetDevice(ctx->device));
@@ -948,6 +968,7 @@ extern "C" int s252_commit_device_columns_inplace(s252_ctx* ctx, const void* col
 
 extern "C" int s252_lde_and_commit(s252_ctx* ctx, const s252_fe* polys, size_t n_coeffs, size_t n_polys, size_t domain_size,
                                    size_t blowup, uint64_t coset_offset, int mem, s252_commit** out, uint8_t root[32]) {
+    NVTX_RANGE("s252_lde_and_commit");
     if (!ctx || !polys || !out || !root) return S252_ERR_INVALID;
     *out = nullptr;
     CU(ctx, cudaSetDevice(ctx->device));
@@ -983,6 +1004,7 @@ extern "C" int s252_lde_and_commit(s252_ctx* ctx, const s252_fe* polys, size_t n
 
 extern "C" int s252_merkle_build(s252_ctx* ctx, const s252_fe* rows, size_t n_rows, size_t n_cols, int mem, s252_commit** out,
                                  uint8_t root[32]) {
+    NVTX_RANGE("s252_merkle_build");
     if (!ctx || !rows || !out || !root) return S252_ERR_INVALID;
     *out = nullptr;
     CU(ctx, cudaSetDevice(ctx->device));
@@ -1081,6 +1103,7 @@ static int open_common(s252_ctx* ctx, const fe* cols, size_t col_stride, unsigne
     return S252_OK;
 }
 extern "C" int s252_commit_open(s252_commit* c, const uint64_t* indices, size_t n_idx, s252_fe* rows_out, uint8_t* paths_out) {
+    NVTX_RANGE("s252_commit_open");
     s252_ctx* ctx = c->ctx;
     CU(ctx, cudaSetDevice(ctx->device));
     if (!indices && n_idx) return S252_ERR_INVALID;
@@ -1248,6 +1271,7 @@ static int fri_from_layer0(s252_ctx* ctx, s252_fri* f, size_t number_layers, s25
 extern "C" int s252_fri_commit_phase(s252_ctx* ctx, size_t number_layers, const s252_fe* p0, size_t n_coeffs,
                                      s252_transcript* transcript, const s252_fe* coset_offset, size_t domain_size, int mem,
                                      s252_fri** out, s252_fe* last_value, uint8_t* roots_out) {
+    NVTX_RANGE("s252_fri_commit_phase");
     if (!ctx || !transcript || !coset_offset || !out || !last_value || (!p0 && n_coeffs)) return S252_ERR_INVALID;
     *out = nullptr;
     CU(ctx, cudaSetDevice(ctx->device));
@@ -1279,6 +1303,7 @@ extern "C" int s252_fri_commit_phase(s252_ctx* ctx, size_t number_layers, const 
 // (prover.rs:296-300) from the coefficients resident in a commit handle.
 extern "C" int s252_commit_evaluate_at(s252_commit* c, const s252_fe* points, size_t n_points, s252_fe* out, size_t out_stride,
                                        size_t col_offset) {
+    NVTX_RANGE("s252_commit_evaluate_at");
     if (!c || !points || !out) return S252_ERR_INVALID;
     s252_ctx* ctx = c->ctx;
     CU(ctx, cudaSetDevice(ctx->device));
@@ -1464,6 +1489,7 @@ extern "C" int s252_fri_commit_phase_deep(s252_ctx* ctx, size_t number_layers, s
                                           const s252_fe* h1_z2, const s252_fe* h2_z2, const s252_fe* gamma,
                                           const s252_fe* gamma_p, const s252_fe* trace_gammas, s252_transcript* transcript,
                                           uint64_t coset_offset, s252_fri** out, s252_fe* last_value, uint8_t* roots_out) {
+    NVTX_RANGE("s252_fri_commit_phase_deep");
     if (!ctx || !trace_commits || !composition_commit || !z || !transition_offsets || !trace_ood || !h1_z2 || !h2_z2 || !gamma ||
         !gamma_p || !trace_gammas || !transcript || !out || !last_value)
         return S252_ERR_INVALID;
@@ -1503,6 +1529,7 @@ extern "C" int s252_fri_commit_phase_deep(s252_ctx* ctx, size_t number_layers, s
 extern "C" int s252_fri_commit_phase_evals(s252_ctx* ctx, size_t number_layers, const void* p0_evals, size_t domain_size,
                                            s252_transcript* transcript, uint64_t coset_offset, s252_fri** out, s252_fe* last_value,
                                            uint8_t* roots_out) {
+    NVTX_RANGE("s252_fri_commit_phase_evals");
     if (!ctx || !p0_evals || !transcript || !out || !last_value) return S252_ERR_INVALID;
     *out = nullptr;
     CU(ctx, cudaSetDevice(ctx->device));
@@ -1521,6 +1548,93 @@ extern "C" int s252_fri_commit_phase_evals(s252_ctx* ctx, size_t number_layers, 
     *out = f;
     return S252_OK;
 }
+// ---- layer-by-layer interface (fri_layer0 / fri_fold_commit) for a caller that keeps its own transcript:
+// FriLayer::new(p0, offset, domain_size) (fri_commitment.rs:30-47), then per layer fold_polynomial(zeta) + FriLayer::new
+// (fri/mod.rs:43-54), then the last fold (fri/mod.rs:58-66).
+extern "C" int s252_fri_layer0(s252_ctx* ctx, const s252_fe* p0, size_t n_coeffs, const s252_fe* coset_offset, size_t domain_size, int mem,
+                               s252_fri** out, uint8_t root[32]) {
+    NVTX_RANGE("s252_fri_layer0");
+    if (!ctx || !coset_offset || !out || !root || (!p0 && n_coeffs)) return S252_ERR_INVALID;
+    *out = nullptr;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (!is_pow2(domain_size) || n_coeffs > domain_size) FAIL(ctx, S252_ERR_INVALID, "p0 with %zu coefficients does not fit a domain of %zu", n_coeffs, domain_size);
+    const fe h = H::from_lw(coset_offset->limbs);
+    if (H::is_zero(h)) FAIL(ctx, S252_ERR_INVALID, "coset offset must be non-zero");
+    s252_fri* f = new s252_fri();
+    f->ctx = ctx; f->domain_size = domain_size; f->h0 = h;
+    int rc = [&]() -> int {
+        Tmp<fe> staged(ctx);
+        const fe* dp0 = nullptr;
+        if (n_coeffs) TRY(stage_in(ctx, p0, n_coeffs, mem, staged, &dp0));
+        FriLayerDev cur;
+        cur.size = domain_size;
+        TRY(dalloc(ctx, &cur.evals, domain_size));
+        f->layers.push_back(cur);
+        TRY(evaluate_from_lw(ctx, dp0, n_coeffs, domain_size, h, f->layers[0].evals, false));
+        TRY(dalloc(ctx, &f->layers[0].nodes, 4 * (2 * domain_size - 1)));
+        TRY(build_tree(ctx, f->layers[0].evals, domain_size, 1, domain_size, f->layers[0].nodes));
+        return fetch_root(ctx, f->layers[0].nodes, root);
+    }();
+    if (rc != S252_OK) { fri_free(f); return rc; }
+    *out = f;
+    return S252_OK;
+}
+static int fri_fold_step(s252_fri* f, const s252_fe* zeta, bool commit, FriLayerDev* nxt) {
+    s252_ctx* ctx = f->ctx;
+    const size_t k = f->layers.size();                                 // index of the layer being produced
+    const size_t size = f->layers.back().size, half = size / 2;
+    if (half == 0) FAIL(ctx, S252_ERR_INVALID, "FRI layer of size %zu cannot be folded", size);
+    fe w;
+    H::primitive_root(ilog2(f->domain_size), &w);
+    const fe* inv_tw;
+    TRY(get_power_table(ctx, f->domain_size / 2, H::inv(w), H::one(), &inv_tw));
+    fe hk = f->h0;
+    for (size_t j = 0; j + 1 < k; ++j) hk = H::sqr(hk);                 // offset of layer k-1
+    const fe inv2 = H::inv(H::from_u64(2));
+    const fe cfac = H::mul(H::from_lw(zeta->limbs), H::mul(inv2, H::inv(hk)));
+    nxt->size = half;
+    TRY(dalloc(ctx, &nxt->evals, half));
+    if (commit) TRY(dalloc(ctx, &nxt->nodes, 4 * (2 * half - 1)));
+    prof_begin(ctx, "fri_fold_commit");
+    prof_work(ctx, 32.0 * size + 32.0 * half + (commit ? 32.0 * half : 0.0), 3.2 * half, commit ? (double)half : 0.0);
+    s252::fri_fold_commit<<<(unsigned)((half + 127) / 128), 128, 0, ctx->stream>>>(f->layers.back().evals, half, inv_tw,
+                                                                                  (unsigned long long)(f->domain_size / size), cfac, nullptr, inv2,
+                                                                                  nxt->evals, commit ? nxt->nodes + 4 * (half - 1) : nullptr);
+    LAUNCH_CHECK(ctx);
+    return S252_OK;
+}
+extern "C" int s252_fri_fold_commit(s252_fri* f, const s252_fe* zeta, uint8_t root[32]) {
+    NVTX_RANGE("s252_fri_fold_commit");
+    if (!f || !zeta || !root || f->layers.empty()) return S252_ERR_INVALID;
+    s252_ctx* ctx = f->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    FriLayerDev nxt;
+    int rc = fri_fold_step(f, zeta, true, &nxt);
+    if (rc == S252_OK) rc = build_tree_nodes(ctx, nxt.size, nxt.nodes);
+    if (rc == S252_OK) rc = fetch_root(ctx, nxt.nodes, root);
+    if (rc != S252_OK) { dfree(ctx, nxt.evals); dfree(ctx, nxt.nodes); return rc; }
+    f->layers.push_back(nxt);
+    return S252_OK;
+}
+extern "C" int s252_fri_fold_last(s252_fri* f, const s252_fe* zeta, s252_fe* last_value) {
+    NVTX_RANGE("s252_fri_fold_last");
+    if (!f || !zeta || !last_value || f->layers.empty()) return S252_ERR_INVALID;
+    s252_ctx* ctx = f->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    FriLayerDev nxt;
+    int rc = fri_fold_step(f, zeta, false, &nxt);
+    if (rc != S252_OK) { dfree(ctx, nxt.evals); return rc; }
+    // fri_last_value = coefficient 0 of the folded polynomial = mean of its evaluations on the remaining coset
+    std::vector<fe> rem(nxt.size);
+    cudaError_t e = cudaMemcpyAsync(rem.data(), nxt.evals, nxt.size * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    dfree(ctx, nxt.evals);
+    CU(ctx, e);
+    fe acc = H::zero();
+    for (auto& v : rem) acc = H::add(acc, v);
+    H::to_lw(H::mul(acc, H::inv(H::from_u64((uint64_t)nxt.size))), last_value->limbs);
+    return S252_OK;
+}
 // fri_commit_phase continued from layer `layer_index` (a sharded commit phase collapses to one GPU once the
 // layers are small): evals = the layer_size evaluations of that layer on the coset h^(2^layer_index) <w_layer_size>,
 // resident on this device (internal format); number_layers = layers still to commit, this one included.  The
@@ -1528,6 +1642,7 @@ extern "C" int s252_fri_commit_phase_evals(s252_ctx* ctx, size_t number_layers, 
 extern "C" int s252_fri_commit_phase_from_layer(s252_ctx* ctx, size_t number_layers, const void* evals, size_t layer_size,
                                                 s252_transcript* transcript, uint64_t coset_offset, size_t layer_index, s252_fri** out,
                                                 s252_fe* last_value, uint8_t* roots_out) {
+    NVTX_RANGE("s252_fri_commit_phase_from_layer");
     if (!ctx || !evals || !transcript || !out || !last_value) return S252_ERR_INVALID;
     *out = nullptr;
     CU(ctx, cudaSetDevice(ctx->device));
@@ -1553,6 +1668,7 @@ extern "C" int s252_fri_commit_phase_from_layer(s252_ctx* ctx, size_t number_lay
 // h_k = coset_offset^(2^k), w of order layer_size = domain_size >> k.  v, s, out: device, internal format, `count` elements.
 extern "C" int s252_fri_fold_rows(s252_ctx* ctx, const void* v, const void* s, size_t count, size_t i0, size_t layer_size,
                                   size_t domain_size, size_t layer_index, const s252_fe* zeta, uint64_t coset_offset, void* out) {
+    NVTX_RANGE("s252_fri_fold_rows");
     if (!ctx || !v || !s || !zeta || !out) return S252_ERR_INVALID;
     CU(ctx, cudaSetDevice(ctx->device));
     if (!is_pow2(layer_size) || layer_size < 2 || i0 + count > layer_size / 2 || coset_offset == 0 || layer_index >= 64 ||
@@ -1598,6 +1714,7 @@ extern "C" int s252_fri_read_nodes(s252_fri* f, size_t layer, size_t first, size
 }
 extern "C" int s252_fri_query(s252_fri* f, const uint64_t* iotas, size_t n_queries, s252_fe* evals, s252_fe* evals_sym,
                               uint8_t* paths, uint8_t* paths_sym, size_t path_stride) {
+    NVTX_RANGE("s252_fri_query");
     s252_ctx* ctx = f->ctx;
     CU(ctx, cudaSetDevice(ctx->device));
     if (!iotas && n_queries) return S252_ERR_INVALID;
@@ -1668,6 +1785,7 @@ static int grind_round(s252_ctx* ctx, const uint8_t challenge[32], uint8_t grind
 }
 extern "C" int s252_generate_nonce_with_grinding(s252_ctx* ctx, const uint8_t challenge[32], uint8_t grinding_factor,
                                                  uint64_t limit, uint64_t* nonce) {
+    NVTX_RANGE("s252_generate_nonce_with_grinding");
     if (!ctx || !challenge || !nonce) return S252_ERR_INVALID;
     CU(ctx, cudaSetDevice(ctx->device));
     if (grinding_factor > 64) FAIL(ctx, S252_ERR_NOT_FOUND, "a 64-bit head cannot have %u trailing zeros", grinding_factor);
@@ -1690,6 +1808,7 @@ extern "C" int s252_generate_nonce_with_grinding(s252_ctx* ctx, const uint8_t ch
 // anything, calls again with base + 2^32.  The minimum over the parts is the reference's nonce (grinding.rs:44-47).
 extern "C" int s252_grind_round(s252_ctx* ctx, const uint8_t challenge[32], uint8_t grinding_factor, uint64_t base, uint64_t limit,
                                 unsigned part, unsigned parts, uint64_t* found) {
+    NVTX_RANGE("s252_grind_round");
     if (!ctx || !challenge || !found || parts == 0 || part >= parts) return S252_ERR_INVALID;
     CU(ctx, cudaSetDevice(ctx->device));
     if (grinding_factor > 64) FAIL(ctx, S252_ERR_NOT_FOUND, "a 64-bit head cannot have %u trailing zeros", grinding_factor);

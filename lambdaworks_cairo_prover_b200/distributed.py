@@ -111,6 +111,14 @@ class GpuBackend:
     def lde_pipeline(self, group_tables, n_rows, blowup, coset_offset):
         """Yields (handle, lde tensor) per group.  The upload of group g+1 runs on the library's copy stream
         while group g is interpolated and extended (the tables should be pinned host memory)."""
+        if all(getattr(t, "is_cuda", False) for t in group_tables):
+            # the groups are already resident in this GPU's HBM: no staging, no upload
+            for t in group_tables:
+                h = C.c_void_p()
+                self.ctx.check(N.lib().s252_interpolate_and_lde(self.ctx.handle, C.c_void_p(t.data_ptr()), n_rows, t.shape[-2], blowup,
+                                                                coset_offset, N.DEVICE, C.byref(h)), N.FFTError)
+                yield self._wrap(h, n_rows, t.shape[-2], blowup)
+            return
         sizes = [t.nbytes for t in group_tables]
         key = tuple(sizes)
         if key not in self._staging:                      # device staging, reused by later commits of the same shape

@@ -274,6 +274,61 @@ def test_fri_commit_phase(ctx, logn, blowup, ncoef):
     layers.free()
 
 
+@pytest.mark.parametrize("logn,blowup", [(3, 2), (8, 4), (15, 4), (17, 2)])
+def test_fri_layer_by_layer_interface(ctx, logn, blowup):
+    """fri_layer0 / fri_fold_commit for a caller that keeps its own transcript == fri_commit_phase.  The larger sizes cross
+    the thresholds of the single-launch tree top (2^9 and 2^17 leaves) and of the tail kernel."""
+    import ctypes as C
+    from lambdaworks_cairo_prover_b200 import _native as N
+    L = N.lib()
+    n = 1 << logn
+    M = n * blowup
+    p0 = random_felts(900 + logn, n)
+    h = felt.from_int(3)
+    t_ref = O.Transcript()
+    t_ref.append(b"layers")
+    want_last, want_roots, want_evals, _ = O.fri_commit_phase(logn, p0, t_ref, h, M)
+    t = P.DefaultTranscript()
+    t.append(b"layers")
+    fri, root, last = C.c_void_p(), np.empty(32, dtype=np.uint8), np.empty(4, dtype=np.uint64)
+    ctx.check(L.s252_fri_layer0(ctx.handle, N.ptr(p0), n, N.ptr(h), M, N.HOST, C.byref(fri), N.ptr(root)))
+    t.append(root.tobytes())
+    assert root.tobytes() == want_roots[0].tobytes()
+    for k in range(1, logn):
+        zeta = P.transcript_to_field(t)
+        ctx.check(L.s252_fri_fold_commit(fri, N.ptr(zeta), N.ptr(root)))
+        assert root.tobytes() == want_roots[k].tobytes(), k
+        t.append(root.tobytes())
+    zeta = P.transcript_to_field(t)
+    ctx.check(L.s252_fri_fold_last(fri, N.ptr(zeta), N.ptr(last)))
+    assert (last == want_last).all()
+    t.append(felt.to_bytes_be(last))
+    assert t.challenge() == t_ref.challenge()
+    assert L.s252_fri_n_layers(fri) == logn
+    ev = np.empty((M >> (logn - 1), 4), dtype=np.uint64)
+    ctx.check(L.s252_fri_read_layer(fri, logn - 1, 0, ev.shape[0], N.ptr(ev)))
+    assert (ev == want_evals[logn - 1]).all()
+    L.s252_fri_destroy(fri)
+
+
+def test_grinding_split_over_parts_gives_the_minimum(ctx):
+    """disjoint nonce ranges + min == the sequential search, for every way of splitting."""
+    import ctypes as C
+    from lambdaworks_cairo_prover_b200 import _native as N
+    L = N.lib()
+    rng = np.random.default_rng(23)
+    for factor in (3, 14, 20):
+        ch = rng.integers(0, 256, size=32, dtype=np.uint8)
+        want = O.generate_nonce_with_grinding(ch.tobytes(), factor)
+        for parts in (1, 2, 8):
+            found = []
+            for part in range(parts):
+                f = C.c_uint64()
+                ctx.check(L.s252_grind_round(ctx.handle, N.ptr(ch), factor, 0, 0, part, parts, C.byref(f)))
+                found.append(int(f.value))
+            assert min(found) == want, (factor, parts, found)
+
+
 def test_fri_rejects_oversized_polynomial(ctx):
     with pytest.raises(P.Stark252Error):
         P.fri_commit_phase(2, P.Polynomial(random_felts(1, 32)), P.DefaultTranscript(), felt.from_int(3), 16, ctx)
