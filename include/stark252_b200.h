@@ -104,6 +104,21 @@ int s252_evaluate_offset_fft(s252_ctx *ctx, const s252_fe *coeffs, size_t n_coef
 int s252_evaluate_polynomial_on_lde_domain(s252_ctx *ctx, const s252_fe *coeffs, size_t n_coeffs, size_t blowup,
                                            size_t domain_size, const s252_fe *offset, s252_fe *out, int mem);
 
+/* One column's transform shared by `parts` GPUs (a single oversized column; four-step NTT with
+ * one all-to-all).  The column is a 2^l1 x (N / 2^l1) matrix (first digit x inner position, natural index = k1 * inner + i
+ * on the way in).  phase 0: the first pass on this GPU's inner positions [part * inner / parts, ..) of `in`, result left in z
+ * at the same positions; the caller then moves rows k1 in [part * 2^l1 / parts, ..) of z to this GPU (NCCL all-to-all);
+ * phase 1: the remaining passes on those rows: this GPU's outputs k = k1 + 2^l1 * q (runs of 2^l1 / parts values, times
+ * n_cosets) land in `out`, natural order.  phase 2: only writes l1 to *log_l1.
+ * inverse != 0: Polynomial::interpolate_fft (n_cosets = 1); else evaluate_offset_fft(n_cosets, Some(N), coset_offset).
+ * in: N elements, z: n_cosets * N, out: n_cosets * N -- device, library-internal element format (s252_commit_device_lde).
+ * lambdaworks_cairo_prover_b200/column_distributed.py drives it. */
+int s252_ntt_shared(s252_ctx *ctx, unsigned log_n, int inverse, size_t n_cosets, uint64_t coset_offset, int phase, unsigned part,
+                    unsigned parts, const void *in, void *z, void *out, unsigned *log_l1);
+/* Element-format change between the reference's LW layout and the library-internal one on device buffers (n elements;
+ * to_internal != 0: LW -> internal).  in == out is allowed. */
+int s252_convert_elements(s252_ctx *ctx, const void *in, void *out, size_t n, int to_internal);
+
 /* ---- round 1 / round 2 commits ------------------------------------------------------------ */
 /* interpolate_and_commit(trace, domain, transcript)         -- src/starks/prover.rs:126-159
  * trace: row-major n_rows x n_cols (TraceTable.table, src/starks/trace.rs:9-13).

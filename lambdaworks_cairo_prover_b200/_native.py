@@ -40,6 +40,8 @@ SIGNATURES = {
     "s252_evaluate_offset_fft_len": (_sz, [_sz, _sz, _sz]),
     "s252_evaluate_offset_fft": (_i, [_vp, _vp, _sz, _sz, _sz, _vp, _vp, _sz, _i]),
     "s252_evaluate_polynomial_on_lde_domain": (_i, [_vp, _vp, _sz, _sz, _sz, _vp, _vp, _i]),
+    "s252_ntt_shared": (_i, [_vp, C.c_uint, _i, _sz, _u64, _i, C.c_uint, C.c_uint, _vp, _vp, _vp, C.POINTER(C.c_uint)]),
+    "s252_convert_elements": (_i, [_vp, _vp, _vp, _sz, _i]),
     "s252_interpolate_and_commit": (_i, [_vp, _vp, _sz, _sz, _sz, _u64, _i, C.POINTER(_vp), _vp]),
     "s252_interpolate_and_lde": (_i, [_vp, _vp, _sz, _sz, _sz, _u64, _i, C.POINTER(_vp)]),
     "s252_commit_device_columns": (_i, [_vp, _vp, _sz, _sz, _sz, C.POINTER(_vp), _vp]),

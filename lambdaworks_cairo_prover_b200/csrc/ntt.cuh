@@ -52,6 +52,9 @@ struct NttPass {
     unsigned in_lw;           // kind B single-pass: input is in the reference's LW element format
     unsigned out_lw;          // kind B: store outputs in LW format
     unsigned first_unit;      // the level-1 twiddle of this pass is 1 (no coset shift): skip that multiply
+    // One transform shared by several GPUs (four-step): a GPU runs only its range of tiles.
+    unsigned block0;          // added to blockIdx.x (strided pass: a contiguous tile range = a range of inner positions or of outer rows)
+    unsigned part_g0, part_gn;   // kind B: this GPU's range of k1 groups [part_g0, part_g0 + part_gn); part_gn = 0: all of them
 };
 
 __device__ __forceinline__ unsigned bitrev32(unsigned x, unsigned bits) { return bits ? __brev(x) >> (32 - bits) : 0u; }
@@ -172,8 +175,9 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_strided(NttPass P) {
     // block order: column fastest, then coset, then tile -- the blocks that share an inter-pass
     // twiddle slice (same tile and coset, different columns) run together, so the slice is read from
     // HBM once and served from L2 to the other columns
-    const unsigned col = blockIdx.x % P.ncols;
-    const unsigned rest = blockIdx.x / P.ncols;
+    const unsigned bidx = blockIdx.x + P.block0;
+    const unsigned col = bidx % P.ncols;
+    const unsigned rest = bidx / P.ncols;
     const unsigned coset = rest % P.ncosets;
     const unsigned tile = rest / P.ncosets;
     const unsigned tiles_per_outer = 1u << (P.logInner - P.logT);
@@ -222,10 +226,10 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_final(NttPass P) {
         out = P.out + col0 * P.out_col_stride;
         out_base = 0;
     } else {
-        // tile -> (k2, group of T consecutive k1)
-        const unsigned groups = 1u << (P.logN1 - P.logT);
+        // tile -> (k2, group of T consecutive k1); a GPU sharing the transform owns a range of the groups
+        const unsigned groups = P.part_gn ? P.part_gn : 1u << (P.logN1 - P.logT);
         const unsigned k2 = tile / groups;
-        const unsigned k1 = (tile % groups) << P.logT;
+        const unsigned k1 = (P.part_g0 + tile % groups) << P.logT;
         in = P.in + col0 * P.in_col_stride + coset * P.in_coset_stride +
              ((((unsigned long long)k1 << P.logN2) + k2) << P.logL);
         out = P.out + col0 * P.out_col_stride;

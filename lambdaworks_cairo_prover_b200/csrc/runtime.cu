@@ -419,8 +419,16 @@ struct Xform {
     fe oscale_base = s252::fe_one();
 };
 
+// A transform shared by `parts` GPUs: phase 0 = the first pass on this GPU's range of inner positions (into zbuf),
+// phase 1 = the remaining passes on this GPU's range of first-digit rows (from zbuf, after the all-to-all).
+struct NttShare {
+    int phase = -1;              // -1: the whole transform on this GPU
+    unsigned part = 0, parts = 1;
+    fe* zbuf = nullptr;          // [ncols][ncosets][N], owned by the caller (it crosses the exchange)
+    unsigned* log_l1 = nullptr;  // out: the first digit (the exchange geometry: rows of 2^l1, N / 2^l1 inner positions)
+};
 static int run_ntt(s252_ctx* ctx, const Xform& X, const fe* in, size_t in_col_stride, bool in_lw, fe* out,
-                   size_t out_col_stride, bool out_lw, unsigned ncols) {
+                   size_t out_col_stride, bool out_lw, unsigned ncols, const NttShare* share = nullptr) {
     const unsigned logn = X.logn;
     const size_t N = (size_t)1 << logn;
     const unsigned maxl = ctx->max_logl;
@@ -446,6 +454,9 @@ static int run_ntt(s252_ctx* ctx, const Xform& X, const fe* in, size_t in_col_st
         TRY(get_power_table(ctx, N, X.has_offset_scale ? X.oscale_base : H::one(), npass == 1 ? n_inv : H::one(), &oscale));
     }
 
+    const bool shared = share && share->phase >= 0;
+    if (shared && (npass == 1 || !share->zbuf || share->parts == 0 || !is_pow2(share->parts) || share->part >= share->parts))
+        FAIL(ctx, S252_ERR_INVALID, "a shared transform needs at least two passes (size > 2^%u) and a power-of-two number of parts", maxl);
     if (npass == 1) {
         const fe* lvl;
         TRY(get_level_table(ctx, logn, X.ncosets, root(logn), X.shift, X.step, &lvl));
@@ -476,19 +487,27 @@ static int run_ntt(s252_ctx* ctx, const Xform& X, const fe* in, size_t in_col_st
         l2 = (logn - l3 + 1) / 2;
         l1 = logn - l3 - l2;
     }
+    const unsigned lparts = shared ? ilog2(share->parts) : 0;
+    if (shared) {
+        if (share->log_l1) *share->log_l1 = l1;
+        if (l1 < lparts || logn - l1 < lparts) FAIL(ctx, S252_ERR_INVALID, "too many parts for a transform of size 2^%u", logn);
+        if (share->phase == 2) return S252_OK;       // geometry query only
+    }
     // scratch: [col][coset][N]
     Tmp<fe> Z(ctx);
-    TRY(dalloc(ctx, &Z.p, (size_t)ncols * X.ncosets * N));
+    if (shared) Z.p = share->zbuf; else TRY(dalloc(ctx, &Z.p, (size_t)ncols * X.ncosets * N));
+    struct Release { Tmp<fe>& z; bool keep; ~Release() { if (keep) z.p = nullptr; } } release{Z, shared};   // the caller's buffer is not ours to free
+    P.block0 = 0; P.part_g0 = 0; P.part_gn = 0;
 
     // pass A1: L = 2^l1 over stride 2^(logn-l1)
-    {
+    if (!shared || share->phase == 0) {
         const unsigned logInner = logn - l1;
         const fe shiftL = H::pow_u64(X.shift, (uint64_t)1 << logInner);
         const fe stepL = H::pow_u64(X.step, (uint64_t)1 << logInner);
         const fe *lvl, *ptw;
         TRY(get_level_table(ctx, l1, X.ncosets, root(l1), shiftL, stepL, &lvl));
         TRY(get_pass_table(ctx, l1, logInner, X.ncosets, root(logn), X.shift, X.step, n_inv, &ptw));
-        unsigned logT = std::min(s252::NTT_TILE_LOG - l1, logInner);
+        unsigned logT = std::min(s252::NTT_TILE_LOG - l1, logInner - lparts);
         if (logT > 5) logT = 5;
         P.in = in; P.out = Z.p; P.lvl = lvl; P.ptw = ptw; P.oscale = nullptr;
         P.in_col_stride = in_col_stride; P.out_col_stride = (size_t)X.ncosets * N;
@@ -496,12 +515,18 @@ static int run_ntt(s252_ctx* ctx, const Xform& X, const fe* in, size_t in_col_st
         P.logL = l1; P.logT = logT; P.logInner = logInner; P.logOuter = 0;
         P.lvl_per_coset = X.ncosets > 1; P.ptw_per_coset = X.ncosets > 1; P.rows_are_cols = 0; P.in_lw = 0; P.out_lw = 0;
         P.first_unit = (X.ncosets == 1 && H::eq(X.shift, H::one())) ? 1 : 0;
-        const size_t tiles = (size_t)1 << (logInner - logT);
+        size_t tiles = (size_t)1 << (logInner - logT);
+        if (shared) {            // this GPU's inner positions [part * inner / parts, ..): a contiguous range of tiles
+            tiles >>= lparts;
+            P.block0 = (unsigned)(tiles * share->part * X.ncosets * ncols);
+        }
         prof_begin(ctx, "ntt_pass_strided");
-        prof_work(ctx, 32.0 * N * ncols * (1 + X.ncosets), (0.5 * l1 + 1.0) * N * X.ncosets * ncols, 0);
+        prof_work(ctx, 32.0 * N * ncols * (1 + X.ncosets) / (shared ? share->parts : 1), (0.5 * l1 + 1.0) * N * X.ncosets * ncols / (shared ? share->parts : 1), 0);
         s252::ntt_pass_strided<<<(unsigned)(tiles * X.ncosets * ncols), s252::NTT_THREADS, smem, ctx->stream>>>(P);
         LAUNCH_CHECK(ctx);
+        P.block0 = 0;
     }
+    if (shared && share->phase == 0) return S252_OK;
     if (npass == 3) {
         // pass A2: in place on Z, view [2^l1][2^l2][2^l3]
         const fe *lvl, *ptw;
@@ -514,28 +539,40 @@ static int run_ntt(s252_ctx* ctx, const Xform& X, const fe* in, size_t in_col_st
         P.in_coset_stride = N; P.out_coset_stride = N;
         P.logL = l2; P.logT = logT; P.logInner = l3; P.logOuter = l1;
         P.lvl_per_coset = 0; P.ptw_per_coset = 0; P.first_unit = 1;
-        const size_t tiles = (size_t)1 << (l1 + l3 - logT);
+        size_t tiles = (size_t)1 << (l1 + l3 - logT);
+        if (shared) {            // this GPU's first-digit rows [part * 2^l1 / parts, ..) = a contiguous range of outer indices
+            tiles >>= lparts;
+            P.block0 = (unsigned)(tiles * share->part * X.ncosets * ncols);
+        }
         prof_begin(ctx, "ntt_pass_strided");
-        prof_work(ctx, 64.0 * N * ncols * X.ncosets, (0.5 * l2 + 1.0) * N * X.ncosets * ncols, 0);
+        prof_work(ctx, 64.0 * N * ncols * X.ncosets / (shared ? share->parts : 1), (0.5 * l2 + 1.0) * N * X.ncosets * ncols / (shared ? share->parts : 1), 0);
         s252::ntt_pass_strided<<<(unsigned)(tiles * X.ncosets * ncols), s252::NTT_THREADS, smem, ctx->stream>>>(P);
         LAUNCH_CHECK(ctx);
+        P.block0 = 0;
     }
     {
         // final pass: rows of 2^l3
         const fe* lvl;
         TRY(get_level_table(ctx, l3, 1, root(l3), H::one(), H::one(), &lvl));
-        unsigned logT = std::min(s252::NTT_TILE_LOG - l3, l1);
+        unsigned logT = std::min(s252::NTT_TILE_LOG - l3, l1 - lparts);
         if (logT > 5) logT = 5;
         P.in = Z.p; P.out = out; P.lvl = lvl; P.ptw = nullptr; P.oscale = oscale;
         P.in_col_stride = (size_t)X.ncosets * N; P.out_col_stride = out_col_stride;
         P.in_coset_stride = N; P.out_coset_stride = 0;
         P.logL = l3; P.logT = logT; P.logN1 = l1; P.logN2 = l2;
         P.lvl_per_coset = 0; P.ptw_per_coset = 0; P.rows_are_cols = 0; P.in_lw = 0; P.out_lw = out_lw; P.first_unit = 1;
-        const size_t tiles = (size_t)1 << (l1 + l2 - logT);
+        size_t tiles = (size_t)1 << (l1 + l2 - logT);
+        if (shared) {            // this GPU's groups of T consecutive first-digit rows, for every k2
+            P.part_gn = 1u << (l1 - logT - lparts);
+            P.part_g0 = P.part_gn * share->part;
+            tiles >>= lparts;
+        }
         prof_begin(ctx, "ntt_pass_final");
-        prof_work(ctx, 64.0 * N * ncols * X.ncosets, 0.5 * l3 * N * X.ncosets * ncols + (oscale ? (double)N * ncols : 0.0), 0);
+        prof_work(ctx, 64.0 * N * ncols * X.ncosets / (shared ? share->parts : 1),
+                  (0.5 * l3 * N * X.ncosets * ncols + (oscale ? (double)N * ncols : 0.0)) / (shared ? share->parts : 1), 0);
         s252::ntt_pass_final<<<(unsigned)(tiles * X.ncosets * ncols), s252::NTT_THREADS, smem, ctx->stream>>>(P);
         LAUNCH_CHECK(ctx);
+        P.part_g0 = 0; P.part_gn = 0;
     }
     return S252_OK;
 }
@@ -720,6 +757,52 @@ extern "C" int s252_evaluate_polynomial_on_lde_domain(s252_ctx* ctx, const s252_
         LAUNCH_CHECK(ctx);
     }
     TRY(stage_out(ctx, dout, out, want, mem));
+    return S252_OK;
+}
+
+// One column's transform shared by `parts` GPUs (a single oversized column; four-step with one
+// all-to-all).  The column is seen as a 2^l1 x (N / 2^l1) matrix (first digit x inner position):
+//   phase 0   this GPU runs the first pass on ITS range of inner positions  [part * inner / parts, ..)  of `in`
+//             (natural order, only that slab needs to be valid) and leaves the result in z at the same positions;
+//   exchange  (caller, NCCL) every GPU collects the rows  k1 in [part * 2^l1 / parts, ..)  of z from all the others;
+//   phase 1   this GPU runs the remaining passes on its rows and writes its outputs -- natural index
+//             k = k1 + 2^l1 * q, hence runs of 2^l1 / parts consecutive values (times n_cosets) -- into `out`.
+//   phase 2   only reports l1.
+// inverse != 0: interpolate_fft (n_cosets must be 1).  Otherwise evaluate_offset_fft(n_cosets, Some(N), coset_offset):
+// out[(k * n_cosets + c)].  in: N elements, z: n_cosets * N, out: n_cosets * N (device, internal format).
+extern "C" int s252_ntt_shared(s252_ctx* ctx, unsigned log_n, int inverse, size_t n_cosets, uint64_t coset_offset, int phase, unsigned part,
+                               unsigned parts, const void* in, void* z, void* out, unsigned* log_l1) {
+    NVTX_RANGE("s252_ntt_shared");
+    if (!ctx || phase < 0 || phase > 2 || (phase != 2 && (!in || !z || !out))) return S252_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (n_cosets == 0 || !is_pow2(n_cosets) || n_cosets > MAX_COSETS || (inverse && n_cosets != 1)) FAIL(ctx, S252_ERR_INVALID, "bad coset count");
+    const size_t N = (size_t)1 << log_n;
+    Xform X;
+    X.logn = log_n;
+    if (inverse) {
+        X.inverse = true;
+    } else {
+        if (coset_offset == 0) FAIL(ctx, S252_ERR_INVALID, "coset offset must be non-zero");
+        fe wlen;
+        if (!H::primitive_root(ilog2(N * n_cosets), &wlen)) FAIL(ctx, S252_ERR_INVALID, "domain has no root of unity");
+        X.ncosets = (unsigned)n_cosets;
+        X.shift = H::from_u64(coset_offset);
+        X.step = wlen;
+    }
+    NttShare sh;
+    sh.phase = phase; sh.part = part; sh.parts = parts; sh.zbuf = reinterpret_cast<fe*>(z); sh.log_l1 = log_l1;
+    if (phase == 2) sh.zbuf = reinterpret_cast<fe*>(ctx->ticket);       // any non-null pointer: nothing is launched
+    return run_ntt(ctx, X, reinterpret_cast<const fe*>(in), N, false, reinterpret_cast<fe*>(out), N * n_cosets, false, 1, &sh);
+}
+
+extern "C" int s252_convert_elements(s252_ctx* ctx, const void* in, void* out, size_t n, int to_internal) {
+    if (!ctx || !in || !out) return S252_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (n == 0) return S252_OK;
+    prof_begin(ctx, to_internal ? "lw_to_internal" : "internal_to_lw");
+    if (to_internal) s252::lw_to_internal<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(reinterpret_cast<const fe*>(in), reinterpret_cast<fe*>(out), n);
+    else s252::internal_to_lw<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(reinterpret_cast<const fe*>(in), reinterpret_cast<fe*>(out), n);
+    LAUNCH_CHECK(ctx);
     return S252_OK;
 }
 

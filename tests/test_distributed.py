@@ -72,11 +72,14 @@ def test_sharded_commit_nccl():
     launch("nccl", world, 11, 18, 4, exchange="a2a")
 
 
-@pytest.mark.parametrize("world,args", [(2, ("3", "4", "3", "3", "1")), (4, ("10", "2", "4", "5", "3")), (1, ("3", "4", "2", "3", "1"))])
+@pytest.mark.parametrize("world,args", [(2, ("3", "4", "3", "3", "1")), (4, ("10", "2", "4", "5", "3")), (1, ("3", "4", "2", "3", "1")),
+                                        (2, ("20", "8", "5", "7", "2"))])
 def test_sharded_cairo_proof_gloo(world, args):
-    """The orchestration of the sharded Cairo prover (column shards, exchange, halos, gathers, transcript replay,
-    openings, serialization) on CPU ranks, with the GPU backend replaced by its oracle double
-    (tests/cairo_oracle_backend.py): bytes == the oracle's single-process prover, for both exchange kinds."""
+    """The orchestration of the sharded Cairo prover (column shards, exchange, halos, gathers, row-block trees of the trace tables,
+    of (H1, H2) and of the FRI layers, the pairwise fold exchange, the collapse to one rank, grinding split over the ranks, transcript
+    replay, openings served by the row owners, serialization) on CPU ranks, with the GPU backend replaced by its oracle double
+    (tests/cairo_oracle_backend.py): bytes == the oracle's single-process prover, for both exchange kinds and with the FRI layers
+    sharded down to 8 / 32 evaluations or collapsed at once."""
     worker = os.path.join(ROOT, "tests", "dist_cairo_worker.py")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(free_port()), worker] + list(args) + ["gloo"]
@@ -99,3 +102,30 @@ def test_sharded_cairo_proof_nccl():
         res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, OMP_NUM_THREADS="1"))
         assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
         assert "DIST_CAIRO_OK" in res.stdout
+
+
+@pytest.mark.parametrize("world,args", [(2, ("6", "4", "3")), (4, ("7", "2", "3")), (2, ("5", "8", "2"))])
+def test_sharded_single_column_gloo(world, args):
+    """ONE column over several ranks -- four-step geometry, the transposes and redistributions, the row-block tree and
+    the openings on CPU ranks (the transform phases restated in python integers) == the oracle's interpolate_and_commit."""
+    worker = os.path.join(ROOT, "tests", "dist_column_worker.py")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", str(free_port()), worker, "gloo"] + list(args)
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, OMP_NUM_THREADS="1"))
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    assert "DIST_COLUMN_OK" in res.stdout
+
+
+@pytest.mark.gpu
+def test_sharded_single_column_nccl():
+    import torch
+    g = torch.cuda.device_count()
+    if g < 2:
+        pytest.skip("needs at least two GPUs")
+    worker = os.path.join(ROOT, "tests", "dist_column_worker.py")
+    for world, args in ((2, ("14", "4")), (4 if g >= 4 else 2, ("16", "8")), (g if g in (2, 4, 8) else 2, ("20", "4"))):
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+               "--master-addr", "127.0.0.1", "--master-port", str(free_port()), worker, "nccl"] + list(args)
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, OMP_NUM_THREADS="1"))
+        assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+        assert "DIST_COLUMN_OK" in res.stdout

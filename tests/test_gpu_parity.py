@@ -146,6 +146,64 @@ def test_three_pass_transform_forced_small(ctx):
         c3.close()
 
 
+def _shared_transform(c, log_n, inverse, blowup, parts, data):
+    """s252_ntt_shared with every part played in turn by this one GPU: all phase-0 slabs, then all phase-1 row ranges.  The parts
+    write disjoint positions of z / out, so the result must be the whole transform."""
+    import ctypes as C
+    L = N.lib()
+    n = 1 << log_n
+    cos = 1 if inverse else blowup
+    d_in, d_z, d_out = c.device_alloc(n * 32), c.device_alloc(cos * n * 32), c.device_alloc(cos * n * 32)
+    c.to_device(d_in, data)
+    c.check(L.s252_convert_elements(c.handle, C.c_void_p(d_in), C.c_void_p(d_in), n, 1))
+    l1 = C.c_uint()
+    c.check(L.s252_ntt_shared(c.handle, log_n, int(inverse), cos, 3, 2, 0, parts, None, None, None, C.byref(l1)))
+    for phase in (0, 1):
+        for part in range(parts):
+            c.check(L.s252_ntt_shared(c.handle, log_n, int(inverse), cos, 3, phase, part, parts, C.c_void_p(d_in), C.c_void_p(d_z),
+                                      C.c_void_p(d_out), None))
+    c.check(L.s252_convert_elements(c.handle, C.c_void_p(d_out), C.c_void_p(d_out), cos * n, 0))
+    out = np.empty((cos * n, 4), dtype=np.uint64)
+    c.to_host(out, d_out)
+    for p_ in (d_in, d_z, d_out):
+        c.device_free(p_)
+    return out, int(l1.value)
+
+
+@pytest.mark.parametrize("log_n,blowup,parts", [(12, 4, 2), (13, 2, 4), (16, 4, 8), (18, 8, 8)])
+def test_shared_transform_two_pass(ctx, log_n, blowup, parts):
+    """the four-step split of ONE column's transform over `parts` GPUs (here: one GPU playing every part)."""
+    ev = random_felts(4100 + log_n, 1 << log_n)
+    got, l1 = _shared_transform(ctx, log_n, True, 1, parts, ev)
+    coeffs = O.interpolate_fft(ev)
+    assert (got == coeffs).all()
+    got, _ = _shared_transform(ctx, log_n, False, blowup, parts, coeffs)
+    assert (got == O.evaluate_offset_fft(coeffs, blowup, 1 << log_n, felt.from_int(3))).all()
+    assert 0 < l1 < log_n
+
+
+def test_shared_transform_three_pass_forced_small():
+    old = os.environ.get("S252_MAX_LOGL")
+    os.environ["S252_MAX_LOGL"] = "5"
+    try:
+        c3 = P.Context(0)
+    finally:
+        if old is None:
+            del os.environ["S252_MAX_LOGL"]
+        else:
+            os.environ["S252_MAX_LOGL"] = old
+    try:
+        for log_n, parts in ((11, 2), (13, 4), (15, 8)):
+            ev = random_felts(4200 + log_n, 1 << log_n)
+            got, _ = _shared_transform(c3, log_n, True, 1, parts, ev)
+            coeffs = O.interpolate_fft(ev)
+            assert (got == coeffs).all(), log_n
+            got, _ = _shared_transform(c3, log_n, False, 4, parts, coeffs)
+            assert (got == O.evaluate_offset_fft(coeffs, 4, 1 << log_n, felt.from_int(3))).all(), log_n
+    finally:
+        c3.close()
+
+
 # ---------------------------------------------------------------- Merkle
 @pytest.mark.parametrize("n,c", [(1, 1), (1, 5), (2, 1), (4, 2), (8, 17), (16, 18), (64, 33), (256, 34), (512, 35),
                                  (1024, 1), (2048, 2), (1 << 13, 4), (1 << 10, 52), (1 << 14, 1), (128, 16), (32, 68), (32, 69)])
