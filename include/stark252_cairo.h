@@ -50,6 +50,16 @@ const char *s252_cairo_last_error(void);
  * 1 + entry_offset with the stack [return_fp, end], and execution stops at the final `ret`. */
 int s252_cairo_vm_run(const uint8_t *program_be, size_t n_words, uint64_t entry_offset, uint64_t max_steps,
                       s252_cairo_run **out);
+/* The same for programs that declare builtins (cairo-vm's BuiltinRunner for the two the AIR knows, src/cairo/air.rs:594-625):
+ * builtins = S252_BUILTIN_OUTPUT | S252_BUILTIN_RANGE_CHECK.  main receives the segment base pointers on the stack below
+ * [return_fp, end], output first (the %builtins order); the segments are relocated behind the execution segment.
+ * s252_cairo_run_segment reports the relocated [begin, end) of a segment (which: 0 = range_check, 1 = output) -- what
+ * generate_prover_args passes on as range_check_builtin_range / output range (run.rs:243-266); returns 1 if present. */
+#define S252_BUILTIN_OUTPUT 1u
+#define S252_BUILTIN_RANGE_CHECK 2u
+int s252_cairo_vm_run_builtins(const uint8_t *program_be, size_t n_words, uint64_t entry_offset, uint64_t max_steps,
+                               unsigned builtins, s252_cairo_run **out);
+int s252_cairo_run_segment(const s252_cairo_run *run, int which, uint64_t range[2]);
 void s252_cairo_run_destroy(s252_cairo_run *run);
 size_t s252_cairo_run_steps(const s252_cairo_run *run);
 size_t s252_cairo_run_trace_len(const s252_cairo_run *run);    /* bytes: 24 per step */

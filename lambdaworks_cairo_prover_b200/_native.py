@@ -93,6 +93,8 @@ SIGNATURES = {
     # include/stark252_cairo.h
     "s252_cairo_last_error": (C.c_char_p, []),
     "s252_cairo_vm_run": (_i, [_vp, _sz, _u64, _u64, C.POINTER(_vp)]),
+    "s252_cairo_vm_run_builtins": (_i, [_vp, _sz, _u64, _u64, C.c_uint, C.POINTER(_vp)]),
+    "s252_cairo_run_segment": (_i, [_vp, _i, _vp]),
     "s252_cairo_run_destroy": (None, [_vp]),
     "s252_cairo_run_steps": (_sz, [_vp]),
     "s252_cairo_run_trace_len": (_sz, [_vp]),

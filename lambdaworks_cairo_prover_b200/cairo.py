@@ -113,6 +113,36 @@ def run_program(words, entry_offset=0, max_steps=0):
     return trace.tobytes(), memory.tobytes(), len(words)
 
 
+BUILTINS = {"output": 1, "range_check": 2}
+
+
+def run_program_with_builtins(words, builtins, entry_offset=0, max_steps=0):
+    """run_program for a program that declares builtins ("output", "range_check": cairo-vm's BuiltinRunner for the two the AIR
+    knows).  Returns (register_states_bytes, memory_bytes, program_size, rc_range, output_range): the ranges are what
+    generate_prover_args hands to build_main_trace (run.rs:243-266), None for an absent builtin."""
+    L = N.lib()
+    be = b"".join(int(w).to_bytes(32, "big") for w in words)
+    buf = np.frombuffer(be, dtype=np.uint8)
+    mask = 0
+    for b in builtins:
+        mask |= BUILTINS[b]
+    h = C.c_void_p()
+    _check(L.s252_cairo_vm_run_builtins(N.ptr(buf), len(words), entry_offset, max_steps, mask, C.byref(h)))
+    try:
+        trace = np.zeros(L.s252_cairo_run_trace_len(h), dtype=np.uint8)
+        memory = np.zeros(L.s252_cairo_run_memory_len(h), dtype=np.uint8)
+        L.s252_cairo_run_trace_bytes(h, N.ptr(trace))
+        L.s252_cairo_run_memory_bytes(h, N.ptr(memory))
+        ranges = []
+        for which in (0, 1):
+            r = np.zeros(2, dtype=np.uint64)
+            present = L.s252_cairo_run_segment(h, which, N.ptr(r))
+            ranges.append((int(r[0]), int(r[1])) if present else None)
+    finally:
+        L.s252_cairo_run_destroy(h)
+    return trace.tobytes(), memory.tobytes(), len(words), ranges[0], ranges[1]
+
+
 def _range_arg(r):
     return None if r is None else np.array([r[0], r[1]] if not isinstance(r, range) else [r.start, r.stop], dtype=np.uint64)
 

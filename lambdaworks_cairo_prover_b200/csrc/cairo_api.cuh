@@ -32,8 +32,26 @@ struct s252_cairo_trace {
 
 extern "C" const char* s252_cairo_last_error(void) { return g_cairo_err.c_str(); }
 
+static int cairo_vm_run_impl(const uint8_t* program_be, size_t n_words, uint64_t entry_offset, uint64_t max_steps, unsigned builtins,
+                             s252_cairo_run** out);
 extern "C" int s252_cairo_vm_run(const uint8_t* program_be, size_t n_words, uint64_t entry_offset, uint64_t max_steps,
                                  s252_cairo_run** out) {
+    return cairo_vm_run_impl(program_be, n_words, entry_offset, max_steps, 0, out);
+}
+extern "C" int s252_cairo_vm_run_builtins(const uint8_t* program_be, size_t n_words, uint64_t entry_offset, uint64_t max_steps,
+                                          unsigned builtins, s252_cairo_run** out) {
+    if (builtins & ~(CA::BUILTIN_OUTPUT | CA::BUILTIN_RANGE_CHECK)) CAIRO_FAIL(S252_ERR_INVALID, "unsupported builtin");
+    return cairo_vm_run_impl(program_be, n_words, entry_offset, max_steps, builtins, out);
+}
+extern "C" int s252_cairo_run_segment(const s252_cairo_run* run, int which, uint64_t range[2]) {
+    if (!run || !range) return 0;
+    const bool has = which == 0 ? run->r.has_rc : run->r.has_output;
+    const uint64_t* r = which == 0 ? run->r.rc_range : run->r.output_range;
+    range[0] = r[0]; range[1] = r[1];
+    return has ? 1 : 0;
+}
+static int cairo_vm_run_impl(const uint8_t* program_be, size_t n_words, uint64_t entry_offset, uint64_t max_steps, unsigned builtins,
+                             s252_cairo_run** out) {
     if (!program_be || !n_words || !out || entry_offset >= n_words) CAIRO_FAIL(S252_ERR_INVALID, "bad program");
     s252_cairo_run* run = nullptr;
     try {
@@ -41,7 +59,7 @@ extern "C" int s252_cairo_vm_run(const uint8_t* program_be, size_t n_words, uint
         for (size_t i = 0; i < n_words; ++i) prog[i] = H::from_bytes_be(program_be + 32 * i);
         run = new s252_cairo_run();
         std::string err;
-        if (!CA::vm_run(prog, entry_offset, max_steps ? max_steps : ~0ULL, &run->r, &err)) {
+        if (!CA::vm_run(prog, entry_offset, max_steps ? max_steps : ~0ULL, &run->r, &err, builtins)) {
             delete run;
             CAIRO_FAIL(S252_ERR_INVALID, "cairo vm: " + err);
         }

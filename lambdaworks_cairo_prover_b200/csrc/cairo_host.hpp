@@ -118,15 +118,32 @@ struct Memory {
 // The machine.  Program at addresses 1..n, execution segment right after it; main is entered with
 // the stack [return_fp, end] (two empty segments, relocated after the run) and the run stops when
 // the final `ret` jumps to `end`.
+// Builtins (cairo-vm's BuiltinRunner, as far as hint-free programs need them): `output` and `range_check`, each a memory
+// segment of its own whose base pointer main receives on the stack in the order of the %builtins directive
+// (output before range_check); after the run the segments are laid out behind the execution segment
+// (run.rs:62-100 relocates; generate_prover_args, run.rs:243-266, hands the range-check range to the AIR).
+enum : unsigned { BUILTIN_OUTPUT = 1, BUILTIN_RANGE_CHECK = 2 };
 struct VmResult {
     std::vector<RegisterState> trace;
     std::vector<std::pair<uint64_t, fe>> memory;   // sorted by address
     size_t program_size = 0;
+    bool has_output = false, has_rc = false;
+    uint64_t output_range[2] = {0, 0}, rc_range[2] = {0, 0};   // [begin, end) after relocation
 };
-inline bool vm_run(const std::vector<fe>& program, uint64_t entry_offset, uint64_t max_steps, VmResult* out, std::string* err) {
+inline bool vm_run(const std::vector<fe>& program, uint64_t entry_offset, uint64_t max_steps, VmResult* out, std::string* err,
+                   unsigned builtins = 0) {
     const uint64_t P = program.size();
     const uint64_t exec_base = 1 + P;
     const uint64_t SENT_FP = (1ULL << 62), SENT_PC = (1ULL << 62) + 1;
+    // builtin segments live at sentinel bases until relocation; a cell value inside such a window is a pointer into the segment
+    const uint64_t SEG_BASE[2] = {1ULL << 60, (1ULL << 60) + (1ULL << 50)}, SEG_SPAN = 1ULL << 24;
+    const unsigned SEG_BIT[2] = {BUILTIN_OUTPUT, BUILTIN_RANGE_CHECK};
+    std::vector<fe> seg_mem[2];
+    std::vector<uint8_t> seg_known[2];
+    auto seg_of = [&](uint64_t a) -> int {
+        for (int s = 0; s < 2; ++s) if ((builtins & SEG_BIT[s]) && a >= SEG_BASE[s] && a < SEG_BASE[s] + SEG_SPAN) return s;
+        return -1;
+    };
     // Flat memory: a stray write far away must not allocate gigabytes.  The segments of a run are contiguous after
     // relocation, so every legitimate address is below program + 4 cells per step (+ slack); S252_CAIRO_MAX_ADDRESS raises the cap.
     uint64_t MAX_ADDRESS = std::min<uint64_t>(1ULL << 28, (uint64_t)program.size() + 4 * std::min<uint64_t>(max_steps, 1ULL << 26) + (1u << 16));
@@ -135,25 +152,43 @@ inline bool vm_run(const std::vector<fe>& program, uint64_t entry_offset, uint64
     std::vector<uint8_t> known;
     auto ensure = [&](uint64_t a) { if (a >= mem.size()) { size_t n = std::max<size_t>(a + 1, mem.size() * 2); mem.resize(n, fe_zero()); known.resize(n, 0); } };
     auto set = [&](uint64_t a, const fe& v) -> bool {
+        const int sg = seg_of(a);
+        if (sg >= 0) {
+            const uint64_t o = a - SEG_BASE[sg];
+            if (o >= seg_mem[sg].size()) { seg_mem[sg].resize(o + 1, fe_zero()); seg_known[sg].resize(o + 1, 0); }
+            if (seg_known[sg][o]) return H::eq(seg_mem[sg][o], v);
+            seg_mem[sg][o] = v; seg_known[sg][o] = 1;
+            return true;
+        }
         if (a == 0 || a >= MAX_ADDRESS) return false;
         ensure(a);
         if (known[a]) return H::eq(mem[a], v);
         mem[a] = v; known[a] = 1;
         return true;
     };
-    auto has = [&](uint64_t a) { return a < mem.size() && known[a]; };
-    ensure(exec_base + 2);
+    auto has = [&](uint64_t a) {
+        const int sg = seg_of(a);
+        if (sg >= 0) { const uint64_t o = a - SEG_BASE[sg]; return o < seg_mem[sg].size() && seg_known[sg][o] != 0; }
+        return a < mem.size() && known[a];
+    };
+    auto get = [&](uint64_t a) -> const fe& {
+        const int sg = seg_of(a);
+        return sg >= 0 ? seg_mem[sg][a - SEG_BASE[sg]] : mem[a];
+    };
+    unsigned n_stack = 0;
+    ensure(exec_base + 4);
     for (uint64_t i = 0; i < P; ++i) set(1 + i, program[i]);
-    set(exec_base, H::from_u64(SENT_FP));
-    set(exec_base + 1, H::from_u64(SENT_PC));
-    uint64_t pc = 1 + entry_offset, ap = exec_base + 2, fp = exec_base + 2;
-    uint64_t max_exec = exec_base + 1;
+    for (int sg = 0; sg < 2; ++sg) if (builtins & SEG_BIT[sg]) set(exec_base + n_stack++, H::from_u64(SEG_BASE[sg]));
+    set(exec_base + n_stack, H::from_u64(SENT_FP));
+    set(exec_base + n_stack + 1, H::from_u64(SENT_PC));
+    uint64_t pc = 1 + entry_offset, ap = exec_base + n_stack + 2, fp = exec_base + n_stack + 2;
+    uint64_t max_exec = exec_base + n_stack + 1;
     out->trace.clear();
     while (pc != SENT_PC) {
         if (out->trace.size() >= max_steps) { *err = "step limit reached"; return false; }
         if (!has(pc)) { *err = "InstructionNotFound"; return false; }
         Instr in;
-        if (!decode(mem[pc], &in, err)) return false;
+        if (!decode(get(pc), &in, err)) return false;
         out->trace.push_back({pc, fp, ap});
         const uint64_t dst_addr = (in.bit(F_DST_FP) ? fp : ap) + (int64_t)in.soff[0];
         const uint64_t op0_addr = (in.bit(F_OP_0_FP) ? fp : ap) + (int64_t)in.soff[1];
@@ -166,7 +201,7 @@ inline bool vm_run(const std::vector<fe>& program, uint64_t entry_offset, uint64
         switch (in.op1_src()) {
             case 0:
                 if (!has(op0_addr)) { *err = "op0 unknown for double dereference"; return false; }
-                op1_addr = low64(mem[op0_addr]) + (int64_t)in.soff[2];
+                op1_addr = low64(get(op0_addr)) + (int64_t)in.soff[2];
                 break;
             case 1: op1_addr = pc + (int64_t)in.soff[2]; break;
             case 2: op1_addr = fp + (int64_t)in.soff[2]; break;
@@ -174,21 +209,21 @@ inline bool vm_run(const std::vector<fe>& program, uint64_t entry_offset, uint64
         }
         // operand deduction for assert_eq (Cairo whitepaper section 8.4)
         if (in.opcode() == 4 && has(dst_addr)) {
-            const fe dst = mem[dst_addr];
+            const fe dst = get(dst_addr);
             if (in.res_logic() == 0 && !has(op1_addr)) set(op1_addr, dst);
             if (in.res_logic() == 1) {
-                if (!has(op1_addr) && has(op0_addr)) set(op1_addr, H::sub(dst, mem[op0_addr]));
-                else if (!has(op0_addr) && has(op1_addr)) set(op0_addr, H::sub(dst, mem[op1_addr]));
+                if (!has(op1_addr) && has(op0_addr)) set(op1_addr, H::sub(dst, get(op0_addr)));
+                else if (!has(op0_addr) && has(op1_addr)) set(op0_addr, H::sub(dst, get(op1_addr)));
             }
             if (in.res_logic() == 2) {
-                if (!has(op1_addr) && has(op0_addr) && !H::is_zero(mem[op0_addr])) set(op1_addr, H::mul(dst, H::inv(mem[op0_addr])));
-                else if (!has(op0_addr) && has(op1_addr) && !H::is_zero(mem[op1_addr])) set(op0_addr, H::mul(dst, H::inv(mem[op1_addr])));
+                if (!has(op1_addr) && has(op0_addr) && !H::is_zero(get(op0_addr))) set(op1_addr, H::mul(dst, H::inv(get(op0_addr))));
+                else if (!has(op0_addr) && has(op1_addr) && !H::is_zero(get(op1_addr))) set(op0_addr, H::mul(dst, H::inv(get(op1_addr))));
             }
         }
         fe res = fe_zero();
         bool res_known = false;
         if (in.pc_update() != 4 && has(op1_addr) && (in.res_logic() == 0 || has(op0_addr))) {
-            res = in.res_logic() == 0 ? mem[op1_addr] : in.res_logic() == 1 ? H::add(mem[op0_addr], mem[op1_addr]) : H::mul(mem[op0_addr], mem[op1_addr]);
+            res = in.res_logic() == 0 ? get(op1_addr) : in.res_logic() == 1 ? H::add(get(op0_addr), get(op1_addr)) : H::mul(get(op0_addr), get(op1_addr));
             res_known = true;
         }
         if (in.opcode() == 4) {
@@ -207,7 +242,7 @@ inline bool vm_run(const std::vector<fe>& program, uint64_t entry_offset, uint64
             case 0: npc = pc + size; break;
             case 1: if (!res_known) { *err = "jmp abs: res unknown"; return false; } npc = low64(res); break;
             case 2: if (!res_known) { *err = "jmp rel: res unknown"; return false; } npc = low64(H::add(H::from_u64(pc), res)); break;
-            default: npc = H::is_zero(mem[dst_addr]) ? pc + size : low64(H::add(H::from_u64(pc), mem[op1_addr])); break;
+            default: npc = H::is_zero(get(dst_addr)) ? pc + size : low64(H::add(H::from_u64(pc), get(op1_addr))); break;
         }
         switch (in.ap_update()) {
             case 0: nap = ap + (in.opcode() == 1 ? 2 : 0); break;
@@ -215,20 +250,50 @@ inline bool vm_run(const std::vector<fe>& program, uint64_t entry_offset, uint64
             default: nap = ap + 1; break;
         }
         if (in.opcode() == 1) nfp = ap + 2;
-        else if (in.opcode() == 2) nfp = low64(mem[dst_addr]);
+        else if (in.opcode() == 2) nfp = low64(get(dst_addr));
         else nfp = fp;
         pc = npc; ap = nap; fp = nfp;
     }
-    // relocation of the two empty segments [return_fp], [end]: both start where the execution segment ends
+    // relocation: the builtin segments follow the execution segment in declaration order, then the two empty segments
+    // [return_fp], [end] (both start where the last segment ends)
     const uint64_t exec_size = max_exec + 1 - exec_base;
-    const fe reloc = H::from_u64(exec_base + exec_size);
+    uint64_t next = exec_base + exec_size, seg_reloc[2] = {0, 0};
+    for (int sg = 0; sg < 2; ++sg) {
+        if (!(builtins & SEG_BIT[sg])) continue;
+        seg_reloc[sg] = next;
+        next += seg_mem[sg].size();
+    }
+    out->has_output = (builtins & BUILTIN_OUTPUT) != 0;
+    out->has_rc = (builtins & BUILTIN_RANGE_CHECK) != 0;
+    out->output_range[0] = seg_reloc[0]; out->output_range[1] = seg_reloc[0] + seg_mem[0].size();
+    out->rc_range[0] = seg_reloc[1]; out->rc_range[1] = seg_reloc[1] + seg_mem[1].size();
+    const fe reloc = H::from_u64(next);
     const fe sfp = H::from_u64(SENT_FP), spc = H::from_u64(SENT_PC);
+    auto relocate = [&](const fe& v) -> fe {
+        if (H::eq(v, sfp) || H::eq(v, spc)) return reloc;
+        if (builtins) {
+            const H::U256 c = H::to_u256(H::from_mont(v));
+            if (c.w[1] == 0 && c.w[2] == 0 && c.w[3] == 0)
+                for (int sg = 0; sg < 2; ++sg)      // one past the end is a valid pointer (the final builtin pointer main returns)
+                    if ((builtins & SEG_BIT[sg]) && c.w[0] >= SEG_BASE[sg] && c.w[0] <= SEG_BASE[sg] + SEG_SPAN) return H::from_u64(seg_reloc[sg] + (c.w[0] - SEG_BASE[sg]));
+        }
+        return v;
+    };
     out->memory.clear();
     for (uint64_t a = 1; a < mem.size(); ++a) {
         if (!known[a]) continue;
-        fe v = mem[a];
-        if (H::eq(v, sfp) || H::eq(v, spc)) v = reloc;
-        out->memory.push_back({a, v});
+        out->memory.push_back({a, relocate(mem[a])});
+    }
+    for (int sg = 0; sg < 2; ++sg) {
+        if (!(builtins & SEG_BIT[sg])) continue;
+        for (uint64_t o = 0; o < seg_mem[sg].size(); ++o) {
+            if (!seg_known[sg][o]) { *err = "a builtin segment has an unwritten cell"; return false; }
+            if (sg == 1) {      // RangeCheckBuiltinRunner: every value is below 2^128
+                const H::U256 c = H::to_u256(H::from_mont(seg_mem[sg][o]));
+                if (c.w[2] || c.w[3]) { *err = "range-check builtin: value out of range"; return false; }
+            }
+            out->memory.push_back({seg_reloc[sg] + o, relocate(seg_mem[sg][o])});
+        }
     }
     out->program_size = P;
     return true;

@@ -864,10 +864,11 @@ static std::vector<unsigned> upload_groups(unsigned c) {
     return lo;
 }
 // How a host table reaches the device (S252_HOST callers):
-//   2 = pinned memory, read over PCIe by the transposing kernel itself (rows_lw_to_cols_stream), column group by
-//       column group on the copy stream while the previous group is transformed;
-//   1 = pinned memory, strided 2-D DMA of each column group + tile transpose (S252_HOST_UPLOAD=dma2d);
-//   0 = pageable memory (or S252_HOST_UPLOAD=copy): one copy of the whole table on the compute stream.
+//   1 = pinned memory (default): strided 2-D DMA of one column group after the other on the copy stream + tile
+//       transpose, while the previous group is transformed;
+//   2 = pinned memory, read over PCIe by the transposing kernel itself (rows_lw_to_cols_stream; S252_HOST_UPLOAD=zc).
+//       Measured slower than the DMA on B200 (C2 step 48.0 vs 40.8 ms): 32-byte element reads make poor PCIe requests;
+//   0 = pageable memory (or S252_HOST_UPLOAD=copy): one copy of the whole table on the compute stream (49.0 ms).
 static int host_upload_mode(const void* p, const void** dev_alias) {
     *dev_alias = nullptr;
     const char* e = std::getenv("S252_HOST_UPLOAD");
@@ -875,8 +876,7 @@ static int host_upload_mode(const void* p, const void** dev_alias) {
     cudaPointerAttributes attr{};
     if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return 0; }
     if (attr.type != cudaMemoryTypeHost) return 0;
-    if (e && !std::strcmp(e, "dma2d")) return 1;
-    if (!attr.devicePointer) return 1;
+    if (!e || std::strcmp(e, "zc") || !attr.devicePointer) return 1;
     *dev_alias = attr.devicePointer;
     return 2;
 }
@@ -1213,7 +1213,7 @@ static void fri_free(s252_fri* f) {
 // last value back ONCE and replays the same appends on its own transcript (checking the last zeta).
 static unsigned fri_tail_log_max() {
     if (const char* e = std::getenv("S252_FRI_TAIL_LOG")) { const int v = std::atoi(e); if (v >= 0 && v <= (int)s252::FRI_TAIL_LOG_MAX) return (unsigned)v; }
-    return 13;
+    return 11;      // measured on the C2 step (B200): 0 -> 32.30, 11 -> 32.23, 13 -> 32.61, 14 -> 33.15 ms
 }
 static int fri_from_layer0(s252_ctx* ctx, s252_fri* f, size_t number_layers, s252_transcript* transcript, fe h,
                            size_t domain_size, s252_fe* last_value, uint8_t* roots_out) {

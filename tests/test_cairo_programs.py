@@ -89,3 +89,66 @@ def test_expected_values_of_the_arith_program():
     cells = {int.from_bytes(mem[40 * i:40 * i + 8], "little"): int.from_bytes(mem[40 * i + 8:40 * i + 40], "little") for i in range(len(mem) // 40)}
     base = size + 3                                                          # first free cell: program, return fp, return pc
     assert [cells[base + k] for k in range(6)] == [7, 9, 63, 70, 12415, (-3 * 12415) % P]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Programs that declare builtins (hint-free equivalents of the reference's cairo_programs/cairo0/rc_program.cairo and
+# output_program.cairo / signed_div_rem.cairo, tests/integration_tests.rs:153-172: those use library functions whose hints
+# need cairo-lang; here the range-checked / output values are written directly).  main's frame: the builtin pointers sit
+# below [return_fp, return_pc], output first.  The 43-column layout (range-check builtin columns, air.rs:594-625) comes out
+# of a real execution.
+def assert_at_ptr(ptr_fp_off, k):      # [[fp + ptr_fp_off] + k] = [ap - 1]
+    return ins(-1, ptr_fp_off, k, dst_fp=0, op0_fp=1, op1="op0", opcode="assert_eq")
+
+
+def ret_ptr_plus(ptr_fp_off, k):       # [ap] = [fp + ptr_fp_off] + k; ap++
+    return [ins(0, ptr_fp_off, 1, dst_fp=0, op0_fp=1, op1="imm", res="add", ap="add1", opcode="assert_eq"), k]
+
+
+BUILTIN_PROGRAMS = {
+    # %builtins range_check: three values through the builtin (assert_nn(5), assert_nn(2) in rc_program.cairo range-check 5 and 2)
+    "rc": (("range_check",),
+           push_imm(5) + [assert_at_ptr(-3, 0)] + push_imm(2) + [assert_at_ptr(-3, 1)] + push_imm(2**100 + 12345) + [assert_at_ptr(-3, 2)]
+           + ret_ptr_plus(-3, 3) + [RET]),
+    # %builtins output range_check: serialize_word twice, one range check, both pointers returned
+    "output_rc": (("output", "range_check"),
+                  push_imm(1234) + [assert_at_ptr(-4, 0)] + push_imm(P - 4) + [assert_at_ptr(-4, 1)] + push_imm(70000) + [assert_at_ptr(-3, 0)]
+                  + ret_ptr_plus(-4, 2) + ret_ptr_plus(-3, 1) + [RET]),
+    # a loop that range-checks a countdown: the pointer is threaded through ap like compiled code does
+    "rc_loop": (("range_check",),
+                [ins(0, -3, -3, dst_fp=0, op0_fp=1, op1="fp", ap="add1", opcode="assert_eq")]      # [ap] = [fp-3] (rc ptr); ap++
+                + push_imm(3)                                                                       # counter
+                + [ins(-1, -2, 0, dst_fp=0, op0_fp=0, op1="op0", opcode="assert_eq"),              # loop: [[ap-2]] = [ap-1]
+                   ins(0, -2, 1, dst_fp=0, op0_fp=0, op1="imm", res="add", ap="add1", opcode="assert_eq"), 1,       # [ap] = [ap-2] + 1 (ptr)
+                   ins(0, -2, 1, dst_fp=0, op0_fp=0, op1="imm", res="add", ap="add1", opcode="assert_eq"), P - 1,   # [ap] = [ap-2] - 1 (counter)
+                   ins(-1, -1, 1, dst_fp=0, op1="imm", pc="jnz"), P - 5,                           # jmp loop if counter != 0
+                   ins(0, -2, -2, dst_fp=0, op0_fp=0, op1="ap", ap="add1", opcode="assert_eq"),    # [ap] = [ap-2] (final ptr); ap++
+                   RET]),
+}
+
+
+@pytest.mark.parametrize("name", sorted(BUILTIN_PROGRAMS))
+def test_builtin_program_trace_satisfies_the_air(name):
+    builtins, words = BUILTIN_PROGRAMS[name]
+    regs, mem, size, rc_range, out_range = cairo.run_program_with_builtins(words, builtins)
+    assert (rc_range is not None) == ("range_check" in builtins) and (out_range is not None) == ("output" in builtins)
+    cells = {int.from_bytes(mem[40 * i:40 * i + 8], "little"): int.from_bytes(mem[40 * i + 8:40 * i + 40], "little") for i in range(len(mem) // 40)}
+    if name == "rc":
+        assert [cells[a] for a in range(*rc_range)] == [5, 2, 2**100 + 12345]
+    if name == "output_rc":
+        assert [cells[a] for a in range(*out_range)] == [1234, P - 4] and [cells[a] for a in range(*rc_range)] == [70000]
+        assert out_range[1] == rc_range[0]                        # segments are laid out in declaration order
+    if name == "rc_loop":
+        assert [cells[a] for a in range(*rc_range)] == [3, 2, 1]
+    t = cairo.build_main_trace(regs, mem, size, rc_range, out_range)
+    assert t.n_cols == 43                                         # 34 + the nine range-check builtin columns
+    table = np.array(t.table).reshape(t.n_rows(), t.n_cols, 4)
+    opts = ProofOptions.default_test_options()
+    proof = cairo_prove(table, t.pub_inputs, opts, threads=1)     # raises if one of the 50 transition constraints is violated
+    assert cairo_verify(StarkProof.parse(proof.serialize()), t.pub_inputs, opts)
+
+
+def test_range_check_builtin_rejects_wide_values():
+    words = push_imm(2**128) + [assert_at_ptr(-3, 0)] + ret_ptr_plus(-3, 1) + [RET]
+    with pytest.raises(Exception):
+        cairo.run_program_with_builtins(words, ("range_check",))
