@@ -788,6 +788,7 @@ def main():
     # stdout carries exactly one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
     if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
         os.environ["NCCL_DEBUG"] = "WARN"
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL_DEBUG=INFO lines (comm sizes, transports) belong on stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

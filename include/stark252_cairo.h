@@ -135,6 +135,16 @@ int s252_cairo_constraint_evaluations(s252_ctx *ctx, const s252_cairo_trace *tra
 int s252_cairo_prove(s252_ctx *ctx, const s252_cairo_trace *trace, size_t blowup, size_t fri_number_of_queries,
                      uint64_t coset_offset, uint8_t grinding_factor, uint8_t **proof_out, size_t *proof_len);
 void s252_cairo_proof_free(uint8_t *proof);
+/* StarkProof::serialize (proof/stark.rs:161-218) from pieces the caller assembled (the sharded prover gathers them from several
+ * GPUs): ood = the frame (2 x cols, row-major; cols = main_cols + aux_cols), hz = H1(z^2), H2(z^2); evs / ev / pas / pa as
+ * s252_fri_query returns them ([Q][layers] values, [Q][layers][depth] digests, layer k uses depth - k of them); rows and paths as
+ * s252_commit_open returns them (depth digests per query).  *proof_out is malloc'ed; release it with s252_cairo_proof_free. */
+int s252_cairo_serialize_proof(size_t trace_rows, const uint8_t *root_main, const uint8_t *root_aux, const uint8_t *root_comp,
+                               const s252_fe *ood, size_t cols, const s252_fe *hz, size_t layers, const uint8_t *fri_roots,
+                               const s252_fe *last, size_t n_queries, size_t depth, const s252_fe *evs, const s252_fe *ev,
+                               const uint8_t *pas, const uint8_t *pa, const s252_fe *comp_rows, const uint8_t *comp_paths,
+                               const s252_fe *main_rows, size_t main_cols, const uint8_t *main_paths, const s252_fe *aux_rows,
+                               size_t aux_cols, const uint8_t *aux_paths, uint64_t nonce, uint8_t **proof_out, size_t *proof_len);
 /* ---- building blocks of a proof sharded over several GPUs ------------------------------------
  * The same kernels as s252_cairo_prove, applied to this rank's columns (LDE) or to this rank's block of
  * LDE rows; lambdaworks_cairo_prover_b200/cairo_distributed.py strings them together with NCCL.

@@ -127,6 +127,8 @@ SIGNATURES = {
     "s252_deep_rows": (_i, [_vp, _vp, _vp, _vp, _sz, _sz, _sz, _sz, _sz, _vp, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _vp]),
     "s252_cairo_prove": (_i, [_vp, _vp, _sz, _sz, _u64, _u8, C.POINTER(_vp), C.POINTER(_sz)]),
     "s252_cairo_proof_free": (None, [_vp]),
+    "s252_cairo_serialize_proof": (_i, [_sz, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp, _vp, _sz, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp,
+                                        _vp, _sz, _vp, _u64, C.POINTER(_vp), C.POINTER(_sz)]),
     "s252_cairo_last_prove_stages": (C.c_char_p, []),
 }
 

@@ -8,7 +8,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
-SO = os.path.join(LIBDIR, "libstark252_b200.so")
+# S252_LIB_SUFFIX selects a kernel-variant build (experiments: tools/ntt_variants.sh); empty = the product library
+SO = os.path.join(LIBDIR, "libstark252_b200%s.so" % os.environ.get("S252_LIB_SUFFIX", ""))
 SOURCES = ["runtime.cu"]
 
 
@@ -24,7 +25,7 @@ def needs_build():
         return True
     t = os.path.getmtime(SO)
     # every file the translation unit can include: the list is globbed so that it cannot drift from the sources
-    deps = [f for pat in ("*.cu", "*.cuh", "*.hpp", "*.h") for f in glob.glob(os.path.join(CSRC, pat))]
+    deps = [f for pat in ("*.cu", "*.cuh", "*.hpp", "*.h", "*.inc") for f in glob.glob(os.path.join(CSRC, pat))]
     deps += glob.glob(os.path.join(os.path.dirname(HERE), "include", "*.h"))
     deps.append(os.path.abspath(__file__))
     return any(os.path.getmtime(d) > t for d in deps)

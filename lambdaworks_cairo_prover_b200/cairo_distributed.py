@@ -194,6 +194,31 @@ class GpuCairoBackend(D.GpuBackend):
     def to_bytes_be(v):
         return felt.to_bytes_be(v)
 
+    def serialize_proof(self, n, roots, ood, hz, layers, fri_roots, last, depth, fq, opened, nonce):
+        """StarkProof::serialize in the library (s252_cairo_serialize_proof) from the gathered pieces."""
+        cont = lambda a, dt: np.ascontiguousarray(a, dtype=dt)                                       # noqa: E731
+        q = 0 if fq is None else fq[0].shape[0]
+        if q:
+            ev, evs, pa, pas = (cont(fq[0], np.uint64), cont(fq[1], np.uint64), cont(fq[2], np.uint8), cont(fq[3], np.uint8))
+            (mr, mp), (ar, ap), (cr, cp) = [(cont(r_, np.uint64), cont(p_, np.uint8)) for r_, p_ in opened]
+            args = [N.ptr(evs), N.ptr(ev), N.ptr(pas), N.ptr(pa), N.ptr(cr), N.ptr(cp), N.ptr(mr), mr.shape[1], N.ptr(mp), N.ptr(ar), ar.shape[1], N.ptr(ap)]
+            main_cols, aux_cols = mr.shape[1], ar.shape[1]
+        else:
+            main_cols = ood.shape[1] - 18
+            args = [None, None, None, None, None, None, None, main_cols, None, None, 18, None]
+        ood_c, hz_c, last_c = cont(ood, np.uint64), cont(hz, np.uint64), cont(last, np.uint64)
+        fr = np.frombuffer(b"".join(fri_roots), dtype=np.uint8) if layers else np.zeros(32, dtype=np.uint8)
+        rts = [np.frombuffer(r, dtype=np.uint8) for r in roots]
+        out, ln = C.c_void_p(), C.c_size_t()
+        rc = self.L.s252_cairo_serialize_proof(n, N.ptr(rts[0]), N.ptr(rts[1]), N.ptr(rts[2]), N.ptr(ood_c), ood.shape[1], N.ptr(hz_c), layers, N.ptr(fr),
+                                               N.ptr(last_c), q, depth, *args, nonce, C.byref(out), C.byref(ln))
+        if rc != N.OK:
+            raise N.Stark252Error(rc, self.L.s252_cairo_last_error().decode())
+        try:
+            return C.string_at(out.value, ln.value)
+        finally:
+            self.L.s252_cairo_proof_free(out)
+
     def fri_commit_phase_evals(self, p0, layers, t, opts):
         """-> (fri handle, last value LW, roots uint8[layers, 32])"""
         fri = C.c_void_p()
@@ -377,9 +402,18 @@ def _prove_sharded(trace, options, be, group, timings, exchange, fri_collapse_lo
     mine_ood = (local_ood(sc_main.local), local_ood(sc_aux.local))
     hz = be.evaluate_at(comp, felt.from_ints([z * z % P]))[0]                    # H1(z^2), H2(z^2): every rank holds H1, H2
     if world > 1:
-        parts = [None] * world
-        dist.all_gather_object(parts, mine_ood, group=group)
-        ood = np.concatenate([p_[0] for p_ in parts] + [p_[1] for p_ in parts], axis=1)        # [2, 52, 4]
+        # one all-gather of fixed-size slots (the column counts per rank differ by at most one: pad to the largest)
+        sm_, sa_ = D.column_shards(c_main, world), D.column_shards(18, world)
+        wm, wa = max(hi - lo for lo, hi in sm_), max(hi - lo for lo, hi in sa_)
+        slot = np.zeros((2, wm + wa, 4), dtype=np.uint64)
+        slot[:, :mine_ood[0].shape[1]] = mine_ood[0]
+        slot[:, wm:wm + mine_ood[1].shape[1]] = mine_ood[1]
+        mine_t = torch.from_numpy(slot.view(np.int64)).to(device)
+        all_t = torch.empty((world,) + tuple(mine_t.shape), dtype=torch.int64, device=device)
+        dist.all_gather_into_tensor(all_t.view(-1), mine_t.view(-1), group=group)
+        slots = all_t.cpu().numpy().view(np.uint64)                                             # [world, 2, wm + wa, 4]
+        ood = np.concatenate([slots[r, :, :hi - lo] for r, (lo, hi) in enumerate(sm_)] +
+                             [slots[r, :, wm:wm + hi - lo] for r, (lo, hi) in enumerate(sa_)], axis=1)   # [2, 52, 4]
     else:
         ood = np.concatenate(mine_ood, axis=1)
     ncols = ood.shape[1]
@@ -403,16 +437,18 @@ def _prove_sharded(trace, options, be, group, timings, exchange, fri_collapse_lo
     t.append(_u64be(nonce))                                                      # prover.rs:385
     idx = [be.to_usize(t) % m for _ in range(q_count)]                           # every rank samples the same indices
     mark("grinding")
-    opened = D.open_many([sc_main, sc_aux, sc_comp], idx) if q_count else [([], [])] * 3
-    (main_rows, main_paths), (aux_rows, aux_paths), (comp_rows, comp_paths) = opened
+    opened = D.open_many_packed([sc_main, sc_aux, sc_comp], [idx] * 3, group) if q_count else None
     fq = F.fri_query_sharded(fri, idx, layers, be, group) if q_count else None
     mark("openings")
     proof = None
-    if rank == 0:
+    if rank == 0 and hasattr(be, "serialize_proof"):
+        proof = be.serialize_proof(n, (sc_main.root, sc_aux.root, comp_root), ood, hz, layers, fri.roots, fri.last_value, m.bit_length() - 1, fq, opened,
+                                   nonce)
+    elif rank == 0:
         depth = m.bit_length() - 1
         if q_count:
             ev, evs, pa, pas = fq
-            crow = np.stack([np.asarray(r_).view(np.uint64).reshape(-1, 4) for r_ in comp_rows])
+            (main_rows, main_paths), (aux_rows, aux_paths), (crow, comp_paths) = opened
         bb = lambda a: felt.to_bytes_be_many(np.asarray(a).view(np.uint64).reshape(-1, 4))               # elements -> wire bytes
         u8 = lambda v: np.frombuffer(_u64be(v), dtype=np.uint8)
         const = lambda v: np.tile(u8(v), (q_count, 1))
@@ -434,9 +470,8 @@ def _prove_sharded(trace, options, be, group, timings, exchange, fri_collapse_lo
             out += np.concatenate([const(dec.shape[1]), dec], axis=1).tobytes()
         out += _u64be(q_count)
         if q_count:
-            as_u8 = lambda paths: np.frombuffer(b"".join(b"".join(bytes(x) for x in p_) for p_ in paths), dtype=np.uint8).reshape(q_count, -1)
-            rows52 = np.concatenate([np.stack([np.asarray(r_).view(np.uint64).reshape(-1, 4) for r_ in main_rows]),
-                                     np.stack([np.asarray(r_).view(np.uint64).reshape(-1, 4) for r_ in aux_rows])], axis=1)
+            as_u8 = lambda paths: np.ascontiguousarray(paths).reshape(q_count, -1)
+            rows52 = np.concatenate([main_rows, aux_rows], axis=1)
             opn = np.concatenate([const(depth), as_u8(comp_paths), const(32), bb(crow).reshape(q_count, -1), const(2),
                                   const(depth), as_u8(main_paths), const(depth), as_u8(aux_paths), const(ncols),
                                   bb(rows52).reshape(q_count, -1)], axis=1)

@@ -790,6 +790,84 @@ struct ByteSink {
 };
 }  // namespace
 
+// StarkProof::serialize (proof/stark.rs:161-218) from the pieces of a proof: ood = the frame (2 x cols, row-major), FRI values and
+// paths as s252_fri_query returns them ([Q][layers] values, [Q][layers][depth] digests), openings as s252_commit_open returns them.
+static void serialize_stark_proof(ByteSink& S, size_t N, const uint8_t* root_main, const uint8_t* root_aux, const uint8_t* root_comp,
+                                  const s252_fe* ood, size_t cols, const s252_fe hz[2], size_t layers, const uint8_t* fri_roots,
+                                  const s252_fe& last, size_t Q, size_t depth, const s252_fe* evs, const s252_fe* ev, const uint8_t* pas,
+                                  const uint8_t* pa, const s252_fe* comp_rows, const uint8_t* comp_paths, const s252_fe* main_rows,
+                                  size_t main_cols, const uint8_t* main_paths, const s252_fe* aux_rows, size_t aux_cols,
+                                  const uint8_t* aux_paths, uint64_t nonce) {
+    S.b.reserve(4096 + Q * (2 * layers * (depth + 2) + 3 * (depth + 1) + cols + 8) * 32);
+    S.u64(N);
+    S.u64(2);
+    S.raw(root_main, 32);
+    S.raw(root_aux, 32);
+    {
+        ByteSink F;
+        F.u64(2 * cols); F.u64(32);
+        for (size_t i = 0; i < 2 * cols; ++i) F.felt(ood[i]);
+        F.u64(cols);
+        S.blob(F);
+    }
+    S.raw(root_comp, 32);
+    S.u64(32); S.felt(hz[0]); S.felt(hz[1]);
+    S.u64(layers); S.raw(fri_roots, 32 * layers);
+    S.felt(last);
+    S.u64(Q);
+    for (size_t q = 0; q < Q; ++q) {
+        ByteSink D;
+        D.u64(layers);
+        for (size_t k = 0; k < layers; ++k) D.path(pas + (q * layers + k) * depth * 32, depth - k);
+        D.u64(32);
+        D.u64(layers);
+        for (size_t k = 0; k < layers; ++k) D.felt(evs[q * layers + k]);
+        D.u64(layers);
+        for (size_t k = 0; k < layers; ++k) D.felt(ev[q * layers + k]);
+        D.u64(layers);
+        for (size_t k = 0; k < layers; ++k) D.path(pa + (q * layers + k) * depth * 32, depth - k);
+        S.blob(D);
+    }
+    S.u64(Q);
+    for (size_t q = 0; q < Q; ++q) {
+        ByteSink O;
+        O.path(comp_paths + q * depth * 32, depth);
+        O.u64(32); O.felt(comp_rows[2 * q]); O.felt(comp_rows[2 * q + 1]);
+        O.u64(2);
+        O.path(main_paths + q * depth * 32, depth);
+        O.path(aux_paths + q * depth * 32, depth);
+        O.u64(cols);
+        for (size_t j = 0; j < main_cols; ++j) O.felt(main_rows[q * main_cols + j]);
+        for (size_t j = 0; j < aux_cols; ++j) O.felt(aux_rows[q * aux_cols + j]);
+        S.blob(O);
+    }
+    S.u64(nonce);
+}
+// The same for a caller that assembled the pieces itself (the sharded prover gathers them from several GPUs).
+extern "C" int s252_cairo_serialize_proof(size_t trace_rows, const uint8_t* root_main, const uint8_t* root_aux, const uint8_t* root_comp,
+                                          const s252_fe* ood, size_t cols, const s252_fe* hz, size_t layers, const uint8_t* fri_roots,
+                                          const s252_fe* last, size_t n_queries, size_t depth, const s252_fe* evs, const s252_fe* ev,
+                                          const uint8_t* pas, const uint8_t* pa, const s252_fe* comp_rows, const uint8_t* comp_paths,
+                                          const s252_fe* main_rows, size_t main_cols, const uint8_t* main_paths, const s252_fe* aux_rows,
+                                          size_t aux_cols, const uint8_t* aux_paths, uint64_t nonce, uint8_t** proof_out, size_t* proof_len) {
+    if (!root_main || !root_aux || !root_comp || !ood || !hz || !last || !proof_out || !proof_len || main_cols + aux_cols != cols ||
+        (layers && !fri_roots) || (n_queries && (!evs || !ev || !pas || !pa || !comp_rows || !comp_paths || !main_rows || !main_paths || !aux_rows || !aux_paths)))
+        CAIRO_FAIL(S252_ERR_INVALID, "s252_cairo_serialize_proof: bad arguments");
+    try {
+        ByteSink S;
+        serialize_stark_proof(S, trace_rows, root_main, root_aux, root_comp, ood, cols, hz, layers, fri_roots, *last, n_queries, depth, evs, ev,
+                              pas, pa, comp_rows, comp_paths, main_rows, main_cols, main_paths, aux_rows, aux_cols, aux_paths, nonce);
+        uint8_t* outp = (uint8_t*)std::malloc(S.b.size() ? S.b.size() : 1);
+        if (!outp) CAIRO_FAIL(S252_ERR_INVALID, "out of host memory");
+        std::memcpy(outp, S.b.data(), S.b.size());
+        *proof_out = outp;
+        *proof_len = S.b.size();
+    } catch (const std::exception& e) {
+        CAIRO_FAIL(S252_ERR_INVALID, std::string("s252_cairo_serialize_proof: ") + e.what());
+    }
+    return S252_OK;
+}
+
 extern "C" int s252_cairo_prove(s252_ctx* ctx, const s252_cairo_trace* trace, size_t blowup, size_t n_queries, uint64_t coset_offset,
                                 uint8_t grinding_factor, uint8_t** proof_out, size_t* proof_len) {
     NVTX_RANGE("s252_cairo_prove");
@@ -867,52 +945,14 @@ extern "C" int s252_cairo_prove(s252_ctx* ctx, const s252_cairo_trace* trace, si
         }
         ST.mark("openings");
         // ---- StarkProof::serialize
+        uint8_t r_main[32], r_aux[32], r_comp[32];
+        TRY(s252_commit_root(mainc, r_main));
+        TRY(s252_commit_root(auxc, r_aux));
+        TRY(s252_commit_root(comp, r_comp));
         ByteSink S;
-        S.b.reserve(4096 + Q * (2 * layers * (depth + 2) + 3 * (depth + 1) + cols + 8) * 32);
-        uint8_t r32[32];
-        S.u64(N);
-        S.u64(2);
-        TRY(s252_commit_root(mainc, r32)); S.raw(r32, 32);
-        TRY(s252_commit_root(auxc, r32)); S.raw(r32, 32);
-        {
-            ByteSink F;
-            F.u64(ood.size()); F.u64(32);
-            for (auto& v : ood) F.felt(v);
-            F.u64(cols);
-            S.blob(F);
-        }
-        TRY(s252_commit_root(comp, r32)); S.raw(r32, 32);
-        S.u64(32); S.felt(hz[0]); S.felt(hz[1]);
-        S.u64(layers); S.raw(fri_roots.data(), 32 * layers);
-        S.felt(last);
-        S.u64(Q);
-        for (size_t q = 0; q < Q; ++q) {
-            ByteSink D;
-            D.u64(layers);
-            for (size_t k = 0; k < layers; ++k) D.path(pas.data() + (q * layers + k) * depth * 32, depth - k);
-            D.u64(32);
-            D.u64(layers);
-            for (size_t k = 0; k < layers; ++k) D.felt(evs[q * layers + k]);
-            D.u64(layers);
-            for (size_t k = 0; k < layers; ++k) D.felt(ev[q * layers + k]);
-            D.u64(layers);
-            for (size_t k = 0; k < layers; ++k) D.path(pa.data() + (q * layers + k) * depth * 32, depth - k);
-            S.blob(D);
-        }
-        S.u64(Q);
-        for (size_t q = 0; q < Q; ++q) {
-            ByteSink O;
-            O.path(comp_paths.data() + q * depth * 32, depth);
-            O.u64(32); O.felt(comp_rows[2 * q]); O.felt(comp_rows[2 * q + 1]);
-            O.u64(2);
-            O.path(main_paths.data() + q * depth * 32, depth);
-            O.path(aux_paths.data() + q * depth * 32, depth);
-            O.u64(cols);
-            for (size_t j = 0; j < mainc->n_cols; ++j) O.felt(main_rows[q * mainc->n_cols + j]);
-            for (size_t j = 0; j < auxc->n_cols; ++j) O.felt(aux_rows[q * auxc->n_cols + j]);
-            S.blob(O);
-        }
-        S.u64(nonce);
+        serialize_stark_proof(S, N, r_main, r_aux, r_comp, ood.data(), cols, hz, layers, fri_roots.data(), last, Q, depth, evs.data(), ev.data(),
+                              pas.data(), pa.data(), comp_rows.data(), comp_paths.data(), main_rows.data(), mainc->n_cols, main_paths.data(),
+                              aux_rows.data(), auxc->n_cols, aux_paths.data(), nonce);
         uint8_t* outp = (uint8_t*)std::malloc(S.b.size());
         if (!outp) FAIL(ctx, S252_ERR_INVALID, "out of host memory");
         std::memcpy(outp, S.b.data(), S.b.size());

@@ -151,9 +151,20 @@ __device__ __forceinline__ fe mont_reduce(uint32_t T[16]) {
     return r;
 }
 
+// The product rows with no accumulator initialisation at all (generated and checked by tools/gen_fe_mul.py): every first
+// touch of a limb is a plain wide product or an immediate addend.  Saves ~20 register moves per multiplication.
+#ifndef S252_FE_MUL_GEN
+#define S252_FE_MUL_GEN 0
+#endif
+#include "fe_mul_rows.inc"
+
 // Montgomery product a*b/R mod p, lazily reduced.
 // Requires (a/p)*(b/p) <= 31 (e.g. a < 31p with a fully reduced twiddle b); returns a value < 2p.
 __device__ __forceinline__ fe fe_mul(const fe& a, const fe& b) {
+#if S252_FE_MUL_GEN
+    uint32_t E[17], O[16];
+    fe_mul_rows(E, O, a.l, b.l);
+#else
     // E collects 64-bit products that start on even limbs, O those that start on odd limbs
     // (O[k] has weight 2^(32(k+1))).  The constants preloaded into E are the "+p" and "+1" terms of
     // the two reduction steps (see below); they sit on limbs no product row uses as a carry sink
@@ -168,6 +179,7 @@ __device__ __forceinline__ fe fe_mul(const fe& a, const fe& b) {
         if (i < 6) mad_row4(&E[i + 2], &a.l[1], b.l[i + 1]);   // odd a * b_(i+1) -> limbs i+2, ..
         else       mad_row4_nc(&E[i + 2], &a.l[1], b.l[i + 1]); // top row: no carry out of 2^512
     }
+#endif
     // T = E + (O << 32): one 16-limb carry chain.
     uint32_t T[16];
     T[0] = E[0];

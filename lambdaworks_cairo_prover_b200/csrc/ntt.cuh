@@ -26,6 +26,12 @@
 
 namespace s252 {
 
+#ifndef S252_NTT_MIN_BLOCKS
+#define S252_NTT_MIN_BLOCKS 3          /* resident 64 KB blocks per SM the register budget is sized for */
+#endif
+#ifndef S252_NTT_NO_F2
+#define S252_NTT_NO_F2 0               /* 1: drop the second swizzle term of the tile (fewer address instructions, more bank conflicts) */
+#endif
 constexpr int NTT_THREADS = 256;
 constexpr int NTT_TILE_LOG = 11;                       // 2048 elements = 64 KB of shared memory
 constexpr int NTT_TILE = 1 << NTT_TILE_LOG;
@@ -69,7 +75,11 @@ struct Tile {
     unsigned swz_shift, swz_mask;      // top three index bits -> bank bits (bit-reversed load scatter)
     unsigned f2_shift, f2_mask, f2_lsh;   // item index bits of the first radix-4 step -> free bank bits
     __device__ __forceinline__ unsigned phys(unsigned e) const {
+#if S252_NTT_NO_F2
+        return e ^ ((e >> swz_shift) & swz_mask);
+#else
         return e ^ ((e >> swz_shift) & swz_mask) ^ (((e >> f2_shift) & f2_mask) << f2_lsh);
+#endif
     }
     __device__ __forceinline__ fe ld(unsigned e) const {
         const unsigned q = phys(e);
@@ -92,7 +102,7 @@ __device__ __forceinline__ Tile make_tile(unsigned char* smem, unsigned logE, un
     // differ in t (low logT bits) and in j (bits 2+logT and up), which would all land on the same
     // banks; fold the j bits that sit above bit 2 into the bank bits t leaves free.
     t.f2_shift = 0; t.f2_mask = 0; t.f2_lsh = 0;
-    if (logE >= 9) {
+    if (logE >= 9 && !S252_NTT_NO_F2) {
         if (logT == 0) { t.f2_shift = 3; t.f2_mask = 3; t.f2_lsh = 0; }
         else if (logT == 1) { t.f2_shift = 3; t.f2_mask = 3; t.f2_lsh = 1; }
         else if (logT == 2) { t.f2_shift = 4; t.f2_mask = 1; t.f2_lsh = 2; }
@@ -168,7 +178,7 @@ __device__ __forceinline__ void block_dit(const Tile& sm, const fe* __restrict__
 }
 
 // ---- kind A: strided pass -------------------------------------------------------------------
-__global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_strided(NttPass P) {
+__global__ void __launch_bounds__(NTT_THREADS, S252_NTT_MIN_BLOCKS) ntt_pass_strided(NttPass P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Tile sm = make_tile(smem_raw, P.logL + P.logT, P.logT);
     const unsigned L = 1u << P.logL, T = 1u << P.logT;
@@ -206,7 +216,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_strided(NttPass P) {
 }
 
 // ---- kind B: final pass ----------------------------------------------------------------------
-__global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_final(NttPass P) {
+__global__ void __launch_bounds__(NTT_THREADS, S252_NTT_MIN_BLOCKS) ntt_pass_final(NttPass P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Tile sm = make_tile(smem_raw, P.logL + P.logT, P.logT);
     const unsigned L = 1u << P.logL, T = 1u << P.logT;

@@ -277,6 +277,63 @@ def open_many(commits, indices, index_lists=None):
     return out
 
 
+def open_many_packed(commits, index_lists, group=None):
+    """The openings of several row-block commits gathered on rank 0 with ONE reduction and no per-element Python work:
+    every rank writes the rows and subtree paths of the positions it owns into a zero-filled byte buffer with a fixed
+    layout (an entry has exactly one owner), the buffers are summed onto rank 0, and rank 0 appends the replicated top
+    levels.  Returns, on rank 0, [(rows uint64[n, n_cols, 4], paths uint8[n, depth, 32]), ...] in the order of `commits`
+    (paths leaf -> root); None on the other ranks."""
+    first = commits[0]
+    be = first.backend
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    metas, total = [], 0
+    for sc, idxs in zip(commits, index_lists):
+        rows_per = sc.n_rows // world
+        dl = rows_per.bit_length() - 1
+        esz = 32 * (sc.n_cols + dl)
+        metas.append((total, len(idxs), esz, dl, rows_per))
+        total += len(idxs) * esz
+    host = np.zeros(total, dtype=np.uint8)
+    for sc, idxs, (off, n, esz, dl, rows_per) in zip(commits, index_lists, metas):
+        idx = np.asarray(idxs, dtype=np.int64)
+        mine = np.nonzero(idx // rows_per == rank)[0]
+        if mine.size == 0:
+            continue
+        rows, paths = be.open_block(sc.block, [int(i) for i in idx[mine] % rows_per])
+        view = host[off:off + n * esz].reshape(n, esz)
+        view[mine, :32 * sc.n_cols] = np.stack([np.ascontiguousarray(r).view(np.uint8).reshape(-1) for r in rows])
+        if dl:
+            view[mine, 32 * sc.n_cols:] = np.stack([np.frombuffer(b"".join(bytes(np.asarray(x).tobytes()) for x in p_), dtype=np.uint8)
+                                                    if not isinstance(p_, np.ndarray) else p_.reshape(-1) for p_ in paths])
+    if world > 1:
+        t = torch.from_numpy(host.view(np.int64)).to(be.device)
+        dist.reduce(t, dst=0 if group is None else dist.get_global_rank(group, 0), op=dist.ReduceOp.SUM, group=group)
+        if rank != 0:
+            return None
+        host = t.cpu().numpy().view(np.uint8)
+    dt = world.bit_length() - 1
+    out = []
+    for sc, idxs, (off, n, esz, dl, rows_per) in zip(commits, index_lists, metas):
+        view = host[off:off + n * esz].reshape(n, esz)
+        rows = np.ascontiguousarray(view[:, :32 * sc.n_cols]).view(np.uint64).reshape(n, sc.n_cols, 4)
+        paths = np.zeros((n, dl + dt, 32), dtype=np.uint8)
+        if dl:
+            paths[:, :dl] = view[:, 32 * sc.n_cols:].reshape(n, dl, 32)
+        if dt:
+            # the top of the tree is replicated: the siblings above rank g's subtree root (heap node world-1+g)
+            top = np.zeros((world, dt, 32), dtype=np.uint8)
+            for g in range(world):
+                node, lvl = (world - 1) + g, 0
+                while node != 0:
+                    sib = node + 1 if node & 1 else node - 1
+                    top[g, lvl] = np.frombuffer(sc.top[sib], dtype=np.uint8)
+                    node = (node - 1) >> 1
+                    lvl += 1
+            paths[:, dl:] = top[np.asarray(idxs, dtype=np.int64) // rows_per]
+        out.append((rows, paths))
+    return out
+
+
 def interpolate_and_commit_sharded(shard_table, n_rows, n_cols_total, blowup, coset_offset, transcript, backend, group=None,
                                    pipeline_groups=1, exchange="p2p"):
     """interpolate_and_commit (src/starks/prover.rs:126-159) for ONE trace whose columns are spread

@@ -169,14 +169,11 @@ def fri_query_sharded(fri, iotas, number_layers, be, group=None):
         for k in range(k0):
             size = fri.domain_size >> k
             index_lists.append([i % size for i in iotas] + [(i + size // 2) % size for i in iotas])
-        opened = D.open_many(fri.sharded_layers, None, index_lists=index_lists)
+        opened = D.open_many_packed(fri.sharded_layers, index_lists, group)
         if rank == 0:
             for k, (rows, paths) in enumerate(opened):
-                for a in range(q):
-                    ev[a, k] = np.asarray(rows[a]).view(np.uint64).reshape(-1)[:4]
-                    evs[a, k] = np.asarray(rows[q + a]).view(np.uint64).reshape(-1)[:4]
-                    pa[a, k, :depth - k] = np.frombuffer(b"".join(bytes(x) for x in paths[a]), dtype=np.uint8).reshape(-1, 32)
-                    pas[a, k, :depth - k] = np.frombuffer(b"".join(bytes(x) for x in paths[q + a]), dtype=np.uint8).reshape(-1, 32)
+                ev[:, k], evs[:, k] = rows[:q, 0], rows[q:, 0]
+                pa[:, k, :depth - k], pas[:, k, :depth - k] = paths[:q], paths[q:]
     if rank != 0:
         return None
     if number_layers > k0:

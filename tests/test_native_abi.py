@@ -77,3 +77,53 @@ def test_evaluate_offset_fft_len_rule():
     assert L.s252_evaluate_offset_fft_len(9, 4, 8) == 64
     assert L.s252_evaluate_offset_fft_len(0, 2, 4) == 8
     assert L.s252_evaluate_offset_fft_len(8, 1, 64) == 64
+
+
+@pytest.mark.parametrize("name", ["fibonacci_500", "fibonacci_70000"])
+def test_c_serializer_reproduces_the_reference_proof_files(name):
+    """s252_cairo_serialize_proof (host code; the sharded prover assembles its proof with it) must emit exactly
+    StarkProof::serialize (proof/stark.rs:161-218): the pieces parsed out of the reference's own proof files go back in
+    and the file's bytes must come out."""
+    from conftest import GOLDEN
+    from lambdaworks_cairo_prover_b200 import felt
+    from oracle.proof_format import read_proof_file
+    proof, raw, _ = read_proof_file(os.path.join(GOLDEN, "reference_proofs", name + ".proof"))
+    L = N.lib()
+    q, layers = len(proof.query_list), len(proof.fri_layers_merkle_roots)
+    depth = len(proof.deep_poly_openings[0].lde_composition_poly_proof)
+    cols = proof.trace_ood_frame_evaluations.row_width
+    main_cols = 34
+    f = lambda vals: felt.from_ints(list(vals))                                                   # noqa: E731
+    ood, hz, last = f(proof.trace_ood_frame_evaluations.data), f([proof.composition_poly_even_ood_evaluation,
+                                                                  proof.composition_poly_odd_ood_evaluation]), f([proof.fri_last_value])
+    ev = np.stack([f(d.layers_evaluations) for d in proof.query_list])
+    evs = np.stack([f(d.layers_evaluations_sym) for d in proof.query_list])
+
+    def paths(get, n_layers):
+        out = np.zeros((q, n_layers, depth, 32), dtype=np.uint8)
+        for a in range(q):
+            for k, p in enumerate(get(a)):
+                assert len(p) == depth - k if n_layers > 1 else len(p) == depth
+                out[a, k, :len(p)] = np.frombuffer(b"".join(p), dtype=np.uint8).reshape(-1, 32)
+        return out
+    pa = paths(lambda a: proof.query_list[a].layers_auth_paths, layers)
+    pas = paths(lambda a: proof.query_list[a].layers_auth_paths_sym, layers)
+    o = proof.deep_poly_openings
+    comp_rows = np.stack([f([x.lde_composition_poly_even_evaluation, x.lde_composition_poly_odd_evaluation]) for x in o])
+    comp_paths = paths(lambda a: [o[a].lde_composition_poly_proof], 1)[:, 0]
+    rows = np.stack([f(x.lde_trace_evaluations) for x in o])
+    main_rows, aux_rows = np.ascontiguousarray(rows[:, :main_cols]), np.ascontiguousarray(rows[:, main_cols:])
+    main_paths = paths(lambda a: [o[a].lde_trace_merkle_proofs[0]], 1)[:, 0]
+    aux_paths = paths(lambda a: [o[a].lde_trace_merkle_proofs[1]], 1)[:, 0]
+    roots = [np.frombuffer(r, dtype=np.uint8) for r in proof.lde_trace_merkle_roots + [proof.composition_poly_root]]
+    fr = np.frombuffer(b"".join(proof.fri_layers_merkle_roots), dtype=np.uint8)
+    out, ln = C.c_void_p(), C.c_size_t()
+    c = np.ascontiguousarray
+    rc = L.s252_cairo_serialize_proof(proof.trace_length, N.ptr(roots[0]), N.ptr(roots[1]), N.ptr(roots[2]), N.ptr(c(ood)), cols, N.ptr(c(hz)), layers,
+                                      N.ptr(fr), N.ptr(c(last)), q, depth, N.ptr(c(evs)), N.ptr(c(ev)), N.ptr(c(pas)), N.ptr(c(pa)), N.ptr(c(comp_rows)),
+                                      N.ptr(c(comp_paths)), N.ptr(main_rows), main_cols, N.ptr(c(main_paths)), N.ptr(aux_rows), cols - main_cols,
+                                      N.ptr(c(aux_paths)), proof.nonce, C.byref(out), C.byref(ln))
+    assert rc == 0, L.s252_cairo_last_error()
+    got = C.string_at(out.value, ln.value)
+    L.s252_cairo_proof_free(out)
+    assert got == raw
