@@ -381,7 +381,8 @@ static int commit_from_host_columns(s252_ctx* ctx, const s252_fe* cols_lw, size_
     if (!is_pow2(blowup) || blowup > MAX_COSETS) FAIL(ctx, S252_ERR_INVALID, "blowup factor %zu must be a power of two <= %u", blowup, MAX_COSETS);
     if (coset_offset == 0) FAIL(ctx, S252_ERR_INVALID, "coset offset must be non-zero");
     const size_t M = N * blowup;
-    const unsigned K = std::min<unsigned>(4, c);
+    const std::vector<unsigned> lo = upload_groups(c);              // short first and last groups: the only exposed upload / transforms
+    const unsigned K = (unsigned)lo.size() - 1;
     s252_commit* cm = new s252_commit();
     cm->ctx = ctx; cm->n_cols = c; cm->n_rows = M; cm->n_coeffs = N;
     std::vector<cudaEvent_t> ev(K, nullptr);
@@ -396,8 +397,6 @@ static int commit_from_host_columns(s252_ctx* ctx, const s252_fe* cols_lw, size_
         CU(ctx, cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
         CU(ctx, cudaEventRecord(start, ctx->stream));
         CU(ctx, cudaStreamWaitEvent(ctx->copy_stream, start, 0));
-        std::vector<unsigned> lo(K + 1);
-        for (unsigned g = 0; g <= K; ++g) lo[g] = (unsigned)((size_t)c * g / K);
         for (unsigned g = 0; g < K; ++g) {
             const size_t off = (size_t)lo[g] * N, cnt = (size_t)(lo[g + 1] - lo[g]) * N;
             CU(ctx, cudaMemcpyAsync(staged.p + off, cols_lw + off, cnt * sizeof(fe), cudaMemcpyHostToDevice, ctx->copy_stream));

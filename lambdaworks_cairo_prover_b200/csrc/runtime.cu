@@ -849,14 +849,20 @@ static int lde_from_cols(s252_ctx* ctx, const fe* cols, size_t N, unsigned c, si
     }
     return S252_OK;
 }
-// Column groups of the upload -> transform pipeline of a host-resident table: a short first group (its upload is
-// the only one nothing can hide), then growing ones.  Returns K+1 boundaries.
+// Column groups of the upload -> transform pipeline of a host-resident table.  PCIe (~50 GB/s of strided 2-D DMA for runs
+// of 128 bytes and more, tools/dma2d_bench.py) is about as fast as the transforms consume columns, so the pipeline is
+// upload-bound and what stays exposed is the upload of the FIRST group and the transforms of the LAST one: both are
+// short (weights 1,2,4,4,..,4,2,1).  Returns K+1 boundaries.
 static std::vector<unsigned> upload_groups(unsigned c) {
-    unsigned K = 6;
+    unsigned K = 7;
     if (const char* e = std::getenv("S252_HOST_GROUPS")) { const int v = std::atoi(e); if (v >= 1 && v <= 64) K = (unsigned)v; }
     K = std::min(K, c);
     std::vector<unsigned> cum(K + 1, 0);
-    for (unsigned g = 1; g <= K; ++g) cum[g] = cum[g - 1] + std::min(g, 4u);      // weights 1,2,3,4,4,4,..
+    for (unsigned g = 1; g <= K; ++g) {
+        const unsigned from_end = K - g;                  // 0 for the last group
+        const unsigned w = std::min(std::min(g, from_end + 1), 3u);      // 1,2,3,3,..,3,2,1
+        cum[g] = cum[g - 1] + (w == 3 ? 4 : w);
+    }
     std::vector<unsigned> lo(K + 1, 0);
     for (unsigned g = 1; g <= K; ++g) lo[g] = std::max(lo[g - 1] + 1, (unsigned)(((uint64_t)c * cum[g] + cum[K] / 2) / cum[K]));
     lo[K] = c;
