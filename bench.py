@@ -576,6 +576,12 @@ def run_gpu_sharded(args):
         dist.all_reduce(stage_t, op=dist.ReduceOp.MAX)
     golden = golden_case("c4" if log_n == C4_LOG_N else "c4_small" if log_n == 14 else "")
     parity_ok = None if golden is None else (root.hex() == golden["root"] and root_e2e == root)
+    c3_line = None
+    if args.c3_log_n:
+        try:
+            c3_line = c3_sharded_bench(ctx, args, world, rank, barrier, dist)
+        except Exception as e:
+            c3_line = {"error": "%s: %s" % (type(e).__name__, e)}
     cairo_line = None
     if not args.no_cairo:
         try:
@@ -623,6 +629,8 @@ def run_gpu_sharded(args):
                          "scope": "rank 0's launches"},
             "kernels_rank0": kernels,
         }
+        if c3_line is not None:
+            line["c3_one_column"] = c3_line
         if cairo_line is not None:
             line["cairo_prove"] = cairo_line
         print(json.dumps(line))
@@ -631,6 +639,46 @@ def run_gpu_sharded(args):
     dist.destroy_process_group()
     if parity_ok is False:
         raise SystemExit("bench.py: the sharded commit's root differs from the pinned oracle root")
+
+
+def c3_sharded_bench(ctx, args, world, rank, barrier, dist):
+    """BASELINE config C3 on N GPUs: interpolate_and_commit of ONE column (blowup 4) whose transform is shared by the GPUs
+    (four-step NTT with one all-to-all, column_distributed.py); root checked against the pinned oracle root."""
+    import torch
+
+    import lambdaworks_cairo_prover_b200 as P
+    from lambdaworks_cairo_prover_b200 import column_distributed as CD
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from util import random_felts
+    log_n, blowup = args.c3_log_n, 4
+    golden = golden_case("c3_%d" % log_n)
+    n = 1 << log_n
+    seed = golden["seed"] if golden else 0xB203 + log_n
+    col = torch.from_numpy(random_felts(seed, n).view(np.int64)).pin_memory()
+    be = CD.GpuColumnBackend(ctx)
+    times, root = [], None
+    for it in range(2 + 3):
+        barrier()
+        t0 = time.perf_counter()
+        sc = CD.interpolate_and_commit_column_sharded(col, log_n, blowup, OFFSET, P.DefaultTranscript(), be)
+        root = sc.root
+        ctx.synchronize()
+        barrier()
+        if it >= 2:
+            times.append((time.perf_counter() - t0) * 1e3)
+        sc.free()
+    ms = float(np.median(times))
+    tt = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms = float(tt.item())
+    CD._PLANS.clear()
+    ctx.trim()
+    torch.cuda.empty_cache()
+    return {"workload": "C3: ONE column of 2^%d rows, blowup %d: interpolate_and_commit with the transform shared by %d GPU(s) (four-step, one "
+                        "all-to-all per transform; slab upload inside the timed region)" % (log_n, blowup, world),
+            "ms": ms, "ms_all": [round(x, 2) for x in times], "elems_per_s": n * blowup / (ms * 1e-3), "root": root.hex(),
+            "parity_ok": None if golden is None else root.hex() == golden["root"]}
 
 
 def cairo_prove_sharded_bench(ctx, args, world, rank, barrier, dist):
@@ -810,6 +858,7 @@ def main():
                          "one independent trace per GPU (weak scaling)")
     ap.add_argument("--c4-log-n", type=int, default=C4_LOG_N, help="trace length exponent of the sharded C4 commit")
     ap.add_argument("--pipeline-groups", type=int, default=4, help="sharded mode: column groups per rank of the LDE -> exchange pipeline")
+    ap.add_argument("--c3-log-n", type=int, default=24, help="sharded mode: rows (log2) of the one-column C3 commit (0 = skip; 24 and 26 are pinned)")
     ap.add_argument("--fib-n-large", type=int, default=280000, help="sharded mode: the longer fibonacci program (0 = skip)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -78,6 +78,9 @@ int s252_copy_to_host(s252_ctx *ctx, void *dst, const void *src, size_t bytes);
  * about a millisecond per 10 MB: do it once for a buffer that is reused. */
 int s252_host_register(void *ptr, size_t bytes);
 int s252_host_unregister(void *ptr);
+/* Strided host -> device copy on the context's stream: `height` runs of `width` bytes, `src_pitch` / `dst_pitch` bytes apart
+ * (asynchronous with pinned host memory).  A GPU that shares one column's transform uploads only its slab with it. */
+int s252_copy_2d_to_device(s252_ctx *ctx, void *dst, size_t dst_pitch, const void *src, size_t src_pitch, size_t width, size_t height);
 /* Prefetch of the NEXT trace while the current one is being committed: the copy is queued on a
  * second stream and returns at once (pinned host memory gives a true asynchronous DMA);
  * s252_copy_stream_wait makes all later work on the compute stream wait for the prefetches issued

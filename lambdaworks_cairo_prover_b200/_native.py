@@ -33,6 +33,7 @@ SIGNATURES = {
     "s252_copy_to_host": (_i, [_vp, _vp, _vp, _sz]),
     "s252_host_register": (_i, [_vp, _sz]),
     "s252_host_unregister": (_i, [_vp]),
+    "s252_copy_2d_to_device": (_i, [_vp, _vp, _sz, _vp, _sz, _sz, _sz]),
     "s252_copy_to_device_async": (_i, [_vp, _vp, _vp, _sz]),
     "s252_copy_stream_wait": (_i, [_vp]),
     "s252_interpolate_fft": (_i, [_vp, _vp, _sz, _vp, _i]),

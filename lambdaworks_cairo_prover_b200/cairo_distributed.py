@@ -340,12 +340,14 @@ def _prove_sharded(trace, options, be, group, timings, exchange, fri_collapse_lo
     shards_main = D.column_shards(c_main, world)
     my_lo, my_hi = shards_main[rank]
     my_trace = kept["trace"]
-    for col in range(19, 30):
-        owner = next(r for r, (lo, hi) in enumerate(shards_main) if lo <= col < hi)
+    for owner, (lo, hi) in enumerate(shards_main):              # one broadcast per owner of a run of columns 19..29
+        a, z_ = max(lo, 19), min(hi, 30)
+        if a >= z_:
+            continue
         if owner == rank:
-            aux_in[col - 19].copy_(my_trace[col - my_lo])
+            aux_in[a - 19:z_ - 19].copy_(my_trace[a - my_lo:z_ - my_lo])
         if world > 1:
-            dist.broadcast(aux_in[col - 19], src=gr(owner), group=group)
+            dist.broadcast(aux_in[a - 19:z_ - 19], src=gr(owner), group=group)
     aux_cols = _all_ranks_ok(lambda: be.aux_trace(trace, aux_in, rap), be, group)
 
     def aux_lde(lo, hi):

@@ -80,8 +80,9 @@ class GpuColumnBackend(D.GpuBackend):
     def load_slab(self, host_column, buf, l1_rows, inner, lo, hi):
         """host column (LW, pinned tensor or array [N, 4]) -> buf[pos * inner + i] for i in [lo, hi), library-internal format."""
         h = host_column if torch.is_tensor(host_column) else torch.from_numpy(np.ascontiguousarray(host_column).view(np.int64))
-        view = buf.view(l1_rows, inner, 4)
-        view[:, lo:hi].copy_(h.view(l1_rows, inner, 4)[:, lo:hi], non_blocking=True)
+        self._keep = h                                     # the DMA reads it asynchronously
+        self.ctx.check(N.lib().s252_copy_2d_to_device(self.ctx.handle, C.c_void_p(buf.data_ptr() + 32 * lo), 32 * inner,
+                                                      C.c_void_p(h.data_ptr() + 32 * lo), 32 * inner, 32 * (hi - lo), l1_rows))
         self.ctx.check(N.lib().s252_convert_elements(self.ctx.handle, C.c_void_p(buf.data_ptr()), C.c_void_p(buf.data_ptr()), buf.shape[0], 1))
 
     def ntt_shared(self, log_n, inverse, n_cosets, coset_offset, phase, part, parts, src, z, out):

@@ -321,6 +321,14 @@ extern "C" int s252_host_unregister(void* ptr) {
     if (cudaHostUnregister(ptr) != cudaSuccess) { cudaGetLastError(); return S252_ERR_CUDA; }
     return S252_OK;
 }
+// Strided host -> device copy on the compute stream (a slab of a matrix: `height` runs of `width` bytes).
+extern "C" int s252_copy_2d_to_device(s252_ctx* ctx, void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width,
+                                      size_t height) {
+    if (!ctx || !dst || !src) return S252_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width, height, cudaMemcpyHostToDevice, ctx->stream));
+    return S252_OK;
+}
 // Prefetch: enqueue a host->device copy on the context's copy stream (returns immediately; use
 // pinned host memory for a true asynchronous DMA).  The destination must not be in use by work
 // already queued on the compute stream.
