@@ -245,12 +245,13 @@ int s252_fri_query(s252_fri *f, const uint64_t *iotas, size_t n_queries, s252_fe
 int s252_generate_nonce_with_grinding(s252_ctx *ctx, const uint8_t challenge[32], uint8_t grinding_factor,
                                       uint64_t limit, uint64_t *nonce);
 
-/* The same search shared by `parts` GPUs (one process per GPU): one round over the window [base, base + 2^32), of
- * which this GPU tests batches part, part + parts, .. of 2^18 nonces.  *found = this GPU's smallest accepted nonce or
- * UINT64_MAX.  The caller takes the MIN over the GPUs (an all-reduce) -- that is the reference's nonce -- and calls
- * again with base + 2^32 if no GPU found one. */
+/* The same search shared by `parts` GPUs (one process per GPU): one round over the window [base, base + 2^window_log)
+ * (18 <= window_log <= 40), of which this GPU tests batches part, part + parts, .. of 2^18 nonces.  *found = this GPU's
+ * smallest accepted nonce or UINT64_MAX.  The caller takes the MIN over the GPUs (an all-reduce) -- that is the reference's
+ * nonce -- and calls again with the next window if no GPU found one.  Use window_log ~ grinding_factor + 1: a GPU does not
+ * see the other GPUs' hits while its kernel runs. */
 int s252_grind_round(s252_ctx *ctx, const uint8_t challenge[32], uint8_t grinding_factor, uint64_t base, uint64_t limit,
-                     unsigned part, unsigned parts, uint64_t *found);
+                     unsigned part, unsigned parts, unsigned window_log, uint64_t *found);
 
 /* ByteConversion::to_bytes_be for n elements on the host (the proof's wire format): out = n x 32 bytes. */
 void s252_fe_to_bytes_be(const s252_fe *in, size_t n, uint8_t *out);

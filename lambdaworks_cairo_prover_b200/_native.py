@@ -77,7 +77,7 @@ SIGNATURES = {
     "s252_fri_read_nodes": (_i, [_vp, _sz, _sz, _sz, _vp]),
     "s252_fri_query": (_i, [_vp, _vp, _sz, _vp, _vp, _vp, _vp, _sz]),
     "s252_generate_nonce_with_grinding": (_i, [_vp, _vp, _u8, _u64, C.POINTER(_u64)]),
-    "s252_grind_round": (_i, [_vp, _vp, _u8, _u64, _u64, C.c_uint, C.c_uint, C.POINTER(_u64)]),
+    "s252_grind_round": (_i, [_vp, _vp, _u8, _u64, _u64, C.c_uint, C.c_uint, C.c_uint, C.POINTER(_u64)]),
     "s252_fe_to_bytes_be": (None, [_vp, _sz, _vp]),
     "s252_keccak256": (None, [_vp, _sz, _vp]),
     "s252_transcript_new": (_vp, []),

@@ -184,10 +184,10 @@ class GpuCairoBackend(D.GpuBackend):
     def release_fri(self, fri):
         self.L.s252_fri_destroy(fri)
 
-    def grind_round(self, challenge, factor, base, part, parts):
+    def grind_round(self, challenge, factor, base, part, parts, window_log):
         found = C.c_uint64()
         ch = np.frombuffer(challenge, dtype=np.uint8).copy()
-        self.ctx.check(self.L.s252_grind_round(self.ctx.handle, N.ptr(ch), factor, base, 0, part, parts, C.byref(found)))
+        self.ctx.check(self.L.s252_grind_round(self.ctx.handle, N.ptr(ch), factor, base, 0, part, parts, window_log, C.byref(found)))
         return int(found.value)
 
     @staticmethod

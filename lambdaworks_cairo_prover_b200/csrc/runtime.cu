@@ -1863,16 +1863,18 @@ extern "C" int s252_fri_query(s252_fri* f, const uint64_t* iotas, size_t n_queri
 static const unsigned GRIND_GRID = 1024;                       // x 256 threads = 2^18 nonces per batch
 static const unsigned GRIND_BATCHES = 1u << 14;                // per round, over all parts
 static int grind_round(s252_ctx* ctx, const uint8_t challenge[32], uint8_t grinding_factor, uint64_t base, uint64_t limit,
-                       unsigned part, unsigned parts, uint64_t* found) {
+                       unsigned part, unsigned parts, uint64_t* found, unsigned window_log = 32) {
     uint64_t lanes[4];
     std::memcpy(lanes, challenge, 32);   // little-endian host
     Tmp<unsigned long long> best(ctx);
     TRY(dalloc(ctx, &best.p, 1));
     CU(ctx, cudaMemsetAsync(best.p, 0xff, 8, ctx->stream));
-    const uint64_t window_end = base + (1ull << 32) > base ? std::min<uint64_t>(limit, base + (1ull << 32)) : limit;
+    const uint64_t window = 1ull << window_log;
+    const uint64_t window_end = base + window > base ? std::min<uint64_t>(limit, base + window) : limit;
+    const unsigned batches = (unsigned)std::max<uint64_t>(1, window >> 18);          // 2^18 nonces per batch
     prof_begin(ctx, "grind_kernel");
     s252::grind_kernel<<<GRIND_GRID, 256, 0, ctx->stream>>>(lanes[0], lanes[1], lanes[2], lanes[3], base, window_end,
-                                                            (GRIND_BATCHES + parts - 1) / parts, part, parts, grinding_factor, best.p);
+                                                            (batches + parts - 1) / parts, part, parts, grinding_factor, best.p);
     LAUNCH_CHECK(ctx);
     unsigned long long f;
     CU(ctx, cudaMemcpyAsync(&f, best.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1900,17 +1902,19 @@ extern "C" int s252_generate_nonce_with_grinding(s252_ctx* ctx, const uint8_t ch
     FAIL(ctx, S252_ERR_NOT_FOUND, "nonce not found below %llu", (unsigned long long)limit);
 }
 // The same search shared by `parts` GPUs (disjoint nonce ranges + a `min` all-reduce): one round over the
-// window [base, base + 2^32) of which this GPU tests its round-robin share of the 2^18-nonce batches.  *found is this
-// GPU's smallest accepted nonce or UINT64_MAX; the caller takes the minimum over the GPUs and, if none found
-// anything, calls again with base + 2^32.  The minimum over the parts is the reference's nonce (grinding.rs:44-47).
+// window [base, base + 2^window_log) of which this GPU tests its round-robin share of the 2^18-nonce batches.  *found is
+// this GPU's smallest accepted nonce or UINT64_MAX; the caller takes the minimum over the GPUs and, if none found
+// anything, calls again with the next window.  A GPU does not see the others' hits while its kernel runs, so the window
+// should be about twice the expected position of the first hit (2^(factor+1)): large windows make every GPU search until
+// its OWN first hit.  The minimum over the parts is the reference's nonce (grinding.rs:44-47).
 extern "C" int s252_grind_round(s252_ctx* ctx, const uint8_t challenge[32], uint8_t grinding_factor, uint64_t base, uint64_t limit,
-                                unsigned part, unsigned parts, uint64_t* found) {
+                                unsigned part, unsigned parts, unsigned window_log, uint64_t* found) {
     NVTX_RANGE("s252_grind_round");
-    if (!ctx || !challenge || !found || parts == 0 || part >= parts) return S252_ERR_INVALID;
+    if (!ctx || !challenge || !found || parts == 0 || part >= parts || window_log < 18 || window_log > 40) return S252_ERR_INVALID;
     CU(ctx, cudaSetDevice(ctx->device));
     if (grinding_factor > 64) FAIL(ctx, S252_ERR_NOT_FOUND, "a 64-bit head cannot have %u trailing zeros", grinding_factor);
     if (limit == 0) limit = ~0ull;
-    return grind_round(ctx, challenge, grinding_factor, base, limit, part, parts, found);
+    return grind_round(ctx, challenge, grinding_factor, base, limit, part, parts, found, window_log);
 }
 
 // --------------------------------------------------------------------------------------------

@@ -9,7 +9,7 @@ Row-block distribution, one process per GPU: rank r holds rows [r*size/G, (r+1)*
            formula, verifier.rs:511-512; same values as fold_polynomial + a fresh FFT, fri/mod.rs:43-54).  The
            partner of row i lives G/2 ranks away: every rank sends the two halves of its block to the two ranks
            that fold them -- one pairwise exchange of half a layer per fold (ncclSend/ncclRecv over NVLink).
-  collapse once a layer is small (its folds are latency, not throughput) it is all-gathered and rank 0 finishes the
+  collapse once a layer is small (<= 2^19 evaluations: its folds are latency, not throughput) it is all-gathered and rank 0 finishes the
            phase with the single-GPU path (device-side transcript chain + tail kernel); the other ranks replay the
            transcript from the roots rank 0 broadcasts.
   queries  the owner of a row serves its value and the subtree part of its path; the top levels are replicated.
@@ -104,7 +104,9 @@ def fri_commit_phase_sharded(p0_block, domain_size, number_layers, t, coset_offs
     transcript ends in the same state (last value appended)."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     if collapse_log is None:
-        collapse_log = 17
+        # a layer of 2^19 evaluations costs one GPU ~0.2 ms (fold + leaves + tree); sharding it saves less than the
+        # gather of the subtree roots and the fold exchange cost in latency
+        collapse_log = 19
     sharded = []
     roots = []
     block = p0_block
@@ -187,14 +189,17 @@ def generate_nonce_with_grinding_sharded(challenge, grinding_factor, be, group=N
     """generate_nonce_with_grinding (src/starks/grinding.rs:40-48) with the search split over the ranks; every rank
     returns the same nonce: the global minimum."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
+    # a rank does not see the others' hits while its kernel runs: windows of about twice the expected position of the
+    # first hit keep every rank from searching until its OWN first hit (at least one 2^18-nonce batch per rank)
+    window_log = min(32, max(18 + (world - 1).bit_length(), grinding_factor + 1))
     base = 0
     while base < U64_MAX:
-        found = be.grind_round(challenge, grinding_factor, base, rank, world)
+        found = be.grind_round(challenge, grinding_factor, base, rank, world, window_log)
         best = torch.tensor([found if found < (1 << 63) else (1 << 63) - 1], dtype=torch.int64, device=be.device)
         if world > 1:
             dist.all_reduce(best, op=dist.ReduceOp.MIN, group=group)
         best = int(best.item())
         if best != (1 << 63) - 1:
             return best
-        base += 1 << 32
+        base += 1 << window_log
     raise RuntimeError("nonce not found")

@@ -173,9 +173,9 @@ class OracleCairoBackend:
     def release_fri(self, fri):
         pass
 
-    def grind_round(self, challenge, factor, base, part, parts):
+    def grind_round(self, challenge, factor, base, part, parts, window_log):
         batch = 1 << 18
-        for b in range(part, 1 << 14, parts):
+        for b in range(part, 1 << (window_log - 18), parts):
             for nonce in range(base + b * batch, base + (b + 1) * batch):
                 if O.grinding_zeros(challenge, nonce) >= factor:
                     return nonce

@@ -378,13 +378,17 @@ def test_grinding_split_over_parts_gives_the_minimum(ctx):
     for factor in (3, 14, 20):
         ch = rng.integers(0, 256, size=32, dtype=np.uint8)
         want = O.generate_nonce_with_grinding(ch.tobytes(), factor)
-        for parts in (1, 2, 8):
-            found = []
-            for part in range(parts):
-                f = C.c_uint64()
-                ctx.check(L.s252_grind_round(ctx.handle, N.ptr(ch), factor, 0, 0, part, parts, C.byref(f)))
-                found.append(int(f.value))
-            assert min(found) == want, (factor, parts, found)
+        for parts, window_log in ((1, 32), (2, 32), (8, 32), (8, 21), (4, 20)):
+            base, best = 0, (1 << 64) - 1
+            while best == (1 << 64) - 1:                      # windows until some part finds a nonce, as the orchestration does
+                found = []
+                for part in range(parts):
+                    f = C.c_uint64()
+                    ctx.check(L.s252_grind_round(ctx.handle, N.ptr(ch), factor, base, 0, part, parts, window_log, C.byref(f)))
+                    found.append(int(f.value))
+                best = min(found)
+                base += 1 << window_log
+            assert best == want, (factor, parts, window_log, found)
 
 
 def test_fri_rejects_oversized_polynomial(ctx):
