@@ -672,12 +672,15 @@ def c3_sharded_bench(ctx, args, world, rank, barrier, dist):
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     ms = float(tt.item())
+    stages = {}
+    CD.interpolate_and_commit_column_sharded(col, log_n, blowup, OFFSET, P.DefaultTranscript(), be, timings=stages).free()
     CD._PLANS.clear()
     ctx.trim()
     torch.cuda.empty_cache()
     return {"workload": "C3: ONE column of 2^%d rows, blowup %d: interpolate_and_commit with the transform shared by %d GPU(s) (four-step, one "
                         "all-to-all per transform; slab upload inside the timed region)" % (log_n, blowup, world),
             "ms": ms, "ms_all": [round(x, 2) for x in times], "elems_per_s": n * blowup / (ms * 1e-3), "root": root.hex(),
+            "stages_ms_rank0": {k: round(v, 3) for k, v in stages.items()},
             "parity_ok": None if golden is None else root.hex() == golden["root"]}
 
 

@@ -140,7 +140,9 @@ int s252_interpolate_and_lde(s252_ctx *ctx, const s252_fe *trace, size_t n_rows,
 int s252_commit_device_columns(s252_ctx *ctx, const void *cols, size_t col_stride, size_t n_cols, size_t n_rows,
                                s252_commit **out, uint8_t root[32]);
 /* The same without the copy: the tree is built over the caller's columns (col_stride must equal n_rows),
- * which must stay alive and unchanged while the handle is in use. */
+ * which must stay alive and unchanged while the handle is in use.  root may be NULL: the call then returns without
+ * waiting for the device and the root stays at s252_commit_device_nodes(handle) (a sharded commit gathers the subtree
+ * roots of all GPUs device to device). */
 int s252_commit_device_columns_inplace(s252_ctx *ctx, const void *cols, size_t col_stride, size_t n_cols, size_t n_rows,
                                        s252_commit **out, uint8_t root[32]);
 /* Round 2 (src/starks/prover.rs:254-276): evaluate_polynomial_on_lde_domain for each of n_polys

@@ -66,6 +66,54 @@ def _redistribute(src_buf, dst_buf, plan, group):
     dst_buf.index_copy_(0, recv_idx, recv)
 
 
+def _a2a_blocks(send, group):
+    """send: [G, ...] (slot d goes to rank d) -> recv: [G, ...] (slot s came from rank s); equal splits."""
+    if dist.get_world_size(group) == 1:
+        return send
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv.view(-1), send.contiguous().view(-1), group=group)
+    return recv
+
+
+# The four redistributions as strided views: the ownership patterns are blocks of a 4- or 5-dimensional view of the
+# flat buffer, so packing and unpacking are two tensor copies at HBM speed and the all-to-all has equal splits.  (The
+# index-plan routine above stays as the general fallback and as the specification the tests were first written for.)
+def _transpose_z(z, cosets, rows1, inner, world, rank, group):
+    """[c][k1][i]: "all k1, my i range" -> "my k1 range, all i"."""
+    if world == 1:
+        return
+    wr, wi = rows1 // world, inner // world
+    v = z.view(cosets, world, wr, world, wi, 4)                       # [c, k1 block, k1, i block, i, limb]
+    recv = _a2a_blocks(v[:, :, :, rank].permute(1, 0, 2, 3, 4).contiguous(), group)       # [d][c, wr, wi, 4]
+    v[:, rank] = recv.permute(1, 2, 0, 3, 4)                                              # [c, wr, s, wi, 4]
+
+
+def _runs_to_slabs(coeffs, col, rows1, inner, world, rank, group):
+    """natural index k = k1 + rows1*q.  Own: k1 in my range.  Need: (k mod inner) in my range of width inner/world.
+    With inner = rows1 * R and world | R this is q_lo in my range of width R/world (q = q_lo + R*q_hi)."""
+    if world == 1:
+        col.copy_(coeffs)
+        return
+    r_ = inner // rows1
+    wr = rows1 // world
+    src = coeffs.view(-1, world, r_ // world, world, wr, 4)            # [q_hi, q_lo block, q_lo, k1 block, k1, limb]
+    dst = col.view(-1, world, r_ // world, world, wr, 4)
+    recv = _a2a_blocks(src[:, :, :, rank].permute(1, 0, 2, 3, 4).contiguous(), group)     # [d][q_hi, R/G, wr, 4]
+    dst[:, rank] = recv.permute(1, 2, 0, 3, 4)                                            # [q_hi, R/G, s, wr, 4]
+
+
+def _runs_to_blocks(lde, block_mine, rows1, blowup, world, rank, group):
+    """LDE index j = (k1 + rows1*q)*blowup + c.  Own: k1 in my range.  Need: the contiguous block j in [rank*m/G, ..), i.e.
+    q in my range of width Q/world.  block_mine: [m/world, 4] receives this rank's rows."""
+    if world == 1:
+        block_mine.copy_(lde)
+        return
+    wr = rows1 // world
+    src = lde.view(world, -1, world, wr, blowup, 4)                    # [q block, q, k1 block, k1, c, limb]
+    recv = _a2a_blocks(src[:, :, rank].contiguous(), group)            # [d][Q/G, wr, b, 4]
+    block_mine.view(-1, world, wr, blowup, 4).copy_(recv.permute(1, 0, 2, 3, 4))          # [Q/G, s, wr, b, 4]
+
+
 class GpuColumnBackend(D.GpuBackend):
     """The transform phases on this rank's GPU (s252_ntt_shared) + what distributed.py / fri_distributed.py need."""
 
@@ -114,7 +162,8 @@ class ShardedColumn:
         self.coeff_runs = None
 
 
-def interpolate_and_commit_column_sharded(host_column, log_n, blowup, coset_offset, transcript, be, group=None):
+def interpolate_and_commit_column_sharded(host_column, log_n, blowup, coset_offset, transcript, be, group=None, timings=None,
+                                          force_index_plans=False):
     """interpolate_and_commit (prover.rs:126-159) of a one-column trace of 2^log_n rows (host_column: LW elements, the same
     array on every rank -- each rank reads only its slab).  Appends the root to the transcript; returns a ShardedColumn."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
@@ -135,28 +184,63 @@ def interpolate_and_commit_column_sharded(host_column, log_n, blowup, coset_offs
         own_lde_runs = lambda idx: ((idx // blowup) % rows1) // w_rows          # noqa: E731  LDE index j = k*blowup + c
         own_block = lambda idx: idx // (m // world)                             # noqa: E731  contiguous row blocks
         dev = be.device
+        import time
+        clock = [time.perf_counter()]
+
+        def mark(name):
+            if timings is not None:
+                if hasattr(be, "sync"):
+                    be.sync()
+                now = time.perf_counter()
+                timings[name] = timings.get(name, 0.0) + (now - clock[0]) * 1e3
+                clock[0] = now
+        structured = not force_index_plans and (inner // rows1) % world == 0 and inner >= rows1
         # ---- compute_trace_polys: interpolate_fft (trace.rs:104-110)
         col = be.new_tensor((n, 4))
         be.load_slab(host_column, col, rows1, inner, rank * w_inner, (rank + 1) * w_inner)
         z = be.new_tensor((n, 4))
         coeffs = be.new_tensor((n, 4))
+        mark("upload")
         be.ntt_shared(log_n, True, 1, 0, 0, rank, world, col, z, coeffs)
-        _redistribute(z, z, _plan(("transpose", n, rows1, 1), n, world, rank, dev, own_slab, own_rows), group)
+        mark("transform")
+        if structured:
+            _transpose_z(z, 1, rows1, inner, world, rank, group)
+        else:
+            _redistribute(z, z, _plan(("transpose", n, rows1, 1), n, world, rank, dev, own_slab, own_rows), group)
+        mark("exchange")
         be.ntt_shared(log_n, True, 1, 0, 1, rank, world, col, z, coeffs)
+        mark("transform")
         # ---- compute_lde_trace_evaluations: evaluate_offset_fft(blowup, Some(N), h) (prover.rs:106-123)
         # coefficients: runs -> the slabs the forward transform's first pass reads
-        _redistribute(coeffs, col, _plan(("runs2slab", n, rows1), n, world, rank, dev, own_runs, own_slab), group)
+        if structured:
+            _runs_to_slabs(coeffs, col, rows1, inner, world, rank, group)
+        else:
+            _redistribute(coeffs, col, _plan(("runs2slab", n, rows1), n, world, rank, dev, own_runs, own_slab), group)
+        mark("exchange")
         zc = be.new_tensor((m, 4))
         lde = be.new_tensor((m, 4))
         be.ntt_shared(log_n, False, blowup, coset_offset, 0, rank, world, col, zc, lde)
-        _redistribute(zc, zc, _plan(("transpose", n, rows1, blowup), m, world, rank, dev, own_slab, own_rows), group)
+        mark("transform")
+        if structured:
+            _transpose_z(zc, blowup, rows1, inner, world, rank, group)
+        else:
+            _redistribute(zc, zc, _plan(("transpose", n, rows1, blowup), m, world, rank, dev, own_slab, own_rows), group)
+        mark("exchange")
         be.ntt_shared(log_n, False, blowup, coset_offset, 1, rank, world, col, zc, lde)
+        mark("transform")
         del zc, z, col
         # ---- batch_commit (prover.rs:96-104): LDE runs -> contiguous row blocks, row-block tree
-        block = be.new_tensor((m, 4))
-        _redistribute(lde, block, _plan(("runs2block", n, rows1, blowup), m, world, rank, dev, own_lde_runs, own_block), group)
         rows_per = m // world
-        mine = block[rank * rows_per:(rank + 1) * rows_per].clone()
-        del block, lde
+        mine = be.new_tensor((rows_per, 4))
+        if structured:
+            _runs_to_blocks(lde, mine, rows1, blowup, world, rank, group)
+        else:
+            block = be.new_tensor((m, 4))
+            _redistribute(lde, block, _plan(("runs2block", n, rows1, blowup), m, world, rank, dev, own_lde_runs, own_block), group)
+            mine.copy_(block[rank * rows_per:(rank + 1) * rows_per])
+            del block
+        del lde
+        mark("exchange")
         sc = F.commit_row_block(mine.view(1, rows_per, 4), m, transcript, be, group)
+        mark("hash")
         return ShardedColumn(sc, coeffs, l1, log_n, world)

@@ -991,7 +991,15 @@ static int interpolate_lde_impl(s252_ctx* ctx, const s252_fe* trace, size_t n_ro
         TRY(dalloc(ctx, &cols.p, N * c));
         prof_begin(ctx, "rows_lw_to_cols");
         prof_work(ctx, 64.0 * N * c, 0, 0);
-        s252::rows_lw_to_cols<<<dim3((unsigned)((N + 31) / 32), (c + 31) / 32), 256, 0, ctx->stream>>>(dtrace, N, c, cols.p, N);
+        if (c >= 16) {
+            s252::rows_lw_to_cols<<<dim3((unsigned)((N + 31) / 32), (c + 31) / 32), 256, 0, ctx->stream>>>(dtrace, N, c, cols.p, N);
+        } else {
+            // a narrow table (one rank's columns of a sharded trace) leaves most of a 32 x 32 tile empty: one thread per
+            // element instead -- coalesced reads along the rows, 32-byte sector writes down the columns
+            int sms = 148;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+            s252::rows_lw_to_cols_stream<<<(unsigned)sms * 8, 256, 0, ctx->stream>>>(dtrace, N, c, c, cols.p, N);
+        }
         LAUNCH_CHECK(ctx);
         TRY(lde_from_cols(ctx, cols.p, N, c, blowup, coset_offset, with_tree, cm, root));
         if (keep_trace) { cm->trace = cols.p; cols.p = nullptr; }
@@ -1043,7 +1051,7 @@ extern "C" int s252_commit_device_columns(s252_ctx* ctx, const void* cols, size_
 extern "C" int s252_commit_device_columns_inplace(s252_ctx* ctx, const void* cols, size_t col_stride, size_t n_cols, size_t n_rows,
                                                   s252_commit** out, uint8_t root[32]) {
     NVTX_RANGE("s252_commit_device_columns_inplace");
-    if (!ctx || !cols || !out || !root) return S252_ERR_INVALID;
+    if (!ctx || !cols || !out) return S252_ERR_INVALID;          // root == NULL: leave the root on the device (no read-back, no wait)
     *out = nullptr;
     CU(ctx, cudaSetDevice(ctx->device));
     if (!is_pow2(n_rows) || n_cols == 0 || col_stride != n_rows)
@@ -1055,7 +1063,7 @@ extern "C" int s252_commit_device_columns_inplace(s252_ctx* ctx, const void* col
     int rc = [&]() -> int {
         TRY(dalloc(ctx, &cm->nodes, 4 * (2 * n_rows - 1)));
         TRY(build_tree(ctx, cm->lde, n_rows, (unsigned)n_cols, n_rows, cm->nodes));
-        TRY(fetch_root(ctx, cm->nodes, root));
+        if (root) TRY(fetch_root(ctx, cm->nodes, root));
         return S252_OK;
     }();
     if (rc != S252_OK) { commit_free(cm); return rc; }

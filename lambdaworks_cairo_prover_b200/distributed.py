@@ -156,6 +156,17 @@ class GpuBackend:
         commit._keepalive = cols
         return commit, root.tobytes()
 
+    def commit_block_nosync(self, cols):
+        """commit_block without the read-back: -> (DeviceCommit, int64[4] device tensor viewing the subtree root)."""
+        c_total, rows = cols.shape[0], cols.shape[1]
+        h = C.c_void_p()
+        self.ctx.check(N.lib().s252_commit_device_columns_inplace(self.ctx.handle, C.c_void_p(cols.data_ptr()), rows, c_total, rows,
+                                                                  C.byref(h), None))
+        commit = DeviceCommit(self.ctx, h, b"")
+        commit._keepalive = cols
+        root = torch.as_tensor(_DevicePointer(N.lib().s252_commit_device_nodes(h), 4), device=self.device)
+        return commit, root
+
     def before_collective(self):
         pass                            # stream-ordered: see scope()
 
@@ -380,6 +391,31 @@ def backend_scope(backend):
     return backend.scope() if hasattr(backend, "scope") else contextlib.nullcontext()
 
 
+def gather_subtree_roots(backend, block_cols, group):
+    """Hash this rank's row block, build its subtree and all-gather the G subtree roots: -> (block handle, 32*G bytes).  On GPUs
+    the roots go device to device and the host waits once, for the gathered digests."""
+    world = dist.get_world_size(group)
+    if hasattr(backend, "commit_block_nosync"):
+        block, mine = backend.commit_block_nosync(block_cols)
+        gathered = torch.empty(4 * world, dtype=torch.int64, device=mine.device)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, mine, group=group)
+        else:
+            gathered.copy_(mine)
+        roots = gathered.cpu().numpy().tobytes()
+        rank = dist.get_rank(group)
+        block.root = roots[32 * rank:32 * rank + 32]
+        return block, roots
+    block, sub_root = backend.commit_block(block_cols)
+    mine = torch.frombuffer(bytearray(sub_root), dtype=torch.uint8).to(backend.device)
+    gathered = torch.empty(32 * world, dtype=torch.uint8, device=backend.device)
+    if world > 1:
+        dist.all_gather_into_tensor(gathered, mine, group=group)
+    else:
+        gathered.copy_(mine)
+    return block, bytes(gathered.cpu().numpy().tobytes())
+
+
 def exchange_and_commit(producer, ranges, shards, m, n_cols_total, transcript, backend, group=None, exchange="p2p", timings=None):
     """The exchange + per-rank subtree + top of the tree for LDE columns produced group by group:
     `producer` yields (handle, lde[c_group, M, 4]) for this rank's pipeline groups in order; ranges[r][g] is
@@ -438,13 +474,8 @@ def exchange_and_commit(producer, ranges, shards, m, n_cols_total, transcript, b
         w.wait()
     backend.after_collective()
     mark("exchange")
-    block, sub_root = backend.commit_block(recv)
+    block, roots = gather_subtree_roots(backend, recv, group)
     mark("hash")
-    mine = torch.frombuffer(bytearray(sub_root), dtype=torch.uint8).to(recv.device)
-    gathered = torch.empty(32 * world, dtype=torch.uint8, device=recv.device)
-    dist.all_gather_into_tensor(gathered, mine, group=group)
-    backend.after_collective()
-    roots = bytes(gathered.cpu().numpy().tobytes())
     top = build_top([roots[32 * g:32 * g + 32] for g in range(world)], backend.keccak)
     transcript.append(top[0])
     mark("roots")

@@ -83,14 +83,7 @@ def commit_row_block(block_cols, n_rows_total, t, be, group, shards=None):
     """batch_commit (prover.rs:96-104) of a table whose rows are spread over the ranks in equal contiguous blocks:
     block_cols [c, rows, 4] = all columns of this rank's rows.  Appends the root to the transcript."""
     world = dist.get_world_size(group)
-    block, sub_root = be.commit_block(block_cols)
-    mine = torch.frombuffer(bytearray(sub_root), dtype=torch.uint8).to(be.device)
-    gathered = torch.empty(32 * world, dtype=torch.uint8, device=be.device)
-    if world > 1:
-        dist.all_gather_into_tensor(gathered, mine, group=group)
-    else:
-        gathered.copy_(mine)
-    roots = bytes(gathered.cpu().numpy().tobytes())
+    block, roots = D.gather_subtree_roots(be, block_cols, group)
     top = D.build_top([roots[32 * g:32 * g + 32] for g in range(world)], be.keccak)
     t.append(top[0])
     sc = D.ShardedCommit(be, group, None, block, top, n_rows_total, block_cols.shape[0], shards)
