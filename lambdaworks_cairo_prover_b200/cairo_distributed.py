@@ -263,13 +263,18 @@ def _bcast_bytes(data, n, device, group):
     return bytes(t.cpu().numpy().tobytes())
 
 
-def generate_cairo_proof_sharded(trace, options, ctx, group=None, timings=None, exchange="a2a", fri_collapse_log=None):
+def generate_cairo_proof_sharded(trace, options, ctx, group=None, timings=None, exchange="a2a", fri_collapse_log=None,
+                                 pipeline_groups=None):
     """trace: the same MainTrace on every rank (lambdaworks_cairo_prover_b200.cairo); ctx: this rank's Context (or a
     backend object with GpuCairoBackend's interface).  Returns StarkProof::serialize() bytes on rank 0 and
-    None on the other ranks.  A failure on any rank (an unsatisfied AIR, say) raises on EVERY rank."""
+    None on the other ranks.  A failure on any rank (an unsatisfied AIR, say) raises on EVERY rank.
+    pipeline_groups: column groups per rank of the round-1 commits (default: 2 from 2^20 rows on, else 1).  With more than
+    one group the exchange of a group (point-to-point chunks) runs under the upload + LDE of the next one."""
     be = ctx if hasattr(ctx, "main_lde") else GpuCairoBackend(ctx)
+    if pipeline_groups is None:
+        pipeline_groups = 2 if trace.n_rows() >= (1 << 20) else 1
     with D.backend_scope(be):
-        return _prove_sharded(trace, options, be, group, timings, exchange, fri_collapse_log)
+        return _prove_sharded(trace, options, be, group, timings, exchange, fri_collapse_log, pipeline_groups)
 
 
 def _all_ranks_ok(step, be, group):
@@ -290,7 +295,7 @@ def _all_ranks_ok(step, be, group):
     return out
 
 
-def _prove_sharded(trace, options, be, group, timings, exchange, fri_collapse_log):
+def _prove_sharded(trace, options, be, group, timings, exchange, fri_collapse_log, pipeline_groups):
     import time
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     device = be.device
@@ -318,18 +323,19 @@ def _prove_sharded(trace, options, be, group, timings, exchange, fri_collapse_lo
         shards = D.column_shards(n_cols_total, world)
         if min(hi - lo for lo, hi in shards) == 0:
             raise ValueError("fewer columns than ranks")
-        ranges = [D.group_ranges(hi - lo, 1) for lo, hi in shards]
+        ng = max(1, min(pipeline_groups if world > 1 else 1, min(hi - lo for lo, hi in shards)))
+        ranges = [D.group_ranges(hi - lo, ng) for lo, hi in shards]
         lo, hi = shards[rank]
         sub = None if timings is None else timings.setdefault("commit_detail", {})
-        return D.exchange_and_commit((lde_of_my_columns(lo, hi) for _ in range(1)), ranges, shards, m, n_cols_total, t, be, group,
-                                     exchange=exchange, timings=sub)
+        return D.exchange_and_commit((lde_of_my_columns(lo + a, lo + b) for a, b in ranges[rank]), ranges, shards, m, n_cols_total, t, be, group,
+                                     exchange=exchange if ng == 1 else "p2p", timings=sub)
 
     # ---- round 1 (prover.rs:186-224)
     kept = {}
 
     def main_lde(lo, hi):
         handle, lde, tr = be.main_lde(trace, lo, hi, options)
-        kept["trace"] = tr
+        kept.setdefault("trace", []).append((lo, hi, tr))
         return handle, lde
     sc_main = sharded_commit(c_main, main_lde)
     mark("main_commit")
@@ -338,14 +344,15 @@ def _prove_sharded(trace, options, be, group, timings, exchange, fri_collapse_lo
     # device (uploading them from the host on every rank would multiply the PCIe traffic by the number of ranks)
     aux_in = be.new_tensor((11, n, 4))
     shards_main = D.column_shards(c_main, world)
-    my_lo, my_hi = shards_main[rank]
-    my_trace = kept["trace"]
     for owner, (lo, hi) in enumerate(shards_main):              # one broadcast per owner of a run of columns 19..29
         a, z_ = max(lo, 19), min(hi, 30)
         if a >= z_:
             continue
         if owner == rank:
-            aux_in[a - 19:z_ - 19].copy_(my_trace[a - my_lo:z_ - my_lo])
+            for tlo, thi, tr in kept["trace"]:                  # this rank's columns, one tensor per pipeline group
+                x, y = max(a, tlo), min(z_, thi)
+                if x < y:
+                    aux_in[x - 19:y - 19].copy_(tr[x - tlo:y - tlo])
         if world > 1:
             dist.broadcast(aux_in[a - 19:z_ - 19], src=gr(owner), group=group)
     aux_cols = _all_ranks_ok(lambda: be.aux_trace(trace, aux_in, rap), be, group)

@@ -27,9 +27,10 @@ def main_gloo(fib_n, opts):
     table = np.array(trace.table).reshape(trace.n_rows(), trace.n_cols, 4)
     # fri_collapse_log 2: FRI layers stay sharded (row-block trees, pairwise fold exchange) down to 8 evaluations;
     # None: the default threshold, far above these sizes, so the whole commit phase runs on rank 0 after one gather
-    for exchange, collapse in (("a2a", 2), ("p2p", None), ("p2p", 4)):
+    # the last case pipelines the round-1 commits in two column groups per rank (what traces of 2^20 rows and more do)
+    for exchange, collapse, groups in (("a2a", 2, 1), ("p2p", None, 1), ("p2p", 4, 2)):
         proof = generate_cairo_proof_sharded(trace, opts, OracleCairoBackend(table, trace.pub_inputs), exchange=exchange,
-                                             fri_collapse_log=collapse)
+                                             fri_collapse_log=collapse, pipeline_groups=groups)
         if rank == 0:
             want = cairo_prove(table, trace.pub_inputs, opts, threads=1).serialize()
             assert proof == want, "sharded proof differs from the oracle's (%d vs %d bytes)" % (len(proof), len(want))
@@ -54,8 +55,8 @@ def main():
     regs, mem, size = cairo.run_program(cairo.fibonacci_program(fib_n))
     trace = cairo.build_main_trace(regs, mem, size)
     want = cairo.generate_cairo_proof(trace, opts, ctx) if rank == 0 else None
-    for collapse in (None, 5, 9):
-        proof = generate_cairo_proof_sharded(trace, opts, ctx, fri_collapse_log=collapse)
+    for collapse, groups in ((None, None), (5, 2), (9, 1)):
+        proof = generate_cairo_proof_sharded(trace, opts, ctx, fri_collapse_log=collapse, pipeline_groups=groups)
         if rank == 0:
             assert proof == want, "sharded proof differs from the single-GPU proof (%d vs %d bytes)" % (len(proof), len(want))
         else:
