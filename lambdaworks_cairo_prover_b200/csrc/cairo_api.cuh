@@ -381,7 +381,7 @@ static int commit_from_host_columns(s252_ctx* ctx, const s252_fe* cols_lw, size_
     if (!is_pow2(blowup) || blowup > MAX_COSETS) FAIL(ctx, S252_ERR_INVALID, "blowup factor %zu must be a power of two <= %u", blowup, MAX_COSETS);
     if (coset_offset == 0) FAIL(ctx, S252_ERR_INVALID, "coset offset must be non-zero");
     const size_t M = N * blowup;
-    const std::vector<unsigned> lo = upload_groups(c);              // short first and last groups: the only exposed upload / transforms
+    const std::vector<unsigned> lo = upload_groups(c, true);        // short first and last groups: the only exposed upload / transforms
     const unsigned K = (unsigned)lo.size() - 1;
     s252_commit* cm = new s252_commit();
     cm->ctx = ctx; cm->n_cols = c; cm->n_rows = M; cm->n_coeffs = N;

@@ -857,19 +857,23 @@ static int lde_from_cols(s252_ctx* ctx, const fe* cols, size_t N, unsigned c, si
     }
     return S252_OK;
 }
-// Column groups of the upload -> transform pipeline of a host-resident table.  PCIe (~50 GB/s of strided 2-D DMA for runs
-// of 128 bytes and more, tools/dma2d_bench.py) is about as fast as the transforms consume columns, so the pipeline is
-// upload-bound and what stays exposed is the upload of the FIRST group and the transforms of the LAST one: both are
-// short (weights 1,2,4,4,..,4,2,1).  Returns K+1 boundaries.
-static std::vector<unsigned> upload_groups(unsigned c) {
-    unsigned K = 7;
+// Column groups of the upload -> transform pipeline of a host-resident table.  PCIe is about as fast as the transforms
+// consume columns, so the pipeline is upload-bound and what stays exposed is the upload of the FIRST group and the
+// transforms of the LAST one.  Column-major tables (contiguous DMA at any width) get short groups at both ends
+// (weights 1,2,4,..,4,2,1: main commit of the Cairo prover 21.0 -> 19.0 ms).  Row-major tables travel as strided 2-D DMA,
+// which is slow for narrow runs (tools/dma2d_bench.py: 19 / 38 / 47 / 50 GB/s for runs of 32 / 64 / 128 / >= 256 bytes),
+// so only the first group is short there (weights 1,2,3,4,4,4: measured best, 40.7 ms per C2 step against 41.6 with
+// short groups at both ends).  Returns K+1 boundaries.
+static std::vector<unsigned> upload_groups(unsigned c, bool column_major) {
+    unsigned K = column_major ? 7 : 6;
     if (const char* e = std::getenv("S252_HOST_GROUPS")) { const int v = std::atoi(e); if (v >= 1 && v <= 64) K = (unsigned)v; }
     K = std::min(K, c);
     std::vector<unsigned> cum(K + 1, 0);
     for (unsigned g = 1; g <= K; ++g) {
-        const unsigned from_end = K - g;                  // 0 for the last group
-        const unsigned w = std::min(std::min(g, from_end + 1), 3u);      // 1,2,3,3,..,3,2,1
-        cum[g] = cum[g - 1] + (w == 3 ? 4 : w);
+        unsigned w;
+        if (column_major) { const unsigned m = std::min(std::min(g, K - g + 1), 3u); w = m == 3 ? 4 : m; }     // 1,2,4,..,4,2,1
+        else w = std::min(g, 4u);                                                                              // 1,2,3,4,4,..
+        cum[g] = cum[g - 1] + w;
     }
     std::vector<unsigned> lo(K + 1, 0);
     for (unsigned g = 1; g <= K; ++g) lo[g] = std::max(lo[g - 1] + 1, (unsigned)(((uint64_t)c * cum[g] + cum[K] / 2) / cum[K]));
@@ -903,7 +907,7 @@ static int lde_from_pinned_rows(s252_ctx* ctx, const s252_fe* trace, int mode, c
                                 size_t blowup, uint64_t coset_offset, bool with_tree, bool keep_trace, s252_commit* cm,
                                 uint8_t root[32]) {
     const size_t M = N * blowup;
-    const std::vector<unsigned> lo = upload_groups(c);
+    const std::vector<unsigned> lo = upload_groups(c, false);
     const unsigned K = (unsigned)lo.size() - 1;
     std::vector<cudaEvent_t> ev(K, nullptr);
     cudaEvent_t start = nullptr;
