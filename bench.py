@@ -105,6 +105,34 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+PEAK_NOTE = ("IMAD.WIDE.U32 (32x32->64) products with data-dependent multiplicands: 32 lanes/clk/SM on B200, i.e. one warp "
+             "instruction per 4 cycles per SM sub-partition.  Round 1 quoted 18.3 T: that probe multiplied loop-invariant registers, "
+             "ptxas hoisted the products out of the loop and the loop timed IADD3 pairs (DESIGN.md 3.1)")
+
+
+def integer_peaks(ctx):
+    """The roofline denominators MEASURED_PEAKS.json does not carry: measured live on this GPU (about 0.2 s, outside every timed
+    region) with s252_microbench_int_pipes; profiles/int_peaks.json (an earlier run of tools/microbench.py on this pool) is the
+    fallback."""
+    import ctypes as C
+    from lambdaworks_cairo_prover_b200 import _native as N
+    peaks, src = {}, "profiles/int_peaks.json (tools/microbench.py on this pool's B200)"
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "profiles", "int_peaks.json")))
+    except Exception:
+        pass
+    try:
+        arr = (C.c_double * 8)()
+        ctx.check(N.lib().s252_microbench_int_pipes(ctx.handle, arr))
+        if arr[0] > 0 and arr[1] > 0:
+            peaks = dict(peaks, imad_wide_gops=arr[0], lop3_gops=arr[1], shf_gops=arr[2], imad_wide_plus_lop3_gops=arr[4],
+                         imad_wide_carry_rows_gops=arr[5], imad_lo_gops=arr[6])
+            src = "measured live in this run (s252_microbench_int_pipes, before the timed region)"
+    except Exception:
+        pass
+    return float(peaks.get("imad_wide_gops", 9250.0)), float(peaks.get("lop3_gops", 18500.0)), src
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -291,13 +319,7 @@ def run_gpu(args):
         except Exception:
             pass
         total_kernel_ms = sum(v["ms"] for v in prof.values())
-        int_peaks = {}
-        try:
-            int_peaks = json.load(open(os.path.join(ROOT, "profiles", "int_peaks.json")))
-        except Exception:
-            pass
-        imad_peak = float(int_peaks.get("imad_wide_gops", 18300.0))
-        lop_peak = float(int_peaks.get("lop3_gops", 18450.0))
+        imad_peak, lop_peak, int_peak_src = integer_peaks(ctx)
         kernels = {}
         for name, st in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
             sec = st["ms"] * 1e-3
@@ -332,8 +354,8 @@ def run_gpu(args):
             "roofline": {"bound": "int_issue", "kernel": tname, "achieved": tstat["muls"] * 80 / (tstat["ms"] * 1e-3) / 1e9 if tstat["ms"] else 0.0,
                          "peak": imad_peak, "unit": "G lane-op/s (IMAD.WIDE.U32)",
                          "frac": kernels[tname]["imad_frac"], "traffic": traffic,
-                         "peak_source": "isolated IMAD.WIDE.U32 issue rate measured on this pool's B200 (profiles/int_peaks.json; = 64 lanes/clk/SM); "
-                                        "not in MEASURED_PEAKS.json, which holds HBM and bf16 peaks only",
+                         "peak_source": int_peak_src + "; not in MEASURED_PEAKS.json, which holds HBM and bf16 peaks only",
+                         "peak_note": PEAK_NOTE,
                          "work": "80 wide multiply-adds per field multiplication (SURVEY 8d) x the multiplications of the launch (DESIGN.md section 4)",
                          "hbm": {"achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "peak_source": peak_src}},
             "int_roofline": {"bound": "integer issue (IMAD.WIDE for field kernels, LOP3/SHF for Keccak kernels)",
@@ -341,7 +363,7 @@ def run_gpu(args):
                              "step_frac_how": "sum over kernels of (share of step time) x max(imad_frac, alu_frac); peaks are the "
                                               "isolated-instruction rates below",
                              "imad_wide_peak_gops": imad_peak, "lop3_peak_gops": lop_peak,
-                             "peak_source": "tools/microbench.py on this pool's B200 (profiles/int_peaks.json)",
+                             "peak_source": int_peak_src,
                              "kernels": kernels},
             "result": {"last_root": out_dev[0].hex(), "nonce": out_dev[2]},
         }
@@ -590,13 +612,7 @@ def run_gpu_sharded(args):
             cairo_line = {"error": "%s: %s" % (type(e).__name__, e)}
     if rank == 0:
         elems = cfg["elems_per_step"]
-        int_peaks = {}
-        try:
-            int_peaks = json.load(open(os.path.join(ROOT, "profiles", "int_peaks.json")))
-        except Exception:
-            pass
-        imad_peak = float(int_peaks.get("imad_wide_gops", 18300.0))
-        lop_peak = float(int_peaks.get("lop3_gops", 18450.0))
+        imad_peak, lop_peak, int_peak_src = integer_peaks(ctx)
         total_kernel_ms = sum(v["ms"] for v in prof.values()) or 1.0
         kernels = {}
         for name, st in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
@@ -625,7 +641,7 @@ def run_gpu_sharded(args):
             "pipeline_groups": groups, "gpu_launches": launches, "clocks": clocks,
             "roofline": {"bound": "int_issue", "kernel": tname, "achieved": tstat["muls"] * 80 / (tstat["ms"] * 1e-3) / 1e9 if tstat["ms"] else 0.0,
                          "peak": imad_peak, "unit": "G lane-op/s (IMAD.WIDE.U32)", "frac": kernels[tname]["imad_frac"], "traffic": None,
-                         "peak_source": "isolated IMAD.WIDE.U32 issue rate measured on this pool's B200 (profiles/int_peaks.json)",
+                         "peak_source": int_peak_src, "peak_note": PEAK_NOTE,
                          "scope": "rank 0's launches"},
             "kernels_rank0": kernels,
         }

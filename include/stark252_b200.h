@@ -272,9 +272,11 @@ uint64_t s252_transcript_to_usize(s252_transcript *t);
 /* ---- diagnostics ----------------------------------------------------------------------------- */
 /* Integer-pipe peak micro-benchmarks on this device (the roofline denominators that are not in
  * MEASURED_PEAKS.json): results in Gops/s of 32-bit lane-operations.
- * out[0] = IMAD.WIDE.U32 (independent mad.wide chains), out[1] = LOP3, out[2] = SHF (funnel shift),
- * out[3] = IADD3 with carry, out[4] = IMAD.WIDE and LOP3 interleaved 1:1 (sum of both). */
-int s252_microbench_int_pipes(s252_ctx *ctx, double out[5]);
+ * out[0] = IMAD.WIDE.U32 (pure 32x32->64 products, data-dependent multiplicands), out[1] = LOP3, out[2] = SHF (funnel shift),
+ * out[3] = IADD3 with carry, out[4] = IMAD.WIDE and LOP3 interleaved 1:1 (sum of both), out[5] = wide multiply-adds in the
+ * field multiply's carry rows (IMAD.WIDE.U32.X), out[6] = IMAD (32-bit mad.lo), out[7] = IMAD.WIDE.U32 with both
+ * multiplicands in registers of equal parity. */
+int s252_microbench_int_pipes(s252_ctx *ctx, double out[8]);
 /* Montgomery multiplications per second (Gmul/s) of fe_mul in a register-resident loop. */
 int s252_microbench_fe_mul(s252_ctx *ctx, double *gmuls);
 /* Keccak-f[1600] permutations per second (Gperm/s), register-resident. */

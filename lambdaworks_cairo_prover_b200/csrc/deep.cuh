@@ -84,8 +84,9 @@ struct DeepParams {
     unsigned K;                                  // frame rows (transition offsets)
     const fe* gammas;                            // device: [trace_cols][K] trace-term coefficients, then gamma, gamma'
     // 1/(x_i - z g^k) = g^(-k) * U[i - blowup*k]  with  U[i] = 1/(x_i - z):  x_(i - blowup*k) = x_i / g^k
-    const fe* U;                                 // [m]  1/(x_i - z)
-    const fe* V;                                 // [m]  1/(x_i - z^2)
+    const fe* U;                                 // 1/(x_i - z) for i = u_base, u_base + 1, .. (mod m): the whole coset, or a block + its halo
+    const fe* V;                                 // 1/(x_i - z^2) for i = v_base, ..
+    unsigned long long u_base, v_base;           // global row of U[0] / V[0] (0 when the tables cover the whole coset)
     unsigned long long rot[DEEP_MAX_K];          // (blowup * offset_k) mod m
     fe ginv[DEEP_MAX_K];                         // g^(-offset_k)
     fe ck[DEEP_MAX_K];                           // sum_j gamma_jk * t_j(z g^k)
@@ -135,10 +136,10 @@ __global__ void __launch_bounds__(DEEP_THREADS) deep_composition_kernel(DeepPara
     const unsigned ct = P.ntables - 1;
     const fe h1 = ld_fe(P.cols[ct] + row), h2 = ld_fe(P.cols[ct] + P.strides[ct] + row);
     const fe sz = fe_reduce(fe_add_lazy(fe_mul(h1, ldg_fe(g)), fe_mul(h2, ldg_fe(g + 1))));
-    fe acc = fe_mul_full(fe_sub_full(sz, P.cz2), ld_fe(P.V + gi));
+    fe acc = fe_mul_full(fe_sub_full(sz, P.cz2), ld_fe(P.V + (gi - P.v_base)));
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        const fe inv = fe_mul(P.ginv[k], ld_fe(P.U + ((gi + P.m - P.rot[k]) & (P.m - 1))));         // < 2p
+        const fe inv = fe_mul(P.ginv[k], ld_fe(P.U + ((gi + 2 * P.m - P.rot[k] - P.u_base) & (P.m - 1))));   // < 2p
         acc = fe_reduce(fe_add_lazy(acc, fe_mul(fe_sub_lazy<1>(fe_reduce(s[k]), P.ck[k]), inv)));    // (2)(2)
     }
     st_fe(P.out + row, acc);

@@ -1560,13 +1560,30 @@ static int deep_evaluate_rows(s252_ctx* ctx, const DeepTables& T, size_t row0, s
     TRY(dalloc(ctx, &dg.p, gammas.size()));
     CU(ctx, cudaMemcpyAsync(dg.p, gammas.data(), gammas.size() * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
     P.gammas = dg.p;
-    // inverse tables over the LDE coset x_i = h w^i (whole coset: the frame offsets index it by rotation)
+    // inverse tables over the LDE coset x_i = h w^i; the frame offsets index U by rotation.  A block of rows (one rank of a
+    // sharded proof) needs U only on its rows plus the halo the largest rotation reaches back to, and V only on its rows:
+    // the scans then run over the block instead of the whole coset.
     const fe* dom;
     TRY(get_power_table(ctx, M, wM, h, &dom));
-    TRY(dalloc(ctx, &dU.p, M));
-    TRY(dalloc(ctx, &dV.p, M));
-    TRY(invert_shifted(ctx, dom, M, zz, dU.p));
-    TRY(invert_shifted(ctx, dom, M, H::sqr(zz), dV.p));
+    unsigned long long maxrot = 0;
+    for (unsigned k = 0; k < K; ++k) maxrot = std::max<unsigned long long>(maxrot, P.rot[k]);
+    const bool block = rows < M && rows + maxrot < M;
+    const size_t u_len = block ? rows + (size_t)maxrot : M, v_len = block ? rows : M;
+    P.u_base = block ? (row0 + M - maxrot) % M : 0;
+    P.v_base = block ? row0 : 0;
+    Tmp<fe> dom_ext(ctx);
+    const fe* dom_u = dom + P.u_base;
+    if (block && P.u_base + u_len > M) {                        // the halo wraps around the end of the coset (rank 0)
+        TRY(dalloc(ctx, &dom_ext.p, u_len));
+        const size_t first = M - P.u_base;
+        CU(ctx, cudaMemcpyAsync(dom_ext.p, dom + P.u_base, first * sizeof(fe), cudaMemcpyDeviceToDevice, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(dom_ext.p + first, dom, (u_len - first) * sizeof(fe), cudaMemcpyDeviceToDevice, ctx->stream));
+        dom_u = dom_ext.p;
+    }
+    TRY(dalloc(ctx, &dU.p, u_len));
+    TRY(dalloc(ctx, &dV.p, v_len));
+    TRY(invert_shifted(ctx, dom_u, u_len, zz, dU.p));
+    TRY(invert_shifted(ctx, dom + P.v_base, v_len, H::sqr(zz), dV.p));
     P.U = dU.p; P.V = dV.p;
     P.out = out;
     P.row0 = row0; P.rows = rows;
@@ -2004,7 +2021,7 @@ static int time_kernel(s252_ctx* ctx, F launch, int reps, float* ms_best) {
     *ms_best = best;
     return S252_OK;
 }
-extern "C" int s252_microbench_int_pipes(s252_ctx* ctx, double out[5]) {
+extern "C" int s252_microbench_int_pipes(s252_ctx* ctx, double out[8]) {
     if (!ctx || !out) return S252_ERR_INVALID;
     CU(ctx, cudaSetDevice(ctx->device));
     int sms = 0;
@@ -2012,7 +2029,7 @@ extern "C" int s252_microbench_int_pipes(s252_ctx* ctx, double out[5]) {
     Tmp<uint32_t> sink(ctx);
     const int blocks = sms * 8, threads = 256, iters = 2048;
     TRY(dalloc(ctx, &sink.p, (size_t)blocks * threads));
-    for (int which = 0; which < 5; ++which) {
+    for (int which = 0; which < 8; ++which) {
         float ms;
         TRY(time_kernel(ctx, [&]() { s252::int_pipe_bench<<<blocks, threads, 0, ctx->stream>>>(which, iters, sink.p); }, 5, &ms));
         const double ops = (double)blocks * threads * iters * s252::INT_BENCH_OPS_PER_ITER;

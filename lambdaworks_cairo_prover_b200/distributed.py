@@ -407,8 +407,8 @@ def gather_subtree_roots(backend, block_cols, group):
         block.root = roots[32 * rank:32 * rank + 32]
         return block, roots
     block, sub_root = backend.commit_block(block_cols)
-    mine = torch.frombuffer(bytearray(sub_root), dtype=torch.uint8).to(backend.device)
-    gathered = torch.empty(32 * world, dtype=torch.uint8, device=backend.device)
+    mine = torch.frombuffer(bytearray(sub_root), dtype=torch.uint8).to(block_cols.device)
+    gathered = torch.empty(32 * world, dtype=torch.uint8, device=block_cols.device)
     if world > 1:
         dist.all_gather_into_tensor(gathered, mine, group=group)
     else:

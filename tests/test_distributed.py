@@ -73,7 +73,7 @@ def test_sharded_commit_nccl():
 
 
 @pytest.mark.parametrize("world,args", [(2, ("3", "4", "3", "3", "1")), (4, ("10", "2", "4", "5", "3")), (1, ("3", "4", "2", "3", "1")),
-                                        (2, ("20", "8", "5", "7", "2"))])
+                                        (2, ("20", "8", "5", "7", "2")), (8, ("20", "4", "3", "3", "2"))])
 def test_sharded_cairo_proof_gloo(world, args):
     """The orchestration of the sharded Cairo prover (column shards, exchange, halos, gathers, row-block trees of the trace tables,
     of (H1, H2) and of the FRI layers, the pairwise fold exchange, the collapse to one rank, grinding split over the ranks, transcript
@@ -104,7 +104,7 @@ def test_sharded_cairo_proof_nccl():
         assert "DIST_CAIRO_OK" in res.stdout
 
 
-@pytest.mark.parametrize("world,args", [(2, ("6", "4", "3")), (4, ("7", "2", "3")), (2, ("5", "8", "2"))])
+@pytest.mark.parametrize("world,args", [(2, ("6", "4", "2")), (4, ("7", "2", "3")), (2, ("5", "8", "2")), (4, ("8", "2", "2")), (8, ("9", "4", "3"))])
 def test_sharded_single_column_gloo(world, args):
     """ONE column over several ranks -- four-step geometry, the transposes and redistributions, the row-block tree and
     the openings on CPU ranks (the transform phases restated in python integers) == the oracle's interpolate_and_commit."""

@@ -68,6 +68,33 @@ def test_round3_and_round4_on_device(ctx, logn, c_main, c_aux, blowup, offsets):
     p0 = O.deep_composition_poly(polys, h1p, h2p, z, offsets, ood, hz[0], hz[1], gamma, gamma_p, gammas.reshape(c, len(offsets), 4))
     want_last, want_roots, want_evals, _ = O.fri_commit_phase(logn, p0, t_ref, O.fe_from_u64(h), m)
     assert (layers[0].evaluation == want_evals[0]).all()          # p0 on the LDE coset, no NTT on the GPU side
+    # the same polynomial block by block (what one rank of a sharded proof computes: s252_deep_rows builds its inverse tables
+    # on the block + the halo the frame rotations reach back to; block 0's halo wraps around the end of the coset)
+    import ctypes as C
+    import torch
+    from lambdaworks_cairo_prover_b200 import _native as N
+    L = N.lib()
+    offs = np.array(offsets, dtype=np.uint64)
+    tabs = commits + [comp]
+    for parts in (2, 8):
+        rows = m // parts
+        if rows == 0:
+            continue
+        for part in sorted({0, 1, parts // 2, parts - 1}):
+            row0 = part * rows
+            out = torch.empty((rows, 4), dtype=torch.int64, device="cuda:0")
+            tables = (C.c_void_p * len(tabs))(*[L.s252_commit_device_lde(t.handle) + 32 * row0 for t in tabs])
+            strides = (C.c_size_t * len(tabs))(*[m] * len(tabs))
+            ncs = (C.c_size_t * len(tabs))(*[t.n_cols for t in tabs])
+            ctx.check(L.s252_deep_rows(ctx.handle, tables, strides, ncs, len(tabs), row0, rows, m, n, N.ptr(z), N.ptr(offs), len(offsets),
+                                       N.ptr(np.ascontiguousarray(ood.reshape(-1, 4))), N.ptr(np.ascontiguousarray(hz[0])),
+                                       N.ptr(np.ascontiguousarray(hz[1])), N.ptr(gamma), N.ptr(gamma_p),
+                                       N.ptr(np.ascontiguousarray(gammas.reshape(-1, 4))), h, C.c_void_p(out.data_ptr())))
+            ctx.synchronize()
+            # device buffers hold the library's internal layout: 8 x u32 least-significant first = the 4 u64 limbs of the
+            # reference's layout in reverse order
+            got = out.cpu().numpy().view(np.uint64)[:, ::-1]
+            assert (got == want_evals[0][row0:row0 + rows]).all(), (parts, part)
     assert [layer.root for layer in layers] == [r.tobytes() for r in want_roots]
     assert (last == want_last).all()
     assert t_gpu.challenge() == t_ref.challenge()
