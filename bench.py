@@ -384,6 +384,10 @@ def run_gpu(args):
                                      capture_output=True, text=True, timeout=900)
                 c4 = json.loads(res.stdout.strip().splitlines()[-1])
                 line["c4_one_gpu"] = {k: c4[k] for k in ("value", "unit", "ms_per_step", "scaling", "parity_ok", "e2e", "stages_ms", "config", "result")}
+                # the N = 1 points of the other two one-object-on-N-GPUs measurements of the N > 1 line
+                for src, dst in (("c3_one_column", "c3_one_gpu"), ("c5_fri", "c5_one_gpu")):
+                    if src in c4:
+                        line[dst] = c4[src]
             except Exception as e:
                 line["c4_one_gpu"] = {"error": "%s: %s" % (type(e).__name__, e)}
         print(json.dumps(line))
@@ -604,6 +608,12 @@ def run_gpu_sharded(args):
             c3_line = c3_sharded_bench(ctx, args, world, rank, barrier, dist)
         except Exception as e:
             c3_line = {"error": "%s: %s" % (type(e).__name__, e)}
+    c5_line = None
+    if args.c5_log_n:
+        try:
+            c5_line = c5_sharded_bench(ctx, args, world, rank, barrier, dist)
+        except Exception as e:
+            c5_line = {"error": "%s: %s" % (type(e).__name__, e)}
     cairo_line = None
     if not args.no_cairo:
         try:
@@ -647,6 +657,8 @@ def run_gpu_sharded(args):
         }
         if c3_line is not None:
             line["c3_one_column"] = c3_line
+        if c5_line is not None:
+            line["c5_fri"] = c5_line
         if cairo_line is not None:
             line["cairo_prove"] = cairo_line
         print(json.dumps(line))
@@ -698,6 +710,67 @@ def c3_sharded_bench(ctx, args, world, rank, barrier, dist):
             "ms": ms, "ms_all": [round(x, 2) for x in times], "elems_per_s": n * blowup / (ms * 1e-3), "root": root.hex(),
             "stages_ms_rank0": {k: round(v, 3) for k, v in stages.items()},
             "parity_ok": None if golden is None else root.hex() == golden["root"]}
+
+
+def c5_sharded_bench(ctx, args, world, rank, barrier, dist):
+    """BASELINE config C5 on N GPUs: fri_commit_phase from the 2^(log_n+2) coset evaluations of a seeded polynomial (row blocks,
+    pairwise fold exchange, collapse to one GPU at 2^19: fri_distributed.py) + grinding split over the GPUs; every root, the last
+    value and the nonce are checked against the answers the CPU oracle pinned offline."""
+    import torch
+
+    import lambdaworks_cairo_prover_b200 as P
+    from lambdaworks_cairo_prover_b200 import _native as N, felt, distributed as D, fri_distributed as F
+    from lambdaworks_cairo_prover_b200.cairo_distributed import GpuCairoBackend, _dev_tensor
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from util import random_felts
+    log_n = args.c5_log_n
+    golden = golden_case("c5" if log_n == 22 else "c5_small" if log_n == 16 else "")
+    blowup, grind = (golden["blowup"], golden["grinding_factor"]) if golden else (4, 20)
+    seed = golden["seed"] if golden else 0xC500
+    n = 1 << log_n
+    m = n * blowup
+    # layer 0 (not timed): the LDE of the polynomial on every rank, of which the rank keeps its block of rows
+    commit, _ = P.lde_and_commit([P.Polynomial(random_felts(seed, n))], P.Domain(n, P.ProofOptions(blowup, 3, OFFSET, 1)), ctx)
+    rows = m // world
+    lde = _dev_tensor(N.lib().s252_commit_device_lde(commit.handle), m * 4, torch.device("cuda", torch.cuda.current_device())).view(m, 4)
+    p0_block = lde[rank * rows:(rank + 1) * rows].clone()
+    ctx.synchronize()
+    commit.free()
+    ctx.trim()
+    be = GpuCairoBackend(ctx)
+    times, result = [], None
+    with D.backend_scope(be):
+        for it in range(2 + 3):
+            t = P.DefaultTranscript()
+            t.append(bytes(32))
+            blk = p0_block.clone()
+            ctx.synchronize()
+            torch.cuda.synchronize()
+            barrier()
+            t0 = time.perf_counter()
+            fri = F.fri_commit_phase_sharded(blk, m, log_n, t, OFFSET, be, None)
+            nonce = F.generate_nonce_with_grinding_sharded(t.challenge(), grind, be, None)
+            ctx.synchronize()
+            barrier()
+            if it >= 2:
+                times.append((time.perf_counter() - t0) * 1e3)
+            result = ([r.hex() for r in fri.roots], felt.to_bytes_be(fri.last_value).hex(), int(nonce), fri.tail_first)
+            fri.free(be)
+    ms = float(np.median(times))
+    tt = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms = float(tt.item())
+    del p0_block, lde
+    ctx.trim()
+    torch.cuda.empty_cache()
+    ok = None
+    if golden is not None:
+        ok = result[0] == golden["roots"] and result[1] == golden["last_value"] and result[2] == golden["nonce"]
+    return {"workload": "C5: fri_commit_phase from 2^%d evaluations (%d layers, blowup %d) + grinding %d, ONE phase on %d GPU(s): row-block "
+                        "layer trees, pairwise half-layer exchange per fold, collapse to one GPU at 2^19" % (log_n + 2, log_n, blowup, grind, world),
+            "ms": ms, "ms_all": [round(x, 2) for x in times], "sharded_layers": result[3], "last_root": result[0][-1], "nonce": result[2],
+            "parity_ok": ok}
 
 
 def cairo_prove_sharded_bench(ctx, args, world, rank, barrier, dist):
@@ -877,6 +950,7 @@ def main():
                          "one independent trace per GPU (weak scaling)")
     ap.add_argument("--c4-log-n", type=int, default=C4_LOG_N, help="trace length exponent of the sharded C4 commit")
     ap.add_argument("--pipeline-groups", type=int, default=4, help="sharded mode: column groups per rank of the LDE -> exchange pipeline")
+    ap.add_argument("--c5-log-n", type=int, default=22, help="sharded mode: FRI commit phase from 2^(this+2) evaluations (0 = skip; 22 and 16 are pinned)")
     ap.add_argument("--c3-log-n", type=int, default=24, help="sharded mode: rows (log2) of the one-column C3 commit (0 = skip; 24 and 26 are pinned)")
     ap.add_argument("--fib-n-large", type=int, default=280000, help="sharded mode: the longer fibonacci program (0 = skip)")
     args = ap.parse_args()

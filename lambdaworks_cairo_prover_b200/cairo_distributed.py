@@ -355,7 +355,9 @@ def _prove_sharded(trace, options, be, group, timings, exchange, fri_collapse_lo
                     aux_in[x - 19:y - 19].copy_(tr[x - tlo:y - tlo])
         if world > 1:
             dist.broadcast(aux_in[a - 19:z_ - 19], src=gr(owner), group=group)
+    mark("aux_inputs")
     aux_cols = _all_ranks_ok(lambda: be.aux_trace(trace, aux_in, rap), be, group)
+    mark("aux_build")
 
     def aux_lde(lo, hi):
         return be.cols_lde(aux_cols[lo:hi], options)

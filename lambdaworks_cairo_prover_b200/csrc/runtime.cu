@@ -302,6 +302,15 @@ extern "C" int s252_device_alloc(s252_ctx* ctx, size_t bytes, void** out) {
     return S252_OK;
 }
 extern "C" int s252_device_free(s252_ctx* ctx, void* ptr) {
+    if (!ctx) return S252_ERR_INVALID;
+    if (!ptr) return S252_OK;
+    // buffers the library handed out from its arena (s252_cairo_aux_trace_device, ..) go back to the arena: reuse is ordered on the
+    // context's stream, so neither a synchronisation nor a cudaFree (a device-wide barrier, milliseconds for a GB) is needed
+    if (ctx->arena_size.find(ptr) != ctx->arena_size.end()) {
+        dfree(ctx, ptr);
+        return S252_OK;
+    }
+    CU(ctx, cudaSetDevice(ctx->device));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     CU(ctx, cudaFree(ptr));
     return S252_OK;
