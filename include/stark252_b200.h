@@ -145,6 +145,46 @@ int s252_commit_device_columns(s252_ctx *ctx, const void *cols, size_t col_strid
  * roots of all GPUs device to device). */
 int s252_commit_device_columns_inplace(s252_ctx *ctx, const void *cols, size_t col_stride, size_t n_cols, size_t n_rows,
                                        s252_commit **out, uint8_t root[32]);
+/* ---- ONE trace committed by the GPUs of one box -----------------------------------------------
+ * interpolate_and_commit (src/starks/prover.rs:126-159) with the columns of the trace sharded over G GPUs: one process or
+ * thread per GPU, each with its own s252_ctx; the entry points below are COLLECTIVE (every rank calls them with the same shape
+ * arguments, in the same order).  NCCL is called from inside the library (bound at run time: dlopen of libnccl.so.2, or the
+ * name in S252_NCCL_LIB), so a Rust/C caller needs no Python and no torch.  Rank r owns the contiguous column range
+ * [r*c/G + min(r, c%G), ..) (33 columns over 8 ranks: 5,4,4,4,4,4,4,4 -- SURVEY.md 8d config C4); after the call it holds the
+ * coefficients + LDE of its columns for ALL rows and ALL columns for its block of n_rows*blowup/G LDE rows with the Merkle
+ * subtree over them; the top log2(G) levels are replicated.  G must be a power of two. */
+#define S252_COMM_ID_BYTES 128
+#define S252_MAX_PIPELINE_GROUPS 16
+typedef struct s252_comm s252_comm;                      /* one rank's end of a communicator */
+typedef struct s252_sharded_commit s252_sharded_commit;  /* what one rank holds after a sharded commit */
+/* Rank 0 creates an id (ncclGetUniqueId) and hands it to the other ranks by any means; every rank then joins. */
+int s252_comm_unique_id(uint8_t id[S252_COMM_ID_BYTES]);
+int s252_comm_create(s252_ctx *ctx, const uint8_t id[S252_COMM_ID_BYTES], int rank, int world, s252_comm **out);
+void s252_comm_destroy(s252_comm *comm);
+int s252_comm_rank(const s252_comm *comm);
+int s252_comm_world(const s252_comm *comm);
+/* group_tables[g]: row-major TraceTable [n_rows][group_cols[g]] (LW elements; `mem` = S252_HOST or S252_DEVICE) holding pipeline
+ * group g of this rank's columns -- the groups, in order, are the rank's column range.  The exchange of group g (one ncclSend per
+ * column and destination straight out of the LDE buffer, one ncclRecv per column and source straight into the row block) runs on
+ * a second stream under the upload + transforms of group g+1.  root: the Merkle root of the whole table, the same on every
+ * rank and equal to s252_interpolate_and_commit's on one GPU. */
+int s252_interpolate_and_commit_sharded(s252_ctx *ctx, s252_comm *comm, const s252_fe *const *group_tables, const size_t *group_cols,
+                                        size_t n_groups, size_t n_rows, size_t n_cols_total, size_t blowup, uint64_t coset_offset,
+                                        int mem, s252_sharded_commit **out, uint8_t root[32]);
+void s252_sharded_commit_destroy(s252_sharded_commit *sc);
+size_t s252_sharded_commit_n_rows(const s252_sharded_commit *sc);   /* LDE rows of the whole table */
+size_t s252_sharded_commit_n_cols(const s252_sharded_commit *sc);   /* columns of the whole table */
+/* This rank's columns (coefficients + LDE over all rows), one handle per pipeline group; borrowed, freed with the sharded commit. */
+size_t s252_sharded_commit_n_local(const s252_sharded_commit *sc);
+s252_commit *s252_sharded_commit_local(const s252_sharded_commit *sc, size_t group);
+/* All columns over this rank's row block + the subtree (borrowed). */
+s252_commit *s252_sharded_commit_block(const s252_sharded_commit *sc);
+/* MerkleTree::get_proof_by_pos + the opened rows for global positions (open_deep_composition_poly, prover.rs:484-529), on every
+ * rank: rows_out [n_idx][n_cols] LW, paths_out [n_idx][log2(n_rows)][32] leaf -> root.  The owner of a row serves its values and
+ * the subtree part of the path (one all-reduce of a packed buffer), the top levels are replicated.  S252_ERR_RANGE if a position
+ * is out of range (reference: None). */
+int s252_sharded_commit_open(s252_sharded_commit *sc, const uint64_t *indices, size_t n_idx, s252_fe *rows_out, uint8_t *paths_out);
+
 /* Round 2 (src/starks/prover.rs:254-276): evaluate_polynomial_on_lde_domain for each of n_polys
  * polynomials (polys: n_polys x n_coeffs, polynomial-major; n_coeffs <= domain_size) and
  * batch_commit over the zipped rows. */

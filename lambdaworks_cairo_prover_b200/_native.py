@@ -57,6 +57,19 @@ SIGNATURES = {
     "s252_commit_read_lde": (_i, [_vp, _sz, _sz, _sz, _vp]),
     "s252_commit_read_coeffs": (_i, [_vp, _sz, _vp]),
     "s252_commit_read_nodes": (_i, [_vp, _sz, _sz, _vp]),
+    "s252_comm_unique_id": (_i, [_vp]),
+    "s252_comm_create": (_i, [_vp, _vp, _i, _i, C.POINTER(_vp)]),
+    "s252_comm_destroy": (None, [_vp]),
+    "s252_comm_rank": (_i, [_vp]),
+    "s252_comm_world": (_i, [_vp]),
+    "s252_interpolate_and_commit_sharded": (_i, [_vp, _vp, _vp, _vp, _sz, _sz, _sz, _sz, _u64, _i, C.POINTER(_vp), _vp]),
+    "s252_sharded_commit_destroy": (None, [_vp]),
+    "s252_sharded_commit_n_rows": (_sz, [_vp]),
+    "s252_sharded_commit_n_cols": (_sz, [_vp]),
+    "s252_sharded_commit_n_local": (_sz, [_vp]),
+    "s252_sharded_commit_local": (_vp, [_vp, _sz]),
+    "s252_sharded_commit_block": (_vp, [_vp]),
+    "s252_sharded_commit_open": (_i, [_vp, _vp, _sz, _vp, _vp]),
     "s252_commit_open": (_i, [_vp, _vp, _sz, _vp, _vp]),
     "s252_commit_device_lde": (_vp, [_vp]),
     "s252_commit_device_coeffs": (_vp, [_vp]),

@@ -4,9 +4,11 @@
 // recycles the multi-GB LDE / scratch buffers of consecutive commits without going back to the
 // driver.
 #include <algorithm>
+#include <array>
 #include <cstdio>
 #include <cstdlib>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -2075,4 +2077,5 @@ extern "C" int s252_microbench_keccak(s252_ctx* ctx, double* gperms) {
 
 // --------------------------------------------------------------------------------------------
 // Cairo side (include/stark252_cairo.h)
+#include "sharded.cuh"
 #include "cairo_api.cuh"

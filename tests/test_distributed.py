@@ -129,3 +129,48 @@ def test_sharded_single_column_nccl():
         res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, OMP_NUM_THREADS="1"))
         assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
         assert "DIST_COLUMN_OK" in res.stdout
+
+
+def launch_native(world, logn, n_cols, blowup, groups, mem="host"):
+    """One plain python process per GPU running tests/dist_native_worker.py (no torch.distributed: the library calls NCCL itself)."""
+    import tempfile
+    worker = os.path.join(ROOT, "tests", "dist_native_worker.py")
+    with tempfile.TemporaryDirectory() as d:
+        idfile = os.path.join(d, "nccl_id")
+        procs = [subprocess.Popen([sys.executable, worker, str(r), str(world), str(logn), str(n_cols), str(blowup), str(groups), idfile, mem],
+                                  stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=dict(os.environ, OMP_NUM_THREADS="1"))
+                 for r in range(world)]
+        outs = []
+        for p in procs:
+            try:
+                out, _ = p.communicate(timeout=600)
+            except subprocess.TimeoutExpired:
+                for q in procs:
+                    q.kill()
+                raise
+            outs.append(out)
+        for r, (p, out) in enumerate(zip(procs, outs)):
+            assert p.returncode == 0, "rank %d:\n%s" % (r, out[-4000:])
+            assert "NATIVE_SHARDED_OK" in out
+
+
+@pytest.mark.gpu
+def test_native_sharded_commit_one_rank():
+    """s252_interpolate_and_commit_sharded / s252_sharded_commit_open with a communicator of ONE rank (runs on a single-GPU box):
+    the whole C++ path -- NCCL bound at run time, group bookkeeping, in-place subtree, top levels, packed openings -- against
+    the oracle's root, rows and paths."""
+    launch_native(1, 10, 5, 4, 2)
+    launch_native(1, 8, 3, 8, 3, mem="device")
+
+
+@pytest.mark.gpu
+def test_native_sharded_commit_nccl():
+    """The same over 2 (and 4) GPUs: column shards of unequal width, more pipeline groups than some ranks have columns."""
+    import torch
+    g = torch.cuda.device_count()
+    if g < 2:
+        pytest.skip("needs at least two GPUs")
+    launch_native(2, 10, 5, 4, 2)
+    launch_native(2, 9, 3, 8, 4, mem="device")
+    if g >= 4:
+        launch_native(4, 12, 33, 8, 3)
