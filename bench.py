@@ -560,7 +560,7 @@ def run_gpu_sharded(args):
         dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(tables, steps, warmup, profile):
+    def timed(tables, steps, warmup, profile, step=step):
         for _ in range(warmup):
             step(tables)
         barrier()
@@ -601,6 +601,44 @@ def run_gpu_sharded(args):
     if world > 1:
         dist.all_reduce(stage_t, op=dist.ReduceOp.MAX)
     golden = golden_case("c4" if log_n == C4_LOG_N else "c4_small" if log_n == 14 else "")
+    parity_ok = None if golden is None else (root.hex() == golden["root"] and root_e2e == root)
+    # ---- the same commit through the library's own collective entry point (s252_interpolate_and_commit_sharded: NCCL called from
+    # C++, no torch.distributed on the data path).  When it works it is the headline: it is the call a non-Python host makes.
+    torch_path = None
+    native_err = None
+    torch.cuda.empty_cache()                                   # the row-block buffers of the path above (torch's allocator) go back to the driver
+    try:
+        from lambdaworks_cairo_prover_b200 import sharded as S
+        uid = [S.unique_id() if rank == 0 else None]
+        if world > 1:
+            dist.broadcast_object_list(uid, src=0)
+        comm = S.Communicator(ctx, uid[0], rank, world)
+
+        def native_step(tables, timings=None):
+            if tables[0].is_cuda:
+                sc = S.interpolate_and_commit_sharded(None, n, C4_COLS, C4_BLOWUP, OFFSET, comm, device_pointers=[(t.data_ptr(), t.shape[1]) for t in tables])
+            else:
+                sc = S.interpolate_and_commit_sharded(tables, n, C4_COLS, C4_BLOWUP, OFFSET, comm)
+            r = sc.root
+            sc.free()
+            return r
+        n_ms_dev, n_wall_dev, n_root, n_prof, n_launches, n_clocks = timed(dev, args.steps, args.warmup, True, native_step)
+        n_ms_e2e, _, n_root_e2e, _, _, _ = timed(host, e2e_steps, 2, False, native_step)
+        comm.close()
+        native_ok = n_root == n_root_e2e and (golden is None or n_root.hex() == golden["root"])
+        flag = torch.tensor([1 if native_ok else 0], device="cuda", dtype=torch.int64)
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()):
+            torch_path = {"ms_per_step": ms_dev / args.steps, "e2e_ms_per_step": ms_e2e / e2e_steps, "wall_ms_per_step": wall_dev / args.steps,
+                          "gpu_launches": launches, "root": root.hex(),
+                          "how": "the same commit orchestrated from Python: torch.distributed batch_isend_irecv between C-ABI building blocks "
+                                 "(distributed.py; the path the gloo tests cover)"}
+            ms_dev, wall_dev, root, prof, launches, clocks, ms_e2e, root_e2e = n_ms_dev, n_wall_dev, n_root, n_prof, n_launches, n_clocks, n_ms_e2e, n_root_e2e
+        else:
+            native_err = "root mismatch on the C-ABI path: %s / %s" % (n_root.hex(), n_root_e2e.hex())
+    except Exception as e:                                        # keep the line: the Python-orchestrated numbers stand
+        native_err = "%s: %s" % (type(e).__name__, e)
     parity_ok = None if golden is None else (root.hex() == golden["root"] and root_e2e == root)
     c3_line = None
     if args.c3_log_n:
@@ -649,12 +687,18 @@ def run_gpu_sharded(args):
             "stages_how": "one extra step with a host wait at every mark (max over ranks): `exchange_exposed` is what is left of the all-to-all "
                           "after the LDE of the later column groups has hidden the earlier groups' transfers",
             "pipeline_groups": groups, "gpu_launches": launches, "clocks": clocks,
+            "call": ("s252_interpolate_and_commit_sharded (C ABI; NCCL called from the library, one process per GPU)" if torch_path is not None
+                     else "distributed.exchange_and_commit (torch.distributed between C-ABI building blocks)"),
             "roofline": {"bound": "int_issue", "kernel": tname, "achieved": tstat["muls"] * 80 / (tstat["ms"] * 1e-3) / 1e9 if tstat["ms"] else 0.0,
                          "peak": imad_peak, "unit": "G lane-op/s (IMAD.WIDE.U32)", "frac": kernels[tname]["imad_frac"], "traffic": None,
                          "peak_source": int_peak_src, "peak_note": PEAK_NOTE,
                          "scope": "rank 0's launches"},
             "kernels_rank0": kernels,
         }
+        if torch_path is not None:
+            line["torch_distributed_path"] = torch_path
+        if native_err is not None:
+            line["c_abi_path_error"] = native_err
         if c3_line is not None:
             line["c3_one_column"] = c3_line
         if c5_line is not None:

@@ -112,7 +112,10 @@ extern "C" int s252_comm_create(s252_ctx* ctx, const uint8_t id[S252_COMM_ID_BYT
     std::memcpy(u.internal, id, S252_COMM_ID_BYTES);
     const int r = A.CommInitRank(&c->comm, world, u, rank);
     if (r != 0) { delete c; FAIL(ctx, S252_ERR_CUDA, "ncclCommInitRank: %s", A.GetErrorString(r)); }
-    if (cudaStreamCreateWithFlags(&c->xstream, cudaStreamNonBlocking) != cudaSuccess ||
+    // highest priority: the send/receive kernels must get SM slots while the transforms of the next group fill the GPU
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (cudaStreamCreateWithPriority(&c->xstream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ready, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming) != cudaSuccess) {
         A.CommDestroy(c->comm);
@@ -190,12 +193,36 @@ extern "C" int s252_interpolate_and_commit_sharded(s252_ctx* ctx, s252_comm* com
             rounds = std::max(rounds, ng);
         }
         TRY(dalloc(ctx, &sc->block_cols, n_cols_total * rows_per));
+        // host tables: group g+1 is uploaded on the copy stream (one contiguous DMA into a staging buffer) while group g is
+        // interpolated and extended; the staging buffers come from the arena, so the copy stream first waits for whatever the
+        // compute stream still does with recycled blocks
+        struct StagingSet {
+            s252_ctx* ctx;
+            std::vector<fe*> p;
+            ~StagingSet() { for (fe* q : p) dfree(ctx, q); }
+        } staging{ctx, {}};
+        auto upload = [&](size_t g) -> int {
+            CU(ctx, cudaMemcpyAsync(staging.p[g], group_tables[g], n_rows * group_cols[g] * sizeof(fe), cudaMemcpyHostToDevice, ctx->copy_stream));
+            return S252_OK;
+        };
+        if (mem == S252_HOST) {
+            for (size_t g = 0; g < n_groups; ++g) { fe* q = nullptr; TRY(dalloc(ctx, &q, n_rows * group_cols[g])); staging.p.push_back(q); }
+            CU(ctx, cudaEventRecord(comm->ready, ctx->stream));
+            CU(ctx, cudaStreamWaitEvent(ctx->copy_stream, comm->ready, 0));
+            TRY(upload(0));
+        }
         std::vector<size_t> sent(G, 0);                            // columns of rank r's shard already exchanged
         for (size_t g = 0; g < rounds; ++g) {
             const size_t cg = g < n_groups ? group_cols[g] : 0;
             s252_commit* h = nullptr;
             if (cg) {
-                TRY(interpolate_lde_impl(ctx, group_tables[g], n_rows, cg, blowup, coset_offset, mem, false, &h, nullptr));
+                const s252_fe* table = group_tables[g];
+                if (mem == S252_HOST) {
+                    TRY(s252_copy_stream_wait(ctx));               // the transforms of group g wait for its upload ..
+                    if (g + 1 < n_groups) TRY(upload(g + 1));      // .. and run beside the next one
+                    table = reinterpret_cast<const s252_fe*>(staging.p[g]);
+                }
+                TRY(interpolate_lde_impl(ctx, table, n_rows, cg, blowup, coset_offset, S252_DEVICE, false, &h, nullptr));
                 sc->local.push_back(h);
                 sc->local_cols.push_back(cg);
                 // my own rows of these columns stay on this GPU
