@@ -133,6 +133,40 @@ def integer_peaks(ctx):
     return float(peaks.get("imad_wide_gops", 9250.0)), float(peaks.get("lop3_gops", 18500.0)), src
 
 
+_LAUNCH_AFFINITY = None
+
+
+def restore_launch_affinity():
+    """The CPU baselines run on every core the process was launched with, not on the GPU-local subset."""
+    if _LAUNCH_AFFINITY:
+        try:
+            os.sched_setaffinity(0, _LAUNCH_AFFINITY)
+        except Exception:
+            pass
+
+
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this process to the CPUs NVML reports as local to its GPU before any host table is allocated: pinned host memory then
+    sits on the GPU's NUMA node and the uploads of several ranks do not share one socket's memory controllers and inter-socket
+    link.  Returns the number of CPUs of the set (0: left as launched)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1}
+        global _LAUNCH_AFFINITY
+        _LAUNCH_AFFINITY = os.sched_getaffinity(0)
+        cpus &= _LAUNCH_AFFINITY
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -146,6 +180,7 @@ def run_gpu(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product has no CPU path)")
+    numa_cpus = bind_to_gpu_numa_node(local_rank)
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -351,6 +386,7 @@ def run_gpu(args):
                                                  "double-buffered) under the current step's S252_DEVICE calls"}},
             "gpu_launches": launches,
             "clocks": clocks,
+            "host_cpus_bound": numa_cpus,
             "roofline": {"bound": "int_issue", "kernel": tname, "achieved": tstat["muls"] * 80 / (tstat["ms"] * 1e-3) / 1e9 if tstat["ms"] else 0.0,
                          "peak": imad_peak, "unit": "G lane-op/s (IMAD.WIDE.U32)",
                          "frac": kernels[tname]["imad_frac"], "traffic": traffic,
@@ -372,6 +408,7 @@ def run_gpu(args):
         if cairo_line is not None:
             line["cairo_prove"] = cairo_line
             if not args.no_cpu_baseline and world == 1:
+                restore_launch_affinity()
                 line["cairo_prove"]["cpu_baseline"] = cpu_cairo_prove_sample(args.cpu_fib_n)
     for p in list(dev.values()) + [q for s in staging for q in s.values()]:
         ctx.device_free(p)
@@ -521,6 +558,7 @@ def run_gpu_sharded(args):
     from util import random_felts
 
     world, rank, local_rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    numa_cpus = bind_to_gpu_numa_node(local_rank)
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -686,7 +724,7 @@ def run_gpu_sharded(args):
             "stages_ms": dict(zip(("lde", "exchange_exposed", "hash", "roots"), [round(float(x), 3) for x in stage_t.tolist()])),
             "stages_how": "one extra step with a host wait at every mark (max over ranks): `exchange_exposed` is what is left of the all-to-all "
                           "after the LDE of the later column groups has hidden the earlier groups' transfers",
-            "pipeline_groups": groups, "gpu_launches": launches, "clocks": clocks,
+            "pipeline_groups": groups, "gpu_launches": launches, "clocks": clocks, "host_cpus_bound": numa_cpus,
             "call": ("s252_interpolate_and_commit_sharded (C ABI; NCCL called from the library, one process per GPU)" if torch_path is not None
                      else "distributed.exchange_and_commit (torch.distributed between C-ABI building blocks)"),
             "roofline": {"bound": "int_issue", "kernel": tname, "achieved": tstat["muls"] * 80 / (tstat["ms"] * 1e-3) / 1e9 if tstat["ms"] else 0.0,
@@ -884,6 +922,7 @@ def cpu_commit_sample(log_n, threads):
 
 
 def cpu_baseline_sample(log_n):
+    restore_launch_affinity()
     cores = os.cpu_count() or 1
     value, dt = cpu_commit_sample(log_n, cores)
     return {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "trace_rows": 1 << log_n,
