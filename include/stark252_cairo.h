@@ -135,6 +135,16 @@ int s252_cairo_constraint_evaluations(s252_ctx *ctx, const s252_cairo_trace *tra
 int s252_cairo_prove(s252_ctx *ctx, const s252_cairo_trace *trace, size_t blowup, size_t fri_number_of_queries,
                      uint64_t coset_offset, uint8_t grinding_factor, uint8_t **proof_out, size_t *proof_len);
 void s252_cairo_proof_free(uint8_t *proof);
+/* The same proof as ONE collective call over the GPUs of one box: every rank -- one process or thread per GPU, each
+ * with its own context and its end of an s252_comm (stark252_b200.h) -- calls it with the same trace and options.  Columns are
+ * sharded for the LDE, rows for the trees, the constraint evaluation, the DEEP polynomial, FRI (pairwise fold exchange, collapse
+ * to rank 0 at 2^19 evaluations) and the openings; grinding is split over the ranks; NCCL is called from the library.  Rank 0
+ * receives StarkProof::serialize bytes, byte-identical to s252_cairo_prove's; the other ranks get *proof_out = NULL.  A failure of
+ * a rank-local step (an unsatisfied AIR, say) is returned on EVERY rank.  pipeline_groups: column groups per rank whose exchange
+ * runs under the next group's upload + transforms (0 = default: 2 from 2^20 rows on, else 1). */
+int s252_cairo_prove_sharded(s252_ctx *ctx, s252_comm *comm, const s252_cairo_trace *trace, size_t blowup, size_t fri_number_of_queries,
+                             uint64_t coset_offset, uint8_t grinding_factor, size_t pipeline_groups, uint8_t **proof_out,
+                             size_t *proof_len);
 /* StarkProof::serialize (proof/stark.rs:161-218) from pieces the caller assembled (the sharded prover gathers them from several
  * GPUs): ood = the frame (2 x cols, row-major; cols = main_cols + aux_cols), hz = H1(z^2), H2(z^2); evs / ev / pas / pa as
  * s252_fri_query returns them ([Q][layers] values, [Q][layers][depth] digests, layer k uses depth - k of them); rows and paths as

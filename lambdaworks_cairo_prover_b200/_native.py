@@ -57,6 +57,7 @@ SIGNATURES = {
     "s252_commit_read_lde": (_i, [_vp, _sz, _sz, _sz, _vp]),
     "s252_commit_read_coeffs": (_i, [_vp, _sz, _vp]),
     "s252_commit_read_nodes": (_i, [_vp, _sz, _sz, _vp]),
+    "s252_cairo_prove_sharded": (_i, [_vp, _vp, _vp, _sz, _sz, _u64, C.c_uint8, _sz, C.POINTER(_vp), C.POINTER(_sz)]),
     "s252_comm_unique_id": (_i, [_vp]),
     "s252_comm_create": (_i, [_vp, _vp, _i, _i, C.POINTER(_vp)]),
     "s252_comm_destroy": (None, [_vp]),

@@ -2079,3 +2079,4 @@ extern "C" int s252_microbench_keccak(s252_ctx* ctx, double* gperms) {
 // Cairo side (include/stark252_cairo.h)
 #include "sharded.cuh"
 #include "cairo_api.cuh"
+#include "cairo_sharded.cuh"

@@ -119,3 +119,19 @@ def interpolate_and_commit_sharded(group_tables, n_rows, n_cols_total, blowup, c
     comm.ctx.check(L.s252_interpolate_and_commit_sharded(comm.ctx.handle, comm.handle, ptrs, cols, n_groups, n_rows, n_cols_total, blowup,
                                                          coset_offset, mem, C.byref(h), N.ptr(root)), N.FFTError)
     return ShardedCommitHandle(comm, h, root.tobytes())
+
+
+def generate_cairo_proof_sharded(trace, proof_options, comm, pipeline_groups=0):
+    """generate_cairo_proof (src/cairo/air.rs:1183-1190) as ONE collective call over the GPUs of `comm` (s252_cairo_prove_sharded:
+    the whole orchestration and NCCL inside the library).  trace: the same MainTrace on every rank.  Returns StarkProof::serialize
+    bytes on rank 0, None on the other ranks."""
+    out, n = C.c_void_p(), C.c_size_t()
+    comm.ctx.check(N.lib().s252_cairo_prove_sharded(comm.ctx.handle, comm.handle, trace.handle, proof_options.blowup_factor,
+                                                    proof_options.fri_number_of_queries, proof_options.coset_offset,
+                                                    proof_options.grinding_factor, pipeline_groups, C.byref(out), C.byref(n)))
+    if not out.value:
+        return None
+    try:
+        return C.string_at(out.value, n.value)
+    finally:
+        N.lib().s252_cairo_proof_free(out)

@@ -131,13 +131,16 @@ def test_sharded_single_column_nccl():
         assert "DIST_COLUMN_OK" in res.stdout
 
 
-def launch_native(world, logn, n_cols, blowup, groups, mem="host"):
-    """One plain python process per GPU running tests/dist_native_worker.py (no torch.distributed: the library calls NCCL itself)."""
+def launch_native(world, *args, worker="dist_native_worker.py", ok="NATIVE_SHARDED_OK"):
+    """One plain python process per GPU running a tests/dist_native_*worker.py (no torch.distributed: the library calls NCCL itself).
+    args: the worker's arguments between `world` and the id file (dist_native_worker: logn n_cols blowup groups [mem])."""
     import tempfile
-    worker = os.path.join(ROOT, "tests", "dist_native_worker.py")
+    worker = os.path.join(ROOT, "tests", worker)
+    args = [str(a) for a in args]
+    tail = [args.pop()] if args and args[-1] in ("host", "device") else []
     with tempfile.TemporaryDirectory() as d:
         idfile = os.path.join(d, "nccl_id")
-        procs = [subprocess.Popen([sys.executable, worker, str(r), str(world), str(logn), str(n_cols), str(blowup), str(groups), idfile, mem],
+        procs = [subprocess.Popen([sys.executable, worker, str(r), str(world)] + args + [idfile] + tail,
                                   stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=dict(os.environ, OMP_NUM_THREADS="1"))
                  for r in range(world)]
         outs = []
@@ -151,7 +154,7 @@ def launch_native(world, logn, n_cols, blowup, groups, mem="host"):
             outs.append(out)
         for r, (p, out) in enumerate(zip(procs, outs)):
             assert p.returncode == 0, "rank %d:\n%s" % (r, out[-4000:])
-            assert "NATIVE_SHARDED_OK" in out
+            assert ok in out
 
 
 @pytest.mark.gpu
@@ -160,7 +163,7 @@ def test_native_sharded_commit_one_rank():
     the whole C++ path -- NCCL bound at run time, group bookkeeping, in-place subtree, top levels, packed openings -- against
     the oracle's root, rows and paths."""
     launch_native(1, 10, 5, 4, 2)
-    launch_native(1, 8, 3, 8, 3, mem="device")
+    launch_native(1, 8, 3, 8, 3, "device")
 
 
 @pytest.mark.gpu
@@ -171,6 +174,25 @@ def test_native_sharded_commit_nccl():
     if g < 2:
         pytest.skip("needs at least two GPUs")
     launch_native(2, 10, 5, 4, 2)
-    launch_native(2, 9, 3, 8, 4, mem="device")
+    launch_native(2, 9, 3, 8, 4, "device")
     if g >= 4:
         launch_native(4, 12, 33, 8, 3)
+
+
+@pytest.mark.gpu
+def test_native_sharded_cairo_proof_one_rank():
+    """s252_cairo_prove_sharded with a communicator of ONE rank (runs on a single-GPU box): the whole C++ orchestration -- row-block
+    building blocks, halos, the packed openings, serialization -- must reproduce s252_cairo_prove's bytes."""
+    launch_native(1, 100, 4, 3, 3, 1, worker="dist_native_cairo_worker.py", ok="NATIVE_CAIRO_OK")
+
+
+@pytest.mark.gpu
+def test_native_sharded_cairo_proof_nccl():
+    """ONE Cairo proof over 2 (and 4) GPUs through the single collective C-ABI call == the single-GPU proof, byte for byte; FRI layers
+    sharded down to 32 evaluations, grinding split over the ranks."""
+    import torch
+    g = torch.cuda.device_count()
+    if g < 2:
+        pytest.skip("needs at least two GPUs")
+    launch_native(2, 100, 4, 3, 3, 1, worker="dist_native_cairo_worker.py", ok="NATIVE_CAIRO_OK")
+    launch_native(4 if g >= 4 else 2, 1000, 8, 5, 7, 6, worker="dist_native_cairo_worker.py", ok="NATIVE_CAIRO_OK")
