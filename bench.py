@@ -856,42 +856,63 @@ def c5_sharded_bench(ctx, args, world, rank, barrier, dist):
 
 
 def cairo_prove_sharded_bench(ctx, args, world, rank, barrier, dist):
-    """ONE Cairo proof on N GPUs (cairo_distributed.py): fibonacci_70000 under Provable80Bits (the options of
-    benches/criterion_prover_70k.rs) and a 4x longer trace; the proof must have the digest pinned by the CPU oracle."""
+    """ONE Cairo proof on N GPUs: fibonacci_70000 under Provable80Bits (the options of benches/criterion_prover_70k.rs) and a 4x longer
+    trace, through s252_cairo_prove_sharded -- one collective C-ABI call per rank, the whole orchestration and NCCL inside the library
+    (csrc/cairo_sharded.cuh) -- with the torch.distributed-orchestrated prover (cairo_distributed.py) beside it; the proof must have
+    the digest pinned by the CPU oracle."""
     import hashlib
 
     import lambdaworks_cairo_prover_b200 as P
-    from lambdaworks_cairo_prover_b200 import _native as N, cairo
+    from lambdaworks_cairo_prover_b200 import _native as N, cairo, sharded as S
     from lambdaworks_cairo_prover_b200.cairo_distributed import generate_cairo_proof_sharded
     out = {"metric": "cairo_fib_prove_time", "unit": "ms", "higher_is_better": False, "n_gpus": world,
+           "call": "s252_cairo_prove_sharded (C ABI: one collective call per rank, NCCL called from the library)",
            "how": "wall clock, barrier to barrier, max over ranks: the host trace table of every rank in, StarkProof::serialize bytes out on "
                   "rank 0; ONE proof sharded over the GPUs"}
     opts = P.ProofOptions.new_secure("Provable80Bits", 3)
+    uid = [S.unique_id() if rank == 0 else None]
+    if world > 1:
+        dist.broadcast_object_list(uid, src=0)
+    comm = S.Communicator(ctx, uid[0], rank, world)
     for fib_n, key in ((args.fib_n, "fib"), (args.fib_n_large, "fib_large")):
         if not fib_n:
             continue
         regs, mem, size = cairo.run_program(cairo.fibonacci_program(fib_n))
         trace = cairo.build_main_trace(regs, mem, size)
         N.lib().s252_cairo_trace_pin(trace.handle)
-        times, proof, stages = [], None, {}
+        times, proof = [], None
         for it in range(2 + min(args.steps, 5)):
             barrier()
             t0 = time.perf_counter()
-            proof = generate_cairo_proof_sharded(trace, opts, ctx)
+            proof = S.generate_cairo_proof_sharded(trace, opts, comm)
             barrier()
             if it >= 2:
                 times.append((time.perf_counter() - t0) * 1e3)
+        native_stages = json.loads(N.lib().s252_cairo_last_prove_stages().decode() or "{}")
+        py_times, py_proof, stages = [], None, {}
+        for it in range(2 + 3):
+            barrier()
+            t0 = time.perf_counter()
+            py_proof = generate_cairo_proof_sharded(trace, opts, ctx)
+            barrier()
+            if it >= 2:
+                py_times.append((time.perf_counter() - t0) * 1e3)
         generate_cairo_proof_sharded(trace, opts, ctx, timings=stages)
         golden = golden_case("fib%d_80bits" % fib_n)
         entry = {"program": "cairo0 fibonacci_%d" % fib_n, "trace_rows": trace.n_rows(), "value": float(np.median(times)),
-                 "ms_all": [round(x, 2) for x in times], "stages_ms": {k: round(v, 3) for k, v in stages.items() if not isinstance(v, dict)},
-                 "commit_detail_ms": {k: round(v, 3) for k, v in stages.get("commit_detail", {}).items()}}
+                 "ms_all": [round(x, 2) for x in times],
+                 "stages_ms_rank0_host_marks": {k: round(v, 3) for k, v in native_stages.items() if not isinstance(v, dict)},
+                 "torch_distributed_path": {"value": float(np.median(py_times)), "ms_all": [round(x, 2) for x in py_times],
+                                            "stages_ms_synchronised": {k: round(v, 3) for k, v in stages.items() if not isinstance(v, dict)},
+                                            "commit_detail_ms": {k: round(v, 3) for k, v in stages.get("commit_detail", {}).items()}}}
         if rank == 0:
             entry["proof_bytes"] = len(proof)
             entry["proof_sha256"] = hashlib.sha256(proof).hexdigest()
-            entry["parity_ok"] = None if golden is None else entry["proof_sha256"] == golden["sha256"]
+            entry["same_bytes_both_paths"] = proof == py_proof
+            entry["parity_ok"] = None if golden is None else (entry["proof_sha256"] == golden["sha256"] and proof == py_proof)
         out[key] = entry
         trace.free()
+    comm.close()
     if "fib" in out:
         out["value"] = out["fib"]["value"]
     return out
