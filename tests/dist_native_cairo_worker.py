@@ -45,6 +45,21 @@ def main():
                     len(proof), len(want), collapse, groups)
             else:
                 assert proof is None
+    # a trace that violates the AIR: H exceeds its degree bound on every rank alike -> the error comes back on EVERY rank (nobody
+    # is left waiting in a collective), and the communicator stays usable
+    import numpy as np
+    os.environ.pop("S252_FRI_COLLAPSE_LOG", None)
+    bad = np.array(trace.table).reshape(trace.n_rows(), trace.n_cols, 4).copy()
+    bad[5, 24] = bad[6, 24]
+    bad[5, 24, 3] ^= 12345
+    tb = cairo.trace_from_table(bad.reshape(-1, 4), trace.n_cols, trace.pub_inputs)
+    try:
+        S.generate_cairo_proof_sharded(tb, opts, comm)
+        raise AssertionError("an unsatisfied AIR must be refused")
+    except P.Stark252Error:
+        pass
+    proof = S.generate_cairo_proof_sharded(trace, opts, comm)
+    assert (proof == want) if rank == 0 else proof is None
     comm.close()
     ctx.close()
     print("NATIVE_CAIRO_OK rank %d of %d rows %d" % (rank, world, trace.n_rows()))
