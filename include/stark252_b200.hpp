@@ -60,6 +60,28 @@ class Context {
     s252_ctx* ctx_ = nullptr;
 };
 
+// One rank's end of a communicator over the GPUs of one box (one thread or process per GPU; NCCL is called from the library).
+// Rank 0 makes the id, every rank constructs its Communicator with it.
+using CommId = std::array<uint8_t, S252_COMM_ID_BYTES>;
+inline CommId comm_unique_id() {
+    CommId id{};
+    if (s252_comm_unique_id(id.data()) != S252_OK) throw Error(S252_ERR_CUDA, "NCCL is not available (libnccl.so.2; S252_NCCL_LIB overrides the name)");
+    return id;
+}
+class Communicator {
+  public:
+    Communicator(const Context& ctx, const CommId& id, int rank, int world) { ctx.check(s252_comm_create(ctx.raw(), id.data(), rank, world, &c_)); }
+    ~Communicator() { s252_comm_destroy(c_); }
+    Communicator(const Communicator&) = delete;
+    Communicator& operator=(const Communicator&) = delete;
+    s252_comm* raw() const { return c_; }
+    int rank() const { return s252_comm_rank(c_); }
+    int world() const { return s252_comm_world(c_); }
+
+  private:
+    s252_comm* c_ = nullptr;
+};
+
 class DefaultTranscript {                        // lambdaworks_crypto::fiat_shamir::default_transcript
   public:
     DefaultTranscript() : t_(s252_transcript_new()) {}

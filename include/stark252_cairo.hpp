@@ -83,5 +83,18 @@ inline std::vector<uint8_t> generate_cairo_proof(const Context& ctx, const MainT
     return out;
 }
 
+// The same proof as ONE collective call over the GPUs of `comm` (every rank calls it with the same trace and options):
+// StarkProof::serialize() bytes on rank 0, an empty vector on the other ranks.
+inline std::vector<uint8_t> generate_cairo_proof_sharded(const Context& ctx, const Communicator& comm, const MainTrace& trace,
+                                                         const ProofOptions& options, size_t pipeline_groups = 0) {
+    uint8_t* p = nullptr;
+    size_t n = 0;
+    ctx.check(s252_cairo_prove_sharded(ctx.raw(), comm.raw(), trace.raw(), options.blowup_factor, options.fri_number_of_queries,
+                                       options.coset_offset, options.grinding_factor, pipeline_groups, &p, &n));
+    std::vector<uint8_t> out(p, p + n);
+    if (p) s252_cairo_proof_free(p);
+    return out;
+}
+
 }  // namespace cairo
 }  // namespace stark252

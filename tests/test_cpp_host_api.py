@@ -76,3 +76,42 @@ def test_cpp_layer_matches_oracle():
     assert got["fri_last"] == "".join("%016x" % int(x) for x in last)
     assert got["fri_root3"] == roots[3].tobytes().hex()
     assert int(got["nonce"]) == O.generate_nonce_with_grinding(t.challenge(), 9)
+
+
+SHARDED_SRC = os.path.join(ROOT, "tests", "cpp", "sharded_prove_demo.cpp")
+SHARDED_EXE = os.path.join(ROOT, "tests", "cpp", "sharded_prove_demo")
+
+
+def build_sharded_demo():
+    N.lib()
+    libdir = os.path.dirname(N.library_path())
+    deps = [SHARDED_SRC, N.library_path()] + [os.path.join(ROOT, "include", h) for h in ("stark252_b200.hpp", "stark252_cairo.hpp")]
+    if not os.path.exists(SHARDED_EXE) or os.path.getmtime(SHARDED_EXE) < max(os.path.getmtime(d) for d in deps):
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-pthread", "-I", os.path.join(ROOT, "include"), SHARDED_SRC, "-o", SHARDED_EXE,
+                               "-L", libdir, "-lstark252_b200", "-Wl,-rpath," + libdir])
+    return SHARDED_EXE
+
+
+def test_cpp_sharded_demo_compiles_and_refuses_without_a_gpu():
+    """The thread-per-GPU host of s252_cairo_prove_sharded builds against the headers; without a device it exits with 2
+    (there is no CPU path)."""
+    import torch
+    exe = build_sharded_demo()
+    if not torch.cuda.is_available():
+        assert subprocess.run([exe, "1"], capture_output=True, text=True).returncode == 2
+
+
+@pytest.mark.gpu
+def test_cpp_sharded_prover_one_thread_per_gpu():
+    """One process, one thread per GPU, NCCL inside the library: the sharded proof equals the single-GPU proof (1 rank on any box,
+    2 and 4 ranks when the box has the GPUs)."""
+    import torch
+    exe = build_sharded_demo()
+    env = dict(os.environ)
+    spec = __import__("importlib.util").util.find_spec("nvidia.nccl")
+    if spec and spec.submodule_search_locations:
+        env.setdefault("S252_NCCL_LIB", os.path.join(list(spec.submodule_search_locations)[0], "lib", "libnccl.so.2"))
+    for world in [w for w in (1, 2, 4) if w <= torch.cuda.device_count()]:
+        res = subprocess.run([exe, str(world)], capture_output=True, text=True, env=env, timeout=300)
+        assert res.returncode == 0, res.stdout + res.stderr
+        assert "SHARDED_PROVE_DEMO_OK ranks %d" % world in res.stdout
