@@ -8,9 +8,11 @@
 // Arithmetic is LAZY inside kernels: values live in [0, 32p) (p < 2^252 leaves 4 spare bits),
 // fe_mul returns a value < 2p, and only stores that leave a kernel are brought to [0, p).
 //
-// fe_mul is 80 IMAD.WIDE.U32 (64 schoolbook + 16 for the sparse Montgomery reduction) plus carry
+// fe_mul is 80 32x32->64 multiply-adds (64 schoolbook + 16 for the sparse Montgomery reduction) plus carry
 // glue.  The reduction uses p = 1 (mod 2^192): with mu = -1 the Montgomery quotient of the low
-// 192 bits is just their negation, and  m*p = m + m*(2^59+17)*2^192  needs two small multipliers.
+// 192 bits is just their negation, and  m*p = m + m*(2^59+17)*2^192  needs two small multipliers.  The
+// multiplier 2^27 (limb 7 of p) is applied as funnel shifts on the ALU pipe (S252_MONT_SHIFT), which leaves
+// 72 IMAD.WIDE.U32 for the 4-cycle multiplier pipe: measured 1.6 % on the NTT passes.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -69,6 +71,9 @@ __device__ __forceinline__ void mad_row4_nc(uint32_t* acc, const uint32_t* a, ui
 //   2^256              (limb 8: +1)                        the "+1" of the 64-bit step
 //   2^384*(2^59+17)    (limbs 12,13)                      its "+p"
 // Returns (T_without_constants + multiples of p) / 2^256, a value < 2p when T < 31 p^2.
+#ifndef S252_MONT_SHIFT
+#define S252_MONT_SHIFT 1              /* the 2^27 rows of the reduction as funnel shifts: 72 instead of 80 wide multiplies (0: all 80 as IMAD.WIDE) */
+#endif
 __device__ __forceinline__ fe mont_reduce(uint32_t T[16]) {
     // Reduction step 1 (192-bit digit).  With n = ~T[0..5]:  T + (n+1)*p  has its low 192 bits
     // equal to 2^192 exactly (carry 1 -> preloaded into limb 6) and gains (n+1)*(2^59+17) at
@@ -102,6 +107,33 @@ __device__ __forceinline__ fe mont_reduce(uint32_t T[16]) {
         : "+r"(T[7]), "+r"(T[8]), "+r"(T[9]), "+r"(T[10]), "+r"(T[11]), "+r"(T[12]), "+r"(T[13]), "+r"(T[14]),
           "+r"(T[15])
         : "r"(n1), "r"(n3), "r"(n5), "r"(q0));
+#if S252_MONT_SHIFT
+    // n*q1 = n*2^27 at limb 7 is a shift: seven funnel shifts and one carry chain on the ALU pipe instead of six wide multiplies
+    // on the (4-cycle) multiplier -- they issue in its shadow
+    {
+        uint32_t x0, x1, x2, x3, x4, x5, x6;
+        asm("shl.b32 %0, %7, 27;\n\t"
+            "shf.l.clamp.b32 %1, %7,  %8,  27;\n\t"
+            "shf.l.clamp.b32 %2, %8,  %9,  27;\n\t"
+            "shf.l.clamp.b32 %3, %9,  %10, 27;\n\t"
+            "shf.l.clamp.b32 %4, %10, %11, 27;\n\t"
+            "shf.l.clamp.b32 %5, %11, %12, 27;\n\t"
+            "shr.u32 %6, %12, 5;"
+            : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3), "=r"(x4), "=r"(x5), "=r"(x6)
+            : "r"(n0), "r"(n1), "r"(n2), "r"(n3), "r"(n4), "r"(n5));
+        asm("add.cc.u32  %0, %0, %9;\n\t"
+            "addc.cc.u32 %1, %1, %10;\n\t"
+            "addc.cc.u32 %2, %2, %11;\n\t"
+            "addc.cc.u32 %3, %3, %12;\n\t"
+            "addc.cc.u32 %4, %4, %13;\n\t"
+            "addc.cc.u32 %5, %5, %14;\n\t"
+            "addc.cc.u32 %6, %6, %15;\n\t"
+            "addc.cc.u32 %7, %7, 0;\n\t"
+            "addc.u32    %8, %8, 0;"
+            : "+r"(T[7]), "+r"(T[8]), "+r"(T[9]), "+r"(T[10]), "+r"(T[11]), "+r"(T[12]), "+r"(T[13]), "+r"(T[14]), "+r"(T[15])
+            : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(x4), "r"(x5), "r"(x6));
+    }
+#else
     // {n0,n2,n4}*q1 -> limbs 7,9,11
     asm("mad.lo.cc.u32  %0, %9,  %12, %0;\n\t"
         "madc.hi.cc.u32 %1, %9,  %12, %1;\n\t"
@@ -126,9 +158,36 @@ __device__ __forceinline__ fe mont_reduce(uint32_t T[16]) {
         "addc.u32    %7, %7, 0;"
         : "+r"(T[8]), "+r"(T[9]), "+r"(T[10]), "+r"(T[11]), "+r"(T[12]), "+r"(T[13]), "+r"(T[14]), "+r"(T[15])
         : "r"(n1), "r"(n3), "r"(n5), "r"(q1));
+#endif
     // Reduction step 2 (64-bit digit): limbs 6,7 are cancelled the same way; (n'+1)*p adds
     // n'*(2^59+17) at limb 12 (the "+1" copy and the carry into limb 8 were preloaded).
     const uint32_t r0 = ~T[6], r1 = ~T[7];
+#if S252_MONT_SHIFT
+    asm("mad.lo.cc.u32  %0, %4, %5, %0;\n\t"     // r0*q0 -> 12,13
+        "madc.hi.cc.u32 %1, %4, %5, %1;\n\t"
+        "addc.cc.u32    %2, %2, 0;\n\t"
+        "addc.u32       %3, %3, 0;"
+        : "+r"(T[12]), "+r"(T[13]), "+r"(T[14]), "+r"(T[15])
+        : "r"(r0), "r"(q0));
+    asm("mad.lo.cc.u32  %0, %3, %4, %0;\n\t"     // r1*q0 -> 13,14
+        "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+        "addc.u32       %2, %2, 0;"
+        : "+r"(T[13]), "+r"(T[14]), "+r"(T[15])
+        : "r"(r1), "r"(q0));
+    {
+        uint32_t y0, y1, y2;                      // (r1:r0)*2^27 -> 13,14,15
+        asm("shl.b32 %0, %3, 27;\n\t"
+            "shf.l.clamp.b32 %1, %3, %4, 27;\n\t"
+            "shr.u32 %2, %4, 5;"
+            : "=r"(y0), "=r"(y1), "=r"(y2)
+            : "r"(r0), "r"(r1));
+        asm("add.cc.u32  %0, %0, %3;\n\t"
+            "addc.cc.u32 %1, %1, %4;\n\t"
+            "addc.u32    %2, %2, %5;"
+            : "+r"(T[13]), "+r"(T[14]), "+r"(T[15])
+            : "r"(y0), "r"(y1), "r"(y2));
+    }
+#else
     asm("mad.lo.cc.u32  %0, %4, %6, %0;\n\t"     // r0*q0 -> 12,13
         "madc.hi.cc.u32 %1, %4, %6, %1;\n\t"
         "madc.lo.cc.u32 %2, %5, %7, %2;\n\t"     // r1*q1 -> 14,15
@@ -145,6 +204,7 @@ __device__ __forceinline__ fe mont_reduce(uint32_t T[16]) {
         "addc.u32       %2, %2, 0;"
         : "+r"(T[13]), "+r"(T[14]), "+r"(T[15])
         : "r"(r0), "r"(q1));
+#endif
     fe r;
 #pragma unroll
     for (int i = 0; i < 8; ++i) r.l[i] = T[8 + i];
