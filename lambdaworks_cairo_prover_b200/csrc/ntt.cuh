@@ -123,8 +123,15 @@ __device__ __forceinline__ void bfly(fe& a, fe& b, const fe* __restrict__ tw) {
 // One radix-4 step (DIT levels lev and lev+1) over the whole tile: four elements, four butterflies, three
 // twiddle loads per work item.  FIRST_UNIT: lev == 0 of a transform without coset shift, where the level-1
 // twiddle and the first level-2 twiddle are 1 -- three of the four multiplications disappear at compile time.
+// warp_sync: the NEXT step is another radix-4 step whose four inputs per item were all written by items of the same aligned run of
+// (4 << lev) << logT <= 32 work items, i.e. by lanes of the same warp (items w = tid + k*256 keep their lane in every step): a warp
+// barrier orders those shared-memory accesses and the block barrier is skipped.
+#ifndef S252_NTT_WARP_SYNC
+#define S252_NTT_WARP_SYNC 1
+#endif
 template <bool FIRST_UNIT>
-__device__ __forceinline__ void radix4_step(const Tile& sm, const fe* __restrict__ lvl, unsigned logL, unsigned logT, unsigned lev) {
+__device__ __forceinline__ void radix4_step(const Tile& sm, const fe* __restrict__ lvl, unsigned logL, unsigned logT, unsigned lev,
+                                            bool warp_sync = false) {
     const unsigned T = 1u << logT;
     const unsigned half = 1u << lev;
     const unsigned items = (1u << (logL - 2)) << logT;
@@ -141,7 +148,7 @@ __device__ __forceinline__ void radix4_step(const Tile& sm, const fe* __restrict
         bfly<false>(x1, x3, lvl + 3 * half + jj);
         sm.st(e0, x0); sm.st(e0 + es, x1); sm.st(e0 + 2 * es, x2); sm.st(e0 + 3 * es, x3);
     }
-    __syncthreads();
+    if (warp_sync) __syncwarp(); else __syncthreads();
 }
 
 // All levels of a size-L DIT transform on every one of the T sequences held in the tile (input
@@ -152,13 +159,15 @@ __device__ __forceinline__ void block_dit(const Tile& sm, const fe* __restrict__
                                           bool first_unit) {
     const unsigned T = 1u << logT;
     unsigned lev = 0;
+    // a step may end in a warp barrier when another radix-4 step follows (lev + 3 < logL) and its producers sit in the same warp
+    auto weak = [&](unsigned l) { return S252_NTT_WARP_SYNC && l + 3 < logL && (((4u << l) << logT) <= 32u); };
     if (logL >= 2) {
-        if (first_unit) radix4_step<true>(sm, lvl, logL, logT, 0);
-        else radix4_step<false>(sm, lvl, logL, logT, 0);
+        if (first_unit) radix4_step<true>(sm, lvl, logL, logT, 0, weak(0));
+        else radix4_step<false>(sm, lvl, logL, logT, 0, weak(0));
         lev = 2;
     }
 #pragma unroll 1
-    for (; lev + 1 < logL; lev += 2) radix4_step<false>(sm, lvl, logL, logT, lev);
+    for (; lev + 1 < logL; lev += 2) radix4_step<false>(sm, lvl, logL, logT, lev, weak(lev));
     if (lev < logL) {   // odd number of levels: one radix-2 level remains
         const unsigned half = 1u << lev;
         const unsigned items = (1u << (logL - 1)) << logT;
