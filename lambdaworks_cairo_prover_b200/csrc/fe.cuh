@@ -79,7 +79,10 @@ __device__ __forceinline__ fe mont_reduce(uint32_t T[16]) {
     // equal to 2^192 exactly (carry 1 -> preloaded into limb 6) and gains (n+1)*(2^59+17) at
     // limb 6; the "+1" copy of (2^59+17) was preloaded too, so only n*(2^59+17) is added here.
     const uint32_t n0 = ~T[0], n1 = ~T[1], n2 = ~T[2], n3 = ~T[3], n4 = ~T[4], n5 = ~T[5];
-    const uint32_t q0 = S252_P6, q1 = S252_P7;
+    const uint32_t q0 = S252_P6;
+#if !S252_MONT_SHIFT
+    const uint32_t q1 = S252_P7;
+#endif
     // {n0,n2,n4}*q0 -> limbs 6,8,10 ; carry ripples to limb 15
     asm("mad.lo.cc.u32  %0, %10, %13, %0;\n\t"
         "madc.hi.cc.u32 %1, %10, %13, %1;\n\t"

@@ -152,6 +152,30 @@ extern "C" void s252_sharded_commit_destroy(s252_sharded_commit* sc) {
     delete sc;
 }
 
+// rows [0, width) of `height` columns from a table with column pitch spitch into one with pitch dpitch (elements); 16 bytes per
+// thread, grid-stride.  The DMA engine's 2-D device-to-device copy runs at a fraction of HBM speed; at one or two ranks the rows a
+// rank keeps for itself are most of the table.
+__global__ void __launch_bounds__(256) copy_rows_kernel(uint4* __restrict__ dst, unsigned long long dpitch, const uint4* __restrict__ src,
+                                                        unsigned long long spitch, unsigned long long width, unsigned long long height) {
+    const unsigned long long per_col = 2 * width, total = per_col * height;       // an element is two 16-byte halves
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long c = i / per_col, r = i - c * per_col;
+        dst[c * 2 * dpitch + r] = src[c * 2 * spitch + r];
+    }
+}
+static int copy_rows(s252_ctx* ctx, fe* dst, size_t dpitch, const fe* src, size_t spitch, size_t width, size_t height) {
+    if (width == 0 || height == 0) return S252_OK;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    const unsigned long long total = 2ull * width * height;
+    const unsigned blocks = (unsigned)std::min<unsigned long long>((total + 255) / 256, (unsigned long long)sms * 16);
+    prof_begin(ctx, "copy_rows_kernel");
+    prof_work(ctx, 64.0 * width * height, 0, 0);
+    copy_rows_kernel<<<blocks, 256, 0, ctx->stream>>>(reinterpret_cast<uint4*>(dst), dpitch, reinterpret_cast<const uint4*>(src), spitch, width, height);
+    LAUNCH_CHECK(ctx);
+    return S252_OK;
+}
+
 // The tail of every row-block commit: leaves + subtree over sc->block_cols in place, subtree roots all-gathered device to device,
 // top levels on the host of every rank.
 static int sharded_finish_tree(s252_ctx* ctx, s252_comm* comm, s252_sharded_commit* sc, uint8_t root[32]) {
@@ -242,8 +266,7 @@ static int sharded_commit_core(s252_ctx* ctx, s252_comm* comm, const size_t* gro
                 sc->local.push_back(h);
                 sc->local_cols.push_back(cg);
                 // my own rows of these columns stay on this GPU
-                CU(ctx, cudaMemcpy2DAsync(sc->block_cols + (lo + sent[me]) * rows_per, rows_per * sizeof(fe), h->lde + me * rows_per, M * sizeof(fe),
-                                          rows_per * sizeof(fe), cg, cudaMemcpyDeviceToDevice, ctx->stream));
+                TRY(copy_rows(ctx, sc->block_cols + (lo + sent[me]) * rows_per, rows_per, h->lde + me * rows_per, M, rows_per, cg));
             }
             if (G > 1) {
                 // the exchange of this group starts when its LDE is complete and runs beside the next group's upload + transforms
