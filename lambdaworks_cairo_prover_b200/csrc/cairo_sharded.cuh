@@ -230,7 +230,8 @@ extern "C" int s252_cairo_prove_sharded(s252_ctx* ctx, s252_comm* comm, const s2
             ST.mark("aux_inputs");
             int rc = dalloc(ctx, &aux, c_aux * N);
             if (rc == S252_OK) rc = cairo_build_aux(ctx, aux_in.p, s252::CAIRO_PC, N, trace->pi, rap, aux);
-            TRY(sharded_all_ok(ctx, comm, rc));
+            rc = sharded_all_ok(ctx, comm, rc);
+            if (rc != S252_OK) { dfree(ctx, aux); return rc; }
         }
         ST.mark("aux_build");
         groups_of(c_aux, &wa, &lo_a);
