@@ -196,3 +196,18 @@ def test_native_sharded_cairo_proof_nccl():
         pytest.skip("needs at least two GPUs")
     launch_native(2, 100, 4, 3, 3, 1, worker="dist_native_cairo_worker.py", ok="NATIVE_CAIRO_OK")
     launch_native(4 if g >= 4 else 2, 1000, 8, 5, 7, 6, worker="dist_native_cairo_worker.py", ok="NATIVE_CAIRO_OK")
+
+
+def test_native_and_python_paths_shard_columns_alike():
+    """The C-ABI collective calls (sharded.py / csrc/sharded.cuh: shard_range) and the torch.distributed path (distributed.py:
+    column_shards) must cut a table into the same contiguous column ranges, and pipeline groups by the same rule."""
+    from lambdaworks_cairo_prover_b200 import distributed as D, sharded as S
+    for n_cols in (1, 2, 3, 18, 33, 34, 43, 52):
+        for world in (1, 2, 4, 8, 16):
+            if n_cols < world:
+                continue
+            assert [S.my_columns(n_cols, world, r) for r in range(world)] == D.column_shards(n_cols, world)
+    for width in (1, 4, 5, 9):
+        for groups in (1, 2, 3, 4):
+            g = max(1, min(groups, width))
+            assert [S.my_columns(width, g, k) for k in range(g)] == D.group_ranges(width, groups)
